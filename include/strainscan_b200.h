@@ -1,0 +1,205 @@
+/*
+ * strainscan_b200.h -- C ABI of the B200-native match+count engine for StrainScan's
+ * identification hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference has no FFI for this path: it shells out to a bundled third-party binary and
+ * re-parses its text output.  Every entry point below replaces one piece of that process/file
+ * protocol; the reference lines it stands in for are cited per function
+ * (paths relative to the StrainScan tree):
+ *
+ *   library/identify.py:73-103                      jellyfish_count()      (L1, k = 31)
+ *   library/identify_low_mem.py:67-90               jellyfish_count()      (L1, -e DBs)
+ *   library/identify_low_depth.py:46-74             jellyfish_count()      (-b 1)
+ *   library/Vote_Strain_L2_Lasso_new_sp.py:354-403  vote_strain_L2() count block (L2, k = -k)
+ *   library/identify.py:115-127                     match_node()           (per-node gather)
+ *   library/identify_strains_L2_Enet_Pscan_new_sp.py:33-49,94-134   per-strain hit statistics
+ *
+ * Semantics are those of `jellyfish count -m K --if F reads... ; jellyfish dump -c` WITHOUT -C
+ * (forward strand only, case folded, any non-ACGT byte breaks the window, zero-count records
+ * stay valid), see SURVEY.md Appendix A.3 and DESIGN.md.
+ *
+ * All functions return SS_OK (0) or an SS_ERR_* code; ss_last_error() gives the message of the
+ * calling thread's last failure.  There is NO CPU fallback: ss_init fails with SS_ERR_NO_DEVICE
+ * when no sm_100 GPU is usable.  Calls block; handles are not re-entrant (one caller at a time
+ * per ss_ctx).  No temp files are written (the reference writes temp_<uuid>.jf/.fa into cwd).
+ */
+#ifndef STRAINSCAN_B200_H
+#define STRAINSCAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_OK               0
+#define SS_ERR_NO_DEVICE    1   /* no CUDA device of compute capability 10.x */
+#define SS_ERR_CUDA         2   /* a CUDA runtime call or kernel failed */
+#define SS_ERR_IO           3   /* file open/read/inflate failure */
+#define SS_ERR_FORMAT       4   /* input is not 4-line FASTQ (wrapped FASTQ / FASTA reads are rejected) */
+#define SS_ERR_ARG          5   /* bad argument (NULL, k out of 1..32, ...) */
+#define SS_ERR_NOMEM        6
+#define SS_ERR_UNSUPPORTED  7
+
+/* per-record flag bits returned by ss_kmerset_flags() */
+#define SS_REC_IN_SET     1u    /* upper(record) has length k and is all ACGT: a key of the dump */
+#define SS_REC_IS_LAST    2u    /* no later record has the same upper-cased string (identify.py:94) */
+#define SS_REC_RAW_UPPER  4u    /* the raw record string is itself a dumped key (Vote_...:315) */
+
+typedef struct ss_ctx     ss_ctx;      /* one GPU: streams, staging buffers, scratch */
+typedef struct ss_kmerset ss_kmerset;  /* GPU-resident probe table seeded from a k-mer FASTA */
+typedef struct ss_reads   ss_reads;    /* GPU-resident FASTQ text (the read cache) */
+
+typedef struct ss_stats {
+    uint64_t text_bytes;      /* FASTQ bytes scanned */
+    uint64_t n_reads;         /* sequence lines seen */
+    uint64_t n_kmers;         /* valid k-windows probed (the unit of work) */
+    uint64_t n_hits;          /* probes that found their k-mer */
+    uint64_t n_second_probe;  /* probes that needed a second 32-byte sector */
+    double   ms_index;        /* device time: newline index + scan kernels (CUDA events) */
+    double   ms_probe;        /* device time: fused scan/encode/probe/count kernel */
+    double   ms_gather;       /* device time: slot -> record-ordinal gather */
+    double   ms_h2d;          /* device time of host->device copies issued by this call */
+    double   ms_total;        /* wall time of the call */
+    uint32_t probe_launches;  /* launches of the probe kernel inside this call */
+    uint32_t total_launches;  /* all kernel launches inside this call */
+} ss_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Bind to CUDA device `device`.  Replaces locating/spawning library/jellyfish-linux
+ * (identify.py:77, Vote_...:354). */
+int ss_init(int device, ss_ctx **ctx);
+int ss_shutdown(ss_ctx *ctx);
+const char *ss_last_error(void);
+/* Run the kernels on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) so the
+ * caller can order its own work (NCCL all-reduce, CUDA events) after them; NULL = the context's own. */
+int ss_set_stream(ss_ctx *ctx, void *stream);
+/* name (<= name_cap bytes), SM count, total memory */
+int ss_device_info(const ss_ctx *ctx, char *name, size_t name_cap, int *n_sm, uint64_t *mem_bytes);
+
+/* ---- k-mer set: replaces `--if <fasta>` seeding + the adapters' FASTA re-read --------------- */
+
+/* Load a k-mer FASTA (Tree_database/kmer.fa, Kmer_Sets_L2/Kmer_Sets/C<id>/all_kmer.fasta;
+ * records ">id\nKMER\n", record ordinal = line pair index as in identify.py:92-95) and build the
+ * open-addressing probe table in HBM.  1 <= k <= 32.  Replaces `--if` (identify.py:82,86;
+ * Vote_...:359-371) and kmer_index_dict (identify.py:90-95). */
+int ss_kmerset_from_fasta(ss_ctx *ctx, const char *path, int k, ss_kmerset **set);
+int ss_kmerset_from_text(ss_ctx *ctx, const char *text, size_t len, int k, ss_kmerset **set);
+int ss_kmerset_free(ss_kmerset *set);
+uint64_t ss_kmerset_records(const ss_kmerset *set);   /* int(len(lines)/2) */
+uint64_t ss_kmerset_distinct(const ss_kmerset *set);  /* distinct valid k-mers (= dump lines) */
+int ss_kmerset_k(const ss_kmerset *set);
+uint64_t ss_kmerset_table_bytes(const ss_kmerset *set);
+/* flags[n_records]: SS_REC_* bits.  valid_kmers of identify.py:410 = IN_SET & IS_LAST. */
+int ss_kmerset_flags(const ss_kmerset *set, uint8_t *flags);
+/* ids[n_records]: integer after '>' (all_kmer.fasta: kid, Build_kmer_sets_...:397-399); 0 if none */
+int ss_kmerset_header_ids(const ss_kmerset *set, uint64_t *ids);
+
+/* ---- reads: replaces the read-file argv / `zcat a b |` pipe --------------------------------- */
+
+/* Read (and inflate, if the name ends in .gz -- identify.py:81) the files in argv order and keep
+ * shard `shard` of `n_shards` (record-aligned byte ranges) resident in HBM.  Paired-end = two
+ * paths, concatenated exactly as the reference does (identify.py:75-76, Vote_...:367,371). */
+int ss_reads_from_files(ss_ctx *ctx, const char *const *paths, int n_paths, int shard, int n_shards,
+                        ss_reads **reads);
+/* Same from in-memory FASTQ text (each buffer = one file's uncompressed contents). */
+int ss_reads_from_host(ss_ctx *ctx, const char *const *bufs, const size_t *lens, int n_bufs,
+                       ss_reads **reads);
+/* Borrow a device buffer that already holds FASTQ text of whole records (`len` bytes).  It must
+ * be 256-byte aligned with capacity >= ss_reads_device_capacity(len); the tail is overwritten with
+ * '\n' padding.  The caller keeps ownership (e.g. a torch uint8 tensor). */
+int ss_reads_from_device(ss_ctx *ctx, void *dev_ptr, size_t len, size_t capacity, ss_reads **reads);
+size_t ss_reads_device_capacity(size_t len);
+uint64_t ss_reads_bytes(const ss_reads *reads);
+int ss_reads_free(ss_reads *reads);
+
+/* ---- match + count: replaces `jellyfish count` + `jellyfish dump -c` + the dump parse -------- */
+
+/* counts[i] (i = record ordinal, n_records entries) = number of forward-strand occurrences of
+ * upper(record i) in the reads, 0 for records that are not keys.  HOST output.
+ * Replaces identify.py:82-101 minus the dict (see strainscan_b200/identify_shim.py). */
+int ss_count(ss_ctx *ctx, const ss_kmerset *set, const ss_reads *reads, uint32_t *counts, ss_stats *stats);
+/* Same, DEVICE output (n_records uint32), left on the context's stream and synchronised before
+ * return; used for the multi-GPU sum (NCCL all-reduce by the caller) and by the reducers. */
+int ss_count_device(ss_ctx *ctx, const ss_kmerset *set, const ss_reads *reads, uint32_t *dev_counts,
+                    ss_stats *stats);
+/* End-to-end from HOST text: stages the buffers to the GPU in chunks (pinned double buffering,
+ * copy overlapped with the kernels), counts, copies the dense vector back.  `counts` may be a host
+ * or a device pointer (unified addressing decides). */
+int ss_count_host(ss_ctx *ctx, const ss_kmerset *set, const char *const *bufs, const size_t *lens,
+                  int n_bufs, uint32_t *counts, ss_stats *stats);
+/* End-to-end from files (plain or .gz), shard `shard` of `n_shards`. */
+int ss_count_files(ss_ctx *ctx, const ss_kmerset *set, const char *const *paths, int n_paths,
+                   int shard, int n_shards, uint32_t *counts, ss_stats *stats);
+
+/* L2 adapter on a dense DEVICE vector (after any cross-GPU sum): rows whose raw record is not a
+ * dumped key -> 0, count == 1 -> 0 (remove_1, Vote_...:312-322), rows ordered by kid.
+ * py_o[n_records] int64 HOST output. */
+int ss_l2_finalize(ss_ctx *ctx, const ss_kmerset *set, const uint32_t *dev_counts, int64_t *py_o);
+
+/* ---- reducers over a dense DEVICE count vector ------------------------------------------------ */
+
+/* Per-node hit statistics, match_node() for many nodes at once (identify.py:115-127):
+ * CSR node -> record ordinals (node_ptr[n_nodes+1], ordinals[node_ptr[n_nodes]], HOST arrays).
+ * Per node: length = #distinct valid ordinals, covered = #valid ordinals with count > 0,
+ * sum = their count total (before the 100x-median outlier trim, which stays on the host). */
+int ss_node_reduce(ss_ctx *ctx, const ss_kmerset *set, const uint32_t *dev_counts,
+                   const uint64_t *node_ptr, const uint32_t *ordinals, uint32_t n_nodes,
+                   uint32_t *length, uint32_t *covered, uint64_t *sum);
+
+/* Per-strain hit statistics (stat_cov / get_remainc / get_candidate_arr,
+ * identify_strains_L2_Enet_Pscan_new_sp.py:33-49,94-134) on the CSC form of all_strains_re.npz:
+ * col_ptr[n_strains+1], rows[nnz] (HOST), y = py_o (HOST int64, n_rows), row_mask (HOST uint8,
+ * n_rows, may be NULL = all rows).  Per strain: total = #masked rows with X=1,
+ * covered = #masked rows with X=1 and y > 1, sum = sum of y over covered rows. */
+int ss_strain_reduce(ss_ctx *ctx, const uint64_t *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                     const int64_t *y, const uint8_t *row_mask, uint64_t n_rows,
+                     uint64_t *total, uint64_t *covered, uint64_t *sum);
+
+/* ---- measurement + synthetic workload helpers (bench.py, full-size parity tests) ---------------- */
+
+/* K0: uniform-random 32-byte sector gathers over a `bytes`-sized buffer; returns useful GB/s
+ * (best of `iters`).  The denominator of the probe kernel's random-access roofline. */
+int ss_bench_random_gather(ss_ctx *ctx, uint64_t bytes, uint64_t n_probes, int iters, double *gbps);
+
+/* Counter-based synthetic pan-genome (strainscan_b200/csrc/ss_synth.cuh): a heap-ordered binary
+ * cluster search tree over n_leaves clusters; every genome block belongs to one ancestor of the
+ * leaf, so its k-mers are specific to that node, as Build_tree.py's node k-mer sets are. */
+#define SS_SYNTH_MAX_SOURCES 8
+typedef struct ss_synth_params {
+    uint64_t seed;
+    uint32_t n_leaves;       /* clusters */
+    uint32_t genome_len;     /* bases per cluster genome */
+    uint32_t block_len;      /* ownership granularity */
+    uint32_t k;
+    uint32_t read_len;
+    uint32_t header_len;     /* bytes of the '@' header line without its newline */
+    uint32_t n_sources;      /* strains the reads are drawn from (<= SS_SYNTH_MAX_SOURCES) */
+    uint32_t source_leaf[SS_SYNTH_MAX_SOURCES];    /* cluster index 0..n_leaves-1 */
+    uint32_t source_strain[SS_SYNTH_MAX_SOURCES];  /* strain index inside the cluster */
+    uint32_t source_cum[SS_SYNTH_MAX_SOURCES];     /* cumulative abundance scaled to 2^32-1 */
+    uint32_t p_offtarget;    /* P(read is random sequence outside the DB) x 2^32 */
+    uint32_t p_sub;          /* per-base substitution probability x 2^32 */
+    uint32_t p_n;            /* per-base N probability x 2^32 */
+    uint32_t snp_rate;       /* per-base strain SNP probability x 2^32 */
+} ss_synth_params;
+
+/* bytes of one synthetic FASTQ record / one synthetic k-mer FASTA record */
+size_t ss_synth_read_record_bytes(const ss_synth_params *p);
+size_t ss_synth_db_record_bytes(const ss_synth_params *p);
+/* Write reads [first_read, first_read + n_reads) as 4-line FASTQ into DEVICE memory. */
+int ss_synth_reads_device(ss_ctx *ctx, const ss_synth_params *p, void *dev_text, uint64_t n_reads,
+                          uint64_t first_read);
+/* Write the synthetic Tree_database/kmer.fa (both strands as separate records, shuffled by an affine
+ * permutation) into HOST memory: node_sizes[n_nodes] records per node (even numbers; n_nodes =
+ * 2*n_leaves-1).  text_out must hold sum(node_sizes) * ss_synth_db_record_bytes(); node_of_record
+ * (may be NULL) receives the owner node of every record, i.e. the content of kmers/<node>. */
+int ss_synth_db_host(ss_ctx *ctx, const ss_synth_params *p, const uint32_t *node_sizes, uint32_t n_nodes,
+                     char *text_out, uint32_t *node_of_record);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

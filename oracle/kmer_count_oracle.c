@@ -52,13 +52,12 @@ static void init_code(void) {
 
 /* ---- seeded set: open addressing over the packed k-mer (first base most significant) */
 typedef struct {
-    uint64_t *keys;   /* EMPTY = all ones */
+    uint64_t *keys;
     uint64_t *cnt;
+    uint8_t  *used;   /* every 64-bit value is a legal key at k = 32 (poly-T = all ones), so occupancy is separate */
     uint64_t  cap;    /* power of two */
     uint64_t  n;
 } kset;
-
-#define EMPTY (~(uint64_t)0)
 
 static uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
@@ -71,12 +70,12 @@ static int kset_init(kset *s, uint64_t expect) {
     while (cap < expect * 2 + 16) cap <<= 1;
     s->keys = (uint64_t *)malloc(cap * sizeof(uint64_t));
     s->cnt = (uint64_t *)calloc(cap, sizeof(uint64_t));
-    if (!s->keys || !s->cnt) return -1;
-    memset(s->keys, 0xff, cap * sizeof(uint64_t));
+    s->used = (uint8_t *)calloc(cap, 1);
+    if (!s->keys || !s->cnt || !s->used) return -1;
     s->cap = cap; s->n = 0;
     return 0;
 }
-static void kset_free(kset *s) { free(s->keys); free(s->cnt); }
+static void kset_free(kset *s) { free(s->keys); free(s->cnt); free(s->used); }
 
 static int kset_grow(kset *s);
 
@@ -84,21 +83,21 @@ static int kset_grow(kset *s);
 static int kset_seed(kset *s, uint64_t key) {
     if ((s->n + 1) * 2 > s->cap) { if (kset_grow(s)) return -1; }
     uint64_t m = s->cap - 1, h = mix64(key) & m;
-    while (s->keys[h] != EMPTY) {
+    while (s->used[h]) {
         if (s->keys[h] == key) return 0;
         h = (h + 1) & m;
     }
-    s->keys[h] = key; s->n++;
+    s->keys[h] = key; s->used[h] = 1; s->n++;
     return 0;
 }
 static int kset_grow(kset *s) {
     kset t;
     if (kset_init(&t, s->cap)) return -1;       /* doubles */
     for (uint64_t i = 0; i < s->cap; i++)
-        if (s->keys[i] != EMPTY) {
+        if (s->used[i]) {
             uint64_t m = t.cap - 1, h = mix64(s->keys[i]) & m;
-            while (t.keys[h] != EMPTY) h = (h + 1) & m;
-            t.keys[h] = s->keys[i]; t.cnt[h] = s->cnt[i]; t.n++;
+            while (t.used[h]) h = (h + 1) & m;
+            t.keys[h] = s->keys[i]; t.cnt[h] = s->cnt[i]; t.used[h] = 1; t.n++;
         }
     kset_free(s);
     *s = t;
@@ -107,7 +106,7 @@ static int kset_grow(kset *s) {
 /* returns slot or -1 */
 static int64_t kset_find(const kset *s, uint64_t key) {
     uint64_t m = s->cap - 1, h = mix64(key) & m;
-    while (s->keys[h] != EMPTY) {
+    while (s->used[h]) {
         if (s->keys[h] == key) return (int64_t)h;
         h = (h + 1) & m;
     }

@@ -1,0 +1,969 @@
+// ss_api.cu -- host side of the C ABI (include/strainscan_b200.h): context, k-mer FASTA loader and
+// table build, FASTQ ingest (plain / gz, sharding, chunked streaming), count drivers, reducers.
+//
+// Replaces the process/file protocol around library/jellyfish-linux at
+//   library/identify.py:73-103, library/identify_low_mem.py:67-90, library/identify_low_depth.py:46-74,
+//   library/Vote_Strain_L2_Lasso_new_sp.py:354-403.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ss_common.cuh"
+#include "ss_kernels.cuh"
+#include "ss_synth.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void ss_set_error(const std::string &msg) { g_err = msg; }
+int ss_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    return SS_ERR_CUDA;
+}
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+extern "C" const char *ss_last_error(void) { return g_err.c_str(); }
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+#define SS_CHUNK_BYTES (64ull << 20)   // streaming chunk of FASTQ text (host -> device)
+
+struct ss_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
+    unsigned long long *d_stats = nullptr;   // [0..3] kmers, hits, second, reads; [4] first bad byte
+    unsigned long long *h_stats = nullptr;   // pinned mirror
+    uint32_t *d_dense = nullptr;             // scratch dense vector for host-output counts
+    uint64_t dense_cap = 0;
+    // streaming (ss_count_host / ss_count_files)
+    uint8_t *d_chunk[2] = {nullptr, nullptr};
+    uint32_t *d_chunk_line[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint8_t *h_pinned[2] = {nullptr, nullptr};   // staging for pageable sources
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+};
+
+struct ss_kmerset {
+    ss_ctx *ctx = nullptr;
+    int k = 0;
+    uint64_t n_records = 0, n_distinct = 0, n_buckets = 0;
+    ss_bucket *d_buckets = nullptr;
+    uint32_t *d_slot_cnt = nullptr;   // 4*n_buckets + 1
+    uint32_t *d_slot_of = nullptr;    // n_records
+    uint8_t *d_flags = nullptr;       // n_records
+    uint32_t *d_row_of = nullptr;     // n_records or null (kid order == ordinal order)
+    std::vector<uint8_t> flags;
+    std::vector<uint64_t> header_ids;
+    int has_ones = 0;
+    ss_table_view view() const {
+        ss_table_view v;
+        v.buckets = d_buckets; v.slot_cnt = d_slot_cnt; v.n_buckets = n_buckets;
+        v.kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+        v.vmask = (k == 32) ? ~0u : ((1u << k) - 1u);
+        v.k = k; v.has_ones = has_ones;
+        return v;
+    }
+};
+
+struct ss_reads {
+    ss_ctx *ctx = nullptr;
+    uint8_t *d_text = nullptr;
+    uint64_t len = 0;
+    uint32_t n_tiles = 0;
+    uint32_t *d_tile_line = nullptr;
+    bool owns_text = false;
+};
+
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int ss_init(int device, ss_ctx **out) {
+    if (!out) return fail(SS_ERR_ARG, "ss_init: ctx is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SS_ERR_NO_DEVICE, std::string("ss_init: no CUDA device (") + cudaGetErrorString(e) +
+                                          "); this engine has no CPU fallback");
+    if (device < 0 || device >= n) return fail(SS_ERR_ARG, "ss_init: device index out of range");
+    ss_ctx *c = new ss_ctx();
+    c->device = device;
+    SS_CUDA(cudaSetDevice(device));
+    SS_CUDA(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major != 10) {
+        std::string m = std::string("ss_init: device '") + c->prop.name + "' is sm_" + std::to_string(c->prop.major) +
+                        std::to_string(c->prop.minor) + "; kernels are built for sm_100a only (no fallback)";
+        delete c;
+        return fail(SS_ERR_NO_DEVICE, m);
+    }
+    c->n_sm = c->prop.multiProcessorCount;
+    SS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    SS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SS_CUDA(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    SS_CUDA(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
+    SS_CUDA(cudaEventCreate(&c->ev_a)); SS_CUDA(cudaEventCreate(&c->ev_b));
+    SS_CUDA(cudaEventCreate(&c->ev_c)); SS_CUDA(cudaEventCreate(&c->ev_d));
+    for (int i = 0; i < 2; i++) {
+        SS_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return SS_OK;
+}
+
+extern "C" int ss_shutdown(ss_ctx *c) {
+    if (!c) return SS_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_chunk[i]); cudaFree(c->d_chunk_line[i]);
+        if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
+        cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]);
+    }
+    cudaFree(c->d_dense); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
+    cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d);
+    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return SS_OK;
+}
+
+extern "C" int ss_set_stream(ss_ctx *c, void *stream) {
+    if (!c) return fail(SS_ERR_ARG, "ss_set_stream: ctx is NULL");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    return SS_OK;
+}
+
+extern "C" int ss_device_info(const ss_ctx *c, char *name, size_t cap, int *n_sm, uint64_t *mem) {
+    if (!c) return fail(SS_ERR_ARG, "ss_device_info: ctx is NULL");
+    if (name && cap) { strncpy(name, c->prop.name, cap - 1); name[cap - 1] = 0; }
+    if (n_sm) *n_sm = c->n_sm;
+    if (mem) *mem = c->prop.totalGlobalMem;
+    return SS_OK;
+}
+
+static int ensure_dense(ss_ctx *c, uint64_t n) {
+    if (n <= c->dense_cap) return SS_OK;
+    cudaFree(c->d_dense); c->d_dense = nullptr; c->dense_cap = 0;
+    SS_CUDA(cudaMalloc(&c->d_dense, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+    c->dense_cap = n;
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// file helpers
+// ---------------------------------------------------------------------------------------------
+static bool ends_with_gz(const char *path) {   // identify.py:81: re.split('\.', path)[-1] == 'gz'
+    const char *dot = strrchr(path, '.');
+    return dot && strcmp(dot + 1, "gz") == 0;
+}
+
+static int read_file(const char *path, std::vector<char> &out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(SS_ERR_IO, std::string("cannot open ") + path);
+    unsigned char magic[2] = {0, 0};
+    size_t got = fread(magic, 1, 2, f);
+    bool gz = ends_with_gz(path) || (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
+    if (!gz) {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        size_t base = out.size();
+        out.resize(base + (size_t)sz);
+        size_t rd = sz ? fread(out.data() + base, 1, (size_t)sz, f) : 0;
+        fclose(f);
+        if (rd != (size_t)sz) return fail(SS_ERR_IO, std::string("short read on ") + path);
+        return SS_OK;
+    }
+    fclose(f);
+    gzFile g = gzopen(path, "rb");   // handles concatenated members, like zcat
+    if (!g) return fail(SS_ERR_IO, std::string("cannot gzopen ") + path);
+    gzbuffer(g, 1 << 20);
+    const size_t step = 16u << 20;
+    while (true) {
+        size_t base = out.size();
+        out.resize(base + step);
+        int n = gzread(g, out.data() + base, (unsigned)step);
+        if (n < 0) {
+            int en = 0;
+            std::string m = std::string("inflate failed on ") + path + ": " + gzerror(g, &en);
+            gzclose(g);
+            return fail(SS_ERR_IO, m);
+        }
+        out.resize(base + (size_t)n);
+        if ((size_t)n < step) break;
+    }
+    gzclose(g);
+    return SS_OK;
+}
+
+// length of buf without trailing blank lines / whitespace
+static size_t trim_tail(const char *buf, size_t len) {
+    while (len > 0 && (buf[len - 1] == '\n' || buf[len - 1] == '\r' || buf[len - 1] == ' ' || buf[len - 1] == '\t'))
+        len--;
+    return len;
+}
+
+// first byte >= from that starts a FASTQ record: a line opening with '@' whose line+2 opens with '+'
+// (a quality line may open with '@', but then line+2 is a sequence line, never '+')
+static size_t find_record_start(const char *buf, size_t len, size_t from) {
+    if (from == 0) return 0;
+    if (from >= len) return len;
+    size_t p = from;
+    if (buf[p - 1] != '\n') {
+        const char *nl = (const char *)memchr(buf + p, '\n', len - p);
+        if (!nl) return len;
+        p = (size_t)(nl - buf) + 1;
+    }
+    while (p < len) {
+        const char *n1 = (const char *)memchr(buf + p, '\n', len - p);
+        if (!n1) return len;
+        size_t l1 = (size_t)(n1 - buf) + 1;
+        if (buf[p] == '@' && l1 < len) {
+            const char *n2 = (const char *)memchr(buf + l1, '\n', len - l1);
+            if (!n2) return len;
+            size_t l2 = (size_t)(n2 - buf) + 1;
+            if (l2 < len && buf[l2] == '+') return p;
+        }
+        p = l1;
+    }
+    return len;
+}
+
+static int check_fastq_head(const char *buf, size_t len, const char *what) {
+    if (len == 0) return SS_OK;
+    if (buf[0] == '>')
+        return fail(SS_ERR_FORMAT, std::string(what) + ": FASTA read input is not supported by the GPU path "
+                                                        "(convert to 4-line FASTQ)");
+    if (buf[0] != '@') return fail(SS_ERR_FORMAT, std::string(what) + ": not a FASTQ file (first byte is not '@')");
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-mer FASTA -> packed keys (host, threaded) -> device table
+// ---------------------------------------------------------------------------------------------
+static inline int base_code(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return -1;
+    }
+}
+
+static void parse_fasta_range(const char *text, size_t len, size_t lo, size_t hi, uint64_t line_at_lo, int k,
+                              uint64_t n_records, uint64_t *keys, uint8_t *ok, uint8_t *raw_upper,
+                              uint64_t *header_ids) {
+    size_t p = lo;
+    uint64_t line = line_at_lo;
+    if (p > 0 && text[p - 1] != '\n') {   // partial first line belongs to the previous range
+        const char *nl = (const char *)memchr(text + p, '\n', len - p);
+        if (!nl) return;
+        p = (size_t)(nl - text) + 1;
+        line++;
+    }
+    while (p < hi && p < len) {
+        const char *nl = (const char *)memchr(text + p, '\n', len - p);
+        size_t e = nl ? (size_t)(nl - text) : len;
+        uint64_t rec = line >> 1;
+        if (rec < n_records) {
+            size_t n = e - p;   // rstrip() as Python does on the record line
+            while (n > 0 && (text[p + n - 1] == ' ' || text[p + n - 1] == '\t' || text[p + n - 1] == '\r' ||
+                             text[p + n - 1] == '\v' || text[p + n - 1] == '\f'))
+                n--;
+            if ((line & 1) == 0) {
+                uint64_t id = 0;
+                bool good = n > 1 && text[p] == '>';
+                for (size_t j = 1; j < n && good; j++) {
+                    if (text[p + j] < '0' || text[p + j] > '9') good = false;
+                    else id = id * 10 + (uint64_t)(text[p + j] - '0');
+                }
+                header_ids[rec] = good ? id : 0;
+            } else {
+                uint64_t key = 0;
+                bool good = ((int)n == k), up = true;
+                for (int j = 0; j < k && good; j++) {
+                    unsigned char ch = (unsigned char)text[p + j];
+                    int c = base_code(ch);
+                    if (c < 0) { good = false; break; }
+                    if (ch >= 'a') up = false;
+                    key |= (uint64_t)c << (2 * j);   // first base in the low bits, as the kernel extracts it
+                }
+                keys[rec] = good ? key : 0;
+                ok[rec] = good ? 1 : 0;
+                raw_upper[rec] = (good && up) ? 1 : 0;
+            }
+        }
+        line++;
+        p = e + 1;
+    }
+}
+
+static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset **out) {
+    if (!c || !out) return fail(SS_ERR_ARG, "kmerset: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(SS_ERR_UNSUPPORTED, "kmerset: k must be in 1..32 (one 64-bit word per k-mer)");
+    SS_CUDA(cudaSetDevice(c->device));
+
+    // line structure (Python readlines(): a last line without '\n' still counts)
+    unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (len < (1u << 20)) T = 1;
+    std::vector<size_t> cut(T + 1);
+    for (unsigned t = 0; t <= T; t++) cut[t] = len / T * t;
+    cut[T] = len;
+    std::vector<uint64_t> nl(T, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++)
+            th.emplace_back([&, t]() {
+                uint64_t cnt = 0;
+                const char *p = text + cut[t], *e = text + cut[t + 1];
+                while (p < e) {
+                    const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+                    if (!q) break;
+                    cnt++; p = q + 1;
+                }
+                nl[t] = cnt;
+            });
+        for (auto &x : th) x.join();
+    }
+    uint64_t n_lines = 0;
+    std::vector<uint64_t> line_at(T);
+    for (unsigned t = 0; t < T; t++) { line_at[t] = n_lines; n_lines += nl[t]; }
+    if (len > 0 && text[len - 1] != '\n') n_lines++;
+    uint64_t n = n_lines / 2;
+    if (n >= 0xFFFFFFF0ull) return fail(SS_ERR_UNSUPPORTED, "kmerset: more than 2^32 records");
+
+    std::vector<uint64_t> keys(n);
+    std::vector<uint8_t> ok(n, 0), raw_upper(n, 0);
+    ss_kmerset *s = new ss_kmerset();
+    s->ctx = c; s->k = k; s->n_records = n;
+    s->header_ids.assign(n, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++)
+            th.emplace_back([&, t]() {
+                parse_fasta_range(text, len, cut[t], cut[t + 1], line_at[t], k, n, keys.data(), ok.data(),
+                                  raw_upper.data(), s->header_ids.data());
+            });
+        for (auto &x : th) x.join();
+    }
+    uint64_t n_ok = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        n_ok += ok[i];
+        if (k == 32 && ok[i] && keys[i] == SS_EMPTY) s->has_ones = 1;
+    }
+
+    // table geometry: mean SS_BUCKET_LOAD keys per 4-slot bucket (default 1.0 -> P(bucket full) ~ 2 %)
+    double load = 1.0;
+    if (const char *e = getenv("SS_BUCKET_LOAD")) { double v = atof(e); if (v > 0.05 && v <= 3.0) load = v; }
+    s->n_buckets = std::max<uint64_t>(64, (uint64_t)((double)n_ok / load) + 1);
+    if (4 * s->n_buckets + 1 >= 0xFFFFFFFFull) { delete s; return fail(SS_ERR_UNSUPPORTED, "kmerset: table too large"); }
+
+    uint64_t *d_keys = nullptr; uint8_t *d_ok = nullptr; uint32_t *d_last = nullptr;
+    unsigned long long *d_nd = nullptr;
+    const uint64_t n_slots = 4 * s->n_buckets + 1;
+    auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_ok); cudaFree(d_last); cudaFree(d_nd); };
+#define SS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ss_kmerset_free(s); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
+    SS_TRY(cudaMalloc(&s->d_buckets, s->n_buckets * sizeof(ss_bucket)));
+    SS_TRY(cudaMalloc(&s->d_slot_cnt, n_slots * sizeof(uint32_t)));
+    SS_TRY(cudaMalloc(&s->d_slot_of, std::max<uint64_t>(n, 1) * sizeof(uint32_t)));
+    SS_TRY(cudaMalloc(&s->d_flags, std::max<uint64_t>(n, 1)));
+    SS_TRY(cudaMalloc(&d_keys, std::max<uint64_t>(n, 1) * sizeof(uint64_t)));
+    SS_TRY(cudaMalloc(&d_ok, std::max<uint64_t>(n, 1)));
+    SS_TRY(cudaMalloc(&d_last, n_slots * sizeof(uint32_t)));
+    SS_TRY(cudaMalloc(&d_nd, sizeof(unsigned long long)));
+    SS_TRY(cudaMemsetAsync(s->d_buckets, 0xFF, s->n_buckets * sizeof(ss_bucket), c->stream));
+    SS_TRY(cudaMemsetAsync(s->d_slot_cnt, 0, n_slots * sizeof(uint32_t), c->stream));
+    SS_TRY(cudaMemsetAsync(d_last, 0, n_slots * sizeof(uint32_t), c->stream));
+    SS_TRY(cudaMemsetAsync(d_nd, 0, sizeof(unsigned long long), c->stream));
+    if (n) {
+        SS_TRY(cudaMemcpyAsync(d_keys, keys.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        SS_TRY(cudaMemcpyAsync(d_ok, ok.data(), n, cudaMemcpyHostToDevice, c->stream));
+        // flags start as RAW_UPPER bit only; the flags kernel adds IN_SET / IS_LAST
+        std::vector<uint8_t> f0(n);
+        for (uint64_t i = 0; i < n; i++) f0[i] = raw_upper[i] ? SS_REC_RAW_UPPER : 0;
+        SS_TRY(cudaMemcpyAsync(s->d_flags, f0.data(), n, cudaMemcpyHostToDevice, c->stream));
+        SS_TRY(cudaStreamSynchronize(c->stream));   // f0 goes out of scope
+    }
+    SS_TRY(ss_launch_insert(d_keys, d_ok, n, (unsigned long long *)s->d_buckets, s->n_buckets, s->d_slot_of, d_last,
+                            d_nd, c->stream));
+    SS_TRY(ss_launch_flags(s->d_slot_of, d_last, n, s->d_flags, c->stream));
+    s->flags.assign(n, 0);
+    unsigned long long nd = 0;
+    if (n) SS_TRY(cudaMemcpyAsync(s->flags.data(), s->d_flags, n, cudaMemcpyDeviceToHost, c->stream));
+    SS_TRY(cudaMemcpyAsync(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost, c->stream));
+    SS_TRY(cudaStreamSynchronize(c->stream));
+    s->n_distinct = nd + (s->has_ones ? 1 : 0);
+
+    // L2 row order: sorted by kid (Vote_...:386); identity when headers are 1..n in order
+    bool perm = n > 0;
+    bool ident = true;
+    for (uint64_t i = 0; i < n && perm; i++) {
+        uint64_t h = s->header_ids[i];
+        if (h < 1 || h > n) perm = false;
+        if (h != i + 1) ident = false;
+    }
+    if (perm && !ident) {
+        std::vector<uint8_t> seen(n, 0);
+        std::vector<uint32_t> row(n);
+        for (uint64_t i = 0; i < n && perm; i++) {
+            uint64_t r = s->header_ids[i] - 1;
+            if (seen[r]) perm = false;
+            seen[r] = 1; row[i] = (uint32_t)r;
+        }
+        if (perm) {
+            SS_TRY(cudaMalloc(&s->d_row_of, n * sizeof(uint32_t)));
+            SS_TRY(cudaMemcpy(s->d_row_of, row.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
+#undef SS_TRY
+    cleanup();
+    *out = s;
+    return SS_OK;
+}
+
+extern "C" int ss_kmerset_from_text(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset **out) {
+    if (!text && len) return fail(SS_ERR_ARG, "ss_kmerset_from_text: text is NULL");
+    return build_set(c, text, len, k, out);
+}
+
+extern "C" int ss_kmerset_from_fasta(ss_ctx *c, const char *path, int k, ss_kmerset **out) {
+    if (!path) return fail(SS_ERR_ARG, "ss_kmerset_from_fasta: path is NULL");
+    std::vector<char> buf;
+    int rc = read_file(path, buf);
+    if (rc) return rc;
+    return build_set(c, buf.data(), buf.size(), k, out);
+}
+
+extern "C" int ss_kmerset_free(ss_kmerset *s) {
+    if (!s) return SS_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_buckets); cudaFree(s->d_slot_cnt); cudaFree(s->d_slot_of); cudaFree(s->d_flags);
+    cudaFree(s->d_row_of);
+    delete s;
+    return SS_OK;
+}
+extern "C" uint64_t ss_kmerset_records(const ss_kmerset *s) { return s ? s->n_records : 0; }
+extern "C" uint64_t ss_kmerset_distinct(const ss_kmerset *s) { return s ? s->n_distinct : 0; }
+extern "C" int ss_kmerset_k(const ss_kmerset *s) { return s ? s->k : 0; }
+extern "C" uint64_t ss_kmerset_table_bytes(const ss_kmerset *s) {
+    return s ? s->n_buckets * sizeof(ss_bucket) + (4 * s->n_buckets + 1) * 4 + s->n_records * 5 : 0;
+}
+extern "C" int ss_kmerset_flags(const ss_kmerset *s, uint8_t *flags) {
+    if (!s || !flags) return fail(SS_ERR_ARG, "ss_kmerset_flags: NULL argument");
+    if (s->n_records) memcpy(flags, s->flags.data(), s->n_records);
+    return SS_OK;
+}
+extern "C" int ss_kmerset_header_ids(const ss_kmerset *s, uint64_t *ids) {
+    if (!s || !ids) return fail(SS_ERR_ARG, "ss_kmerset_header_ids: NULL argument");
+    if (s->n_records) memcpy(ids, s->header_ids.data(), s->n_records * sizeof(uint64_t));
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reads
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t ss_reads_device_capacity(size_t len) { return round_up(len, SS_TILE) + SS_TEXT_PAD; }
+extern "C" uint64_t ss_reads_bytes(const ss_reads *r) { return r ? r->len : 0; }
+
+extern "C" int ss_reads_free(ss_reads *r) {
+    if (!r) return SS_OK;
+    cudaSetDevice(r->ctx->device);
+    if (r->owns_text) cudaFree(r->d_text);
+    cudaFree(r->d_tile_line);
+    delete r;
+    return SS_OK;
+}
+
+// pad + index a device text buffer; line_base = line index of its first byte
+static int finish_reads(ss_ctx *c, ss_reads *r, size_t capacity) {
+    r->n_tiles = (uint32_t)((r->len + SS_TILE - 1) / SS_TILE);
+    size_t need = ss_reads_device_capacity(r->len);
+    if (capacity < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
+    SS_CUDA(cudaMemsetAsync(r->d_text + r->len, '\n', need - r->len, c->stream));
+    SS_CUDA(cudaMalloc(&r->d_tile_line, std::max<uint32_t>(r->n_tiles, 1) * sizeof(uint32_t)));
+    SS_CUDA(ss_launch_index(r->d_text, r->n_tiles, r->d_tile_line, 0, c->n_sm, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+// concatenate normalised files: each ends with exactly one '\n', no trailing blank lines
+static int gather_host_text(const char *const *bufs, const size_t *lens, int n, std::vector<char> &all) {
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += lens[i] + 1;
+    all.reserve(total);
+    for (int i = 0; i < n; i++) {
+        size_t l = trim_tail(bufs[i], lens[i]);
+        int rc = check_fastq_head(bufs[i], l, "reads");
+        if (rc) return rc;
+        if (l == 0) continue;
+        all.insert(all.end(), bufs[i], bufs[i] + l);
+        all.push_back('\n');
+    }
+    return SS_OK;
+}
+
+static int reads_from_vector(ss_ctx *c, const char *data, size_t len, ss_reads **out) {
+    ss_reads *r = new ss_reads();
+    r->ctx = c; r->len = len; r->owns_text = true;
+    size_t cap = ss_reads_device_capacity(len);
+    cudaError_t e = cudaMalloc(&r->d_text, cap);
+    if (e != cudaSuccess) { delete r; return ss_cuda_fail(e, "cudaMalloc(reads)", __FILE__, __LINE__); }
+    if (len) {
+        e = cudaMemcpyAsync(r->d_text, data, len, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { ss_reads_free(r); return ss_cuda_fail(e, "H2D reads", __FILE__, __LINE__); }
+    }
+    int rc = finish_reads(c, r, cap);
+    if (rc) { ss_reads_free(r); return rc; }
+    *out = r;
+    return SS_OK;
+}
+
+extern "C" int ss_reads_from_host(ss_ctx *c, const char *const *bufs, const size_t *lens, int n, ss_reads **out) {
+    if (!c || !out || (n > 0 && (!bufs || !lens))) return fail(SS_ERR_ARG, "ss_reads_from_host: NULL argument");
+    *out = nullptr;
+    SS_CUDA(cudaSetDevice(c->device));
+    std::vector<char> all;
+    int rc = gather_host_text(bufs, lens, n, all);
+    if (rc) return rc;
+    return reads_from_vector(c, all.data(), all.size(), out);
+}
+
+static int load_files_sharded(const char *const *paths, int n_paths, int shard, int n_shards, std::vector<char> &all,
+                              size_t &lo, size_t &hi) {
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(SS_ERR_ARG, "reads: bad shard / n_shards");
+    for (int i = 0; i < n_paths; i++) {
+        size_t base = all.size();
+        int rc = read_file(paths[i], all);
+        if (rc) return rc;
+        size_t l = trim_tail(all.data() + base, all.size() - base);
+        rc = check_fastq_head(all.data() + base, l, paths[i]);
+        if (rc) return rc;
+        all.resize(base + l);
+        if (l) all.push_back('\n');
+    }
+    size_t T = all.size();
+    lo = find_record_start(all.data(), T, (size_t)((unsigned __int128)T * shard / n_shards));
+    hi = (shard + 1 == n_shards) ? T : find_record_start(all.data(), T, (size_t)((unsigned __int128)T * (shard + 1) / n_shards));
+    return SS_OK;
+}
+
+extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
+                                   ss_reads **out) {
+    if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
+    *out = nullptr;
+    SS_CUDA(cudaSetDevice(c->device));
+    std::vector<char> all;
+    size_t lo = 0, hi = 0;
+    int rc = load_files_sharded(paths, n_paths, shard, n_shards, all, lo, hi);
+    if (rc) return rc;
+    return reads_from_vector(c, all.data() + lo, hi - lo, out);
+}
+
+extern "C" int ss_reads_from_device(ss_ctx *c, void *dev_ptr, size_t len, size_t capacity, ss_reads **out) {
+    if (!c || !out || (!dev_ptr && len)) return fail(SS_ERR_ARG, "ss_reads_from_device: NULL argument");
+    *out = nullptr;
+    if (((uintptr_t)dev_ptr & 255u) != 0) return fail(SS_ERR_ARG, "ss_reads_from_device: pointer must be 256-byte aligned");
+    SS_CUDA(cudaSetDevice(c->device));
+    ss_reads *r = new ss_reads();
+    r->ctx = c; r->d_text = (uint8_t *)dev_ptr; r->len = len; r->owns_text = false;
+    int rc = finish_reads(c, r, capacity);
+    if (rc) { ss_reads_free(r); return rc; }
+    *out = r;
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// count drivers
+// ---------------------------------------------------------------------------------------------
+static int check_format_result(ss_ctx *c, const char *what) {
+    if (c->h_stats[4] != ~0ull) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "%s: input is not 4-line FASTQ (line framing breaks at text byte %llu); wrapped FASTQ / FASTA "
+                 "reads are not supported",
+                 what, c->h_stats[4]);
+        return fail(SS_ERR_FORMAT, buf);
+    }
+    return SS_OK;
+}
+
+static int reset_pass(ss_ctx *c, const ss_kmerset *s) {
+    SS_CUDA(cudaMemsetAsync(s->d_slot_cnt, 0, (4 * s->n_buckets + 1) * sizeof(uint32_t), c->stream));
+    SS_CUDA(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    SS_CUDA(cudaMemsetAsync(c->d_stats + 4, 0xFF, sizeof(unsigned long long), c->stream));
+    return SS_OK;
+}
+
+static void fill_stats(ss_ctx *c, ss_stats *st) {
+    st->n_kmers = c->h_stats[0]; st->n_hits = c->h_stats[1];
+    st->n_second_probe = c->h_stats[2]; st->n_reads = c->h_stats[3];
+}
+
+extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *dev_counts, ss_stats *st) {
+    if (!c || !s || !r || !dev_counts) return fail(SS_ERR_ARG, "ss_count_device: NULL argument");
+    if (s->ctx != c || r->ctx != c) return fail(SS_ERR_ARG, "ss_count_device: handle belongs to another context");
+    double t0 = now_ms();
+    SS_CUDA(cudaSetDevice(c->device));
+    int rc = reset_pass(c, s);
+    if (rc) return rc;
+    SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    SS_CUDA(ss_launch_probe(r->d_text, r->len, r->n_tiles, r->d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
+                            c->n_sm, c->stream));
+    SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, dev_counts, c->stream));
+    SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
+    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    rc = check_format_result(c, "ss_count");
+    if (rc) return rc;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        fill_stats(c, st);
+        st->text_bytes = r->len;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;
+        cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
+        st->probe_launches = r->n_tiles ? 1 : 0;
+        st->total_launches = st->probe_launches + (s->n_records ? 1 : 0);
+        st->ms_total = now_ms() - t0;
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_count(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *counts, ss_stats *st) {
+    if (!c || !s || !r || !counts) return fail(SS_ERR_ARG, "ss_count: NULL argument");
+    double t0 = now_ms();
+    SS_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_dense(c, s->n_records);
+    if (rc) return rc;
+    rc = ss_count_device(c, s, r, c->d_dense, st);
+    if (rc) return rc;
+    if (s->n_records) SS_CUDA(cudaMemcpy(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (st) st->ms_total = now_ms() - t0;
+    return SS_OK;
+}
+
+static int ensure_chunks(ss_ctx *c) {
+    if (c->d_chunk[0]) return SS_OK;
+    size_t cap = ss_reads_device_capacity(SS_CHUNK_BYTES);
+    uint32_t tiles = (uint32_t)(SS_CHUNK_BYTES / SS_TILE) + 2;
+    for (int i = 0; i < 2; i++) {
+        SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
+        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], tiles * sizeof(uint32_t)));
+    }
+    return SS_OK;
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// stream `len` bytes of whole FASTQ records through the double-buffered chunk pipeline
+struct stream_state { int slot = 0; uint32_t probe_launches = 0, total_launches = 0; uint64_t bytes = 0; bool used[2] = {false, false}; };
+
+static int stream_text(ss_ctx *c, const ss_kmerset *s, const char *buf, size_t len, stream_state &ss) {
+    size_t pos = 0;
+    const bool pinned = len ? is_pinned(buf) : true;
+    while (pos < len) {
+        size_t end = pos + SS_CHUNK_BYTES >= len ? len : find_record_start(buf, len, pos + SS_CHUNK_BYTES - (1u << 16));
+        if (end > pos + SS_CHUNK_BYTES || end <= pos) return fail(SS_ERR_FORMAT, "reads: no FASTQ record boundary within 64 KiB");
+        size_t n = end - pos;
+        int b = ss.slot;
+        if (ss.used[b]) SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));   // kernels done with it
+        const char *src = buf + pos;
+        if (!pinned) {   // stage pageable memory through our own pinned buffer so the copy stays asynchronous
+            if (!c->h_pinned[b]) SS_CUDA(cudaMallocHost(&c->h_pinned[b], SS_CHUNK_BYTES));
+            if (ss.used[b]) SS_CUDA(cudaEventSynchronize(c->ev_copied[b]));
+            memcpy(c->h_pinned[b], src, n);
+            src = (const char *)c->h_pinned[b];
+        }
+        SS_CUDA(cudaMemcpyAsync(c->d_chunk[b], src, n, cudaMemcpyHostToDevice, c->copy_stream));
+        SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
+        SS_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        SS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
+        SS_CUDA(ss_launch_index(c->d_chunk[b], tiles, c->d_chunk_line[b], 0, c->n_sm, c->stream));
+        SS_CUDA(ss_launch_probe(c->d_chunk[b], n, tiles, c->d_chunk_line[b], s->view(), c->d_stats, c->d_stats + 4,
+                                c->n_sm, c->stream));
+        SS_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
+        ss.used[b] = true;
+        ss.probe_launches++; ss.total_launches += 3; ss.bytes += n;
+        ss.slot ^= 1;
+        pos = end;
+    }
+    return SS_OK;
+}
+
+static int count_streamed(ss_ctx *c, const ss_kmerset *s, const char *const *bufs, const size_t *lens, int n,
+                          uint32_t *counts, ss_stats *st) {
+    double t0 = now_ms();
+    SS_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_chunks(c);
+    if (rc) return rc;
+    rc = ensure_dense(c, s->n_records);
+    if (rc) return rc;
+    rc = reset_pass(c, s);
+    if (rc) return rc;
+    SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    stream_state ss;
+    for (int i = 0; i < n; i++) {
+        size_t l = trim_tail(bufs[i], lens[i]);
+        rc = check_fastq_head(bufs[i], l, "reads");
+        if (rc) return rc;
+        rc = stream_text(c, s, bufs[i], l, ss);   // every buffer starts a record: line index restarts at 0
+        if (rc) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); return rc; }
+    }
+    SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, c->d_dense, c->stream));
+    SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
+    if (s->n_records)
+        SS_CUDA(cudaMemcpyAsync(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
+    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    rc = check_format_result(c, "ss_count_host");
+    if (rc) return rc;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        fill_stats(c, st);
+        st->text_bytes = ss.bytes;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;   // copies + index + probe, overlapped
+        cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
+        st->probe_launches = ss.probe_launches;
+        st->total_launches = ss.total_launches + 1;
+        st->ms_total = now_ms() - t0;
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_count_host(ss_ctx *c, const ss_kmerset *s, const char *const *bufs, const size_t *lens, int n,
+                             uint32_t *counts, ss_stats *st) {
+    if (!c || !s || !counts || (n > 0 && (!bufs || !lens))) return fail(SS_ERR_ARG, "ss_count_host: NULL argument");
+    if (s->ctx != c) return fail(SS_ERR_ARG, "ss_count_host: set belongs to another context");
+    return count_streamed(c, s, bufs, lens, n, counts, st);
+}
+
+extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const *paths, int n_paths, int shard,
+                              int n_shards, uint32_t *counts, ss_stats *st) {
+    if (!c || !s || !counts || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_count_files: NULL argument");
+    if (s->ctx != c) return fail(SS_ERR_ARG, "ss_count_files: set belongs to another context");
+    std::vector<char> all;
+    size_t lo = 0, hi = 0;
+    int rc = load_files_sharded(paths, n_paths, shard, n_shards, all, lo, hi);
+    if (rc) return rc;
+    const char *b = all.data() + lo;
+    size_t l = hi - lo;
+    return count_streamed(c, s, &b, &l, 1, counts, st);
+}
+
+extern "C" int ss_l2_finalize(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, int64_t *py_o) {
+    if (!c || !s || !dev_counts || !py_o) return fail(SS_ERR_ARG, "ss_l2_finalize: NULL argument");
+    SS_CUDA(cudaSetDevice(c->device));
+    uint64_t n = s->n_records;
+    if (!n) return SS_OK;
+    long long *d = nullptr;
+    SS_CUDA(cudaMalloc(&d, n * sizeof(long long)));
+    cudaError_t e = ss_launch_l2_finalize(dev_counts, s->d_flags, s->d_row_of, n, d, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(py_o, d, n * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return ss_cuda_fail(e, "ss_l2_finalize", __FILE__, __LINE__);
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reducers
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct dev_buf {
+    T *p = nullptr;
+    ~dev_buf() { cudaFree(p); }
+    cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, std::max<uint64_t>(n, 1) * sizeof(T)); }
+};
+
+extern "C" int ss_node_reduce(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, const uint64_t *node_ptr,
+                              const uint32_t *ordinals, uint32_t n_nodes, uint32_t *length, uint32_t *covered,
+                              uint64_t *sum) {
+    if (!c || !s || !dev_counts || !node_ptr || !length || !covered || !sum)
+        return fail(SS_ERR_ARG, "ss_node_reduce: NULL argument");
+    SS_CUDA(cudaSetDevice(c->device));
+    if (n_nodes == 0) return SS_OK;
+    uint64_t nnz = node_ptr[n_nodes];
+    dev_buf<unsigned long long> d_ptr, d_sum;
+    dev_buf<uint32_t> d_ord, d_len, d_cov;
+    SS_CUDA(d_ptr.alloc(n_nodes + 1)); SS_CUDA(d_sum.alloc(n_nodes)); SS_CUDA(d_ord.alloc(nnz));
+    SS_CUDA(d_len.alloc(n_nodes)); SS_CUDA(d_cov.alloc(n_nodes));
+    SS_CUDA(cudaMemcpyAsync(d_ptr.p, node_ptr, (n_nodes + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz) SS_CUDA(cudaMemcpyAsync(d_ord.p, ordinals, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA(ss_launch_node_reduce(dev_counts, s->d_flags, d_ptr.p, d_ord.p, n_nodes, s->n_records, d_len.p, d_cov.p,
+                                  d_sum.p, c->stream));
+    SS_CUDA(cudaMemcpyAsync(length, d_len.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(covered, d_cov.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(sum, d_sum.p, n_nodes * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+extern "C" int ss_strain_reduce(ss_ctx *c, const uint64_t *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                                const int64_t *y, const uint8_t *row_mask, uint64_t n_rows, uint64_t *total,
+                                uint64_t *covered, uint64_t *sum) {
+    if (!c || !col_ptr || !y || !total || !covered || !sum) return fail(SS_ERR_ARG, "ss_strain_reduce: NULL argument");
+    SS_CUDA(cudaSetDevice(c->device));
+    if (n_strains == 0) return SS_OK;
+    uint64_t nnz = col_ptr[n_strains];
+    for (uint64_t i = 0; i < nnz; i++)
+        if (rows[i] >= n_rows) return fail(SS_ERR_ARG, "ss_strain_reduce: row index out of range");
+    dev_buf<unsigned long long> d_ptr, d_tot, d_cov, d_sum;
+    dev_buf<uint32_t> d_rows;
+    dev_buf<long long> d_y;
+    dev_buf<uint8_t> d_mask;
+    SS_CUDA(d_ptr.alloc(n_strains + 1)); SS_CUDA(d_tot.alloc(n_strains)); SS_CUDA(d_cov.alloc(n_strains));
+    SS_CUDA(d_sum.alloc(n_strains)); SS_CUDA(d_rows.alloc(nnz)); SS_CUDA(d_y.alloc(n_rows));
+    SS_CUDA(cudaMemcpyAsync(d_ptr.p, col_ptr, (n_strains + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz) SS_CUDA(cudaMemcpyAsync(d_rows.p, rows, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (n_rows) SS_CUDA(cudaMemcpyAsync(d_y.p, y, n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (row_mask) {
+        SS_CUDA(d_mask.alloc(n_rows));
+        if (n_rows) SS_CUDA(cudaMemcpyAsync(d_mask.p, row_mask, n_rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    SS_CUDA(ss_launch_strain_reduce(d_ptr.p, d_rows.p, n_strains, d_y.p, row_mask ? d_mask.p : nullptr, d_tot.p,
+                                    d_cov.p, d_sum.p, c->stream));
+    SS_CUDA(cudaMemcpyAsync(total, d_tot.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(covered, d_cov.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(sum, d_sum.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement + synthetic workload helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int ss_bench_random_gather(ss_ctx *c, uint64_t bytes, uint64_t n_probes, int iters, double *gbps) {
+    if (!c || !gbps) return fail(SS_ERR_ARG, "ss_bench_random_gather: NULL argument");
+    SS_CUDA(cudaSetDevice(c->device));
+    uint64_t n_sectors = bytes / 32;
+    if (n_sectors == 0 || n_probes == 0) return fail(SS_ERR_ARG, "ss_bench_random_gather: empty");
+    dev_buf<uint8_t> buf;
+    SS_CUDA(buf.alloc(n_sectors * 32));
+    SS_CUDA(cudaMemsetAsync(buf.p, 0x5A, n_sectors * 32, c->stream));
+    double best = 0;
+    for (int i = 0; i < iters + 1; i++) {
+        SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
+        SS_CUDA(ss_launch_random_gather(buf.p, n_sectors, n_probes, 0x1234 + 7919ull * i, c->d_stats + 5, c->n_sm, c->stream));
+        SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
+        SS_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        SS_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+        if (i > 0) best = std::max(best, (double)n_probes * 32.0 / (ms * 1e-3) / 1e9);
+    }
+    *gbps = best;
+    return SS_OK;
+}
+
+extern "C" size_t ss_synth_read_record_bytes(const ss_synth_params *p) {
+    return p ? (size_t)p->header_len + 1 + p->read_len + 1 + 2 + p->read_len + 1 : 0;
+}
+extern "C" size_t ss_synth_db_record_bytes(const ss_synth_params *p) { return p ? (size_t)p->k + 4 : 0; }
+
+static int check_synth(const ss_synth_params *p) {
+    if (!p) return fail(SS_ERR_ARG, "synth: params is NULL");
+    if (p->n_leaves < 1 || p->k < 1 || p->k > 32 || p->block_len < p->k + 1 || p->genome_len < p->block_len ||
+        p->read_len < 1 || p->read_len > p->genome_len || p->header_len < 3 || p->n_sources < 1 ||
+        p->n_sources > SS_SYNTH_MAX_SOURCES)
+        return fail(SS_ERR_ARG, "synth: bad parameters");
+    for (uint32_t i = 0; i < p->n_sources; i++)
+        if (p->source_leaf[i] >= p->n_leaves) return fail(SS_ERR_ARG, "synth: source_leaf out of range");
+    return SS_OK;
+}
+
+extern "C" int ss_synth_reads_device(ss_ctx *c, const ss_synth_params *p, void *dev_text, uint64_t n_reads,
+                                     uint64_t first_read) {
+    if (!c || !dev_text) return fail(SS_ERR_ARG, "ss_synth_reads_device: NULL argument");
+    int rc = check_synth(p);
+    if (rc) return rc;
+    SS_CUDA(cudaSetDevice(c->device));
+    SS_CUDA(ss_launch_synth_reads_impl(*p, (uint8_t *)dev_text, n_reads, first_read, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+extern "C" int ss_synth_db_host(ss_ctx *c, const ss_synth_params *p, const uint32_t *node_sizes, uint32_t n_nodes,
+                                char *text_out, uint32_t *node_of_record) {
+    if (!c || !node_sizes || !text_out) return fail(SS_ERR_ARG, "ss_synth_db_host: NULL argument");
+    int rc = check_synth(p);
+    if (rc) return rc;
+    if (n_nodes != 2 * p->n_leaves - 1) return fail(SS_ERR_ARG, "ss_synth_db_host: n_nodes must be 2*n_leaves-1");
+    SS_CUDA(cudaSetDevice(c->device));
+    // blocks grouped by owner depth
+    uint32_t maxd = ss_synth_max_depth(p->n_leaves);
+    uint32_t n_blocks = p->genome_len / p->block_len;
+    std::vector<std::vector<uint32_t>> by_depth(maxd + 1);
+    for (uint32_t b = 0; b < n_blocks; b++) by_depth[ss_synth_block_depth(p, b)].push_back(b);
+    std::vector<uint32_t> blk_list, blk_off(maxd + 2, 0);
+    for (uint32_t d = 0; d <= maxd; d++) {
+        blk_off[d] = (uint32_t)blk_list.size();
+        blk_list.insert(blk_list.end(), by_depth[d].begin(), by_depth[d].end());
+    }
+    blk_off[maxd + 1] = (uint32_t)blk_list.size();
+    std::vector<unsigned long long> node_off(n_nodes + 1, 0);
+    const uint32_t per_block = p->block_len - p->k + 1;
+    for (uint32_t v = 0; v < n_nodes; v++) {
+        uint32_t d = ss_synth_depth(v);
+        uint64_t avail = (uint64_t)by_depth[d].size() * per_block * 2;
+        if (node_sizes[v] & 1u) return fail(SS_ERR_ARG, "ss_synth_db_host: node sizes must be even (both strands)");
+        if (node_sizes[v] > avail) return fail(SS_ERR_ARG, "ss_synth_db_host: node larger than its owned blocks");
+        node_off[v + 1] = node_off[v] + node_sizes[v];
+    }
+    uint64_t N = node_off[n_nodes];
+    if (N == 0) return SS_OK;
+    if (N >= (1ull << 32)) return fail(SS_ERR_UNSUPPORTED, "ss_synth_db_host: too many records");
+    uint64_t a = (uint64_t)((double)N * 0.6180339887) | 1ull;
+    while (gcd64(a, N) != 1) a += 2;
+    ss_synth_db_plan plan;
+    dev_buf<unsigned long long> d_off;
+    dev_buf<uint32_t> d_list, d_boff, d_node;
+    dev_buf<uint8_t> d_text;
+    const uint64_t rec = p->k + 4;
+    SS_CUDA(d_off.alloc(n_nodes + 1)); SS_CUDA(d_list.alloc(blk_list.size())); SS_CUDA(d_boff.alloc(blk_off.size()));
+    SS_CUDA(d_text.alloc(N * rec));
+    if (node_of_record) SS_CUDA(d_node.alloc(N));
+    SS_CUDA(cudaMemcpy(d_off.p, node_off.data(), (n_nodes + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    SS_CUDA(cudaMemcpy(d_list.p, blk_list.data(), blk_list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    SS_CUDA(cudaMemcpy(d_boff.p, blk_off.data(), blk_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    plan.node_off = d_off.p; plan.n_nodes = n_nodes; plan.blk_list = d_list.p; plan.blk_off = d_boff.p;
+    plan.n_records = N; plan.perm_a = a; plan.perm_c = N / 3;
+    SS_CUDA(ss_launch_synth_db(*p, plan, d_text.p, node_of_record ? d_node.p : nullptr, c->stream));
+    SS_CUDA(cudaMemcpyAsync(text_out, d_text.p, N * rec, cudaMemcpyDeviceToHost, c->stream));
+    if (node_of_record)
+        SS_CUDA(cudaMemcpyAsync(node_of_record, d_node.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}

@@ -1,0 +1,35 @@
+// ss_kernels.cuh -- launch wrappers of ss_probe.cu (host side declarations) and tunables.
+#pragma once
+#include "ss_common.cuh"
+
+#ifndef SS_PROBE_UNROLL
+#define SS_PROBE_UNROLL 4        // independent 32-byte probes in flight per thread
+#endif
+#ifndef SS_PROBE_MIN_CTAS
+#define SS_PROBE_MIN_CTAS 4      // __launch_bounds__ min CTAs/SM (256 threads each)
+#endif
+
+int ss_probe_ctas_per_sm();
+
+cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *tile_line, uint32_t line_base,
+                            int n_sm, cudaStream_t st);
+cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *tile_line,
+                            const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
+                            cudaStream_t st);
+cudaError_t ss_launch_insert(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *slots,
+                             uint64_t n_buckets, uint32_t *slot_of, uint32_t *last_ord,
+                             unsigned long long *n_distinct, cudaStream_t st);
+cudaError_t ss_launch_flags(const uint32_t *slot_of, const uint32_t *last_ord, uint64_t n, uint8_t *flags,
+                            cudaStream_t st);
+cudaError_t ss_launch_gather(const uint32_t *slot_of, const uint32_t *slot_cnt, uint64_t n, uint32_t *dense,
+                             cudaStream_t st);
+cudaError_t ss_launch_l2_finalize(const uint32_t *dense, const uint8_t *flags, const uint32_t *row_of, uint64_t n,
+                                  long long *py_o, cudaStream_t st);
+cudaError_t ss_launch_node_reduce(const uint32_t *dense, const uint8_t *flags, const unsigned long long *node_ptr,
+                                  const uint32_t *ordinals, uint32_t n_nodes, uint64_t n_records, uint32_t *length,
+                                  uint32_t *covered, unsigned long long *sum, cudaStream_t st);
+cudaError_t ss_launch_strain_reduce(const unsigned long long *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                                    const long long *y, const uint8_t *row_mask, unsigned long long *total,
+                                    unsigned long long *covered, unsigned long long *sum, cudaStream_t st);
+cudaError_t ss_launch_random_gather(const void *buf, uint64_t n_sectors, uint64_t n_probes, uint64_t seed,
+                                    unsigned long long *sink, int n_sm, cudaStream_t st);

@@ -1,0 +1,581 @@
+// ss_probe.cu -- sm_100a kernels of the match+count hot path.
+//
+//   K1a ss_nl_count_kernel   newline count per text tile            (streaming HBM)
+//   K1b ss_scan_kernel       exclusive scan -> line index at each tile start
+//   K3  ss_probe_kernel      fused: TMA-staged text tile -> SWAR classify (newline / ACGT / case
+//                            fold) -> 2-bit pack + window-valid bitmap in shared memory ->
+//                            per-position k-mer extract -> one 32-byte-sector probe ->
+//                            red.global.add on the slot counter    (random HBM sectors)
+//   K2  ss_insert_kernel     open-addressing table build (CAS)
+//   K3b ss_gather_kernel     slot counters -> dense per-record vector
+//
+// What it replaces: the inside of `jellyfish count --if` (parser, rolling 2-bit encoder, hash
+// lookup, atomic add) and `jellyfish dump -c` + the Python dump parse, as invoked at
+// library/identify.py:82-101 and library/Vote_Strain_L2_Lasso_new_sp.py:357-403.
+#include "ss_common.cuh"
+#include "ss_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk TMA (cp.async.bulk -> UBLKCP), 256-bit sector load, RED
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// one probe = one 32-byte sector, read-only path, no L1 allocation (random, no reuse)
+__device__ __forceinline__ void ld_bucket(const ss_bucket *p, unsigned long long &a, unsigned long long &b,
+                                          unsigned long long &c, unsigned long long &d) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(p));
+}
+__device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// SWAR byte classification of one 32-bit word (4 text bytes)
+// ---------------------------------------------------------------------------------------------
+// 0x80 in every byte of (w ^ pat) that is NON-zero (exact, no cross-byte carries)
+__device__ __forceinline__ uint32_t nz7(uint32_t w, uint32_t pat) {
+    uint32_t v = w ^ pat;
+    return ((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v;
+}
+// bits 7,15,23,31 -> bits 0..3
+__device__ __forceinline__ uint32_t pack4(uint32_t m7) {
+    return (((m7 >> 7) & 0x01010101u) * 0x00204081u >> 21) & 0xFu;
+}
+// nl4: byte == '\n';  ok4: byte in {A,C,G,T,a,c,g,t};  c8: 2-bit codes (A0 C1 G2 T3), byte i at bits 2i
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &nl4, uint32_t &ok4, uint32_t &c8) {
+    nl4 = pack4(~nz7(w, 0x0A0A0A0Au));
+    uint32_t u = w & 0xDFDFDFDFu;   // fold case
+    uint32_t bad = nz7(u, 0x41414141u) & nz7(u, 0x43434343u) & nz7(u, 0x47474747u) & nz7(u, 0x54545454u);
+    ok4 = pack4(~bad);
+    uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+    c8 = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
+}
+
+struct run_bits { uint32_t nl, ok; uint64_t codes; };
+
+__device__ __forceinline__ run_bits classify_run(const uint8_t *smem_run) {
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(smem_run);
+    uint4 a = r4[0], b = r4[1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    run_bits r; r.nl = 0; r.ok = 0; r.codes = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t nl4, ok4, c8;
+        classify4(w[i], nl4, ok4, c8);
+        r.nl |= nl4 << (4 * i);
+        r.ok |= ok4 << (4 * i);
+        r.codes |= (uint64_t)c8 << (8 * i);
+    }
+    return r;
+}
+
+// Bits of a 32-byte run that lie on a FASTQ sequence line (line index % 4 == 1), given the line
+// index at the run's first byte and the run's newline mask.  Also checks the 4-line framing
+// ('@' opens line 0, '+' opens line 2) and counts sequence lines that end in this run.
+__device__ __forceinline__ uint32_t seq_line_mask(uint32_t nlmask, uint32_t line, const uint8_t *raw_tile,
+                                                  uint32_t run_off, uint64_t tile_gpos, uint64_t text_len,
+                                                  bool check, uint32_t &n_reads, unsigned long long *err) {
+    uint32_t seqmask = 0, start = 0, rem = nlmask;
+    while (true) {
+        uint32_t end = rem ? (uint32_t)(__ffs(rem) - 1) : 32u;
+        if ((line & 3u) == 1u) {
+            uint32_t hi = (end >= 32u) ? 0xFFFFFFFFu : ((1u << end) - 1u);
+            uint32_t lo = (1u << start) - 1u;   // start <= 31 here
+            seqmask |= hi & ~lo;
+        }
+        if (!rem) break;
+        rem &= rem - 1;
+        if (check) {
+            uint64_t gp = tile_gpos + run_off + end + 1;    // first byte of the next line
+            if ((line & 3u) == 1u && gp <= text_len) n_reads++;   // not the '\n' padding after the text
+            uint32_t nxt = (line + 1u) & 3u;
+            if (gp < text_len && (nxt == 0u || nxt == 2u)) {
+                uint8_t c = raw_tile[run_off + end + 1];    // inside tile + halo
+                if (c != (nxt == 0u ? '@' : '+')) atomicMin(err, (unsigned long long)gp);
+            }
+        }
+        line++;
+        start = end + 1;
+        if (start >= 32u) break;
+    }
+    return seqmask;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a / K1b: line index of every tile start
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SS_THREADS) ss_nl_count_kernel(const uint8_t *__restrict__ text, uint32_t n_tiles,
+                                                                   uint32_t *__restrict__ tile_nl) {
+    __shared__ uint32_t wsum[SS_THREADS / 32];
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(text + (uint64_t)t * SS_TILE);
+        // 512 x 16 B per tile: thread i takes chunks i and i + 256 (coalesced)
+        uint32_t c = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint4 v = __ldg(p + threadIdx.x + h * SS_THREADS);
+            c += __popc(~nz7(v.x, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.y, 0x0A0A0A0Au) & 0x80808080u) +
+                 __popc(~nz7(v.z, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.w, 0x0A0A0A0Au) & 0x80808080u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int i = 0; i < SS_THREADS / 32; i++) s += wsum[i];
+            tile_nl[t] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// in-place exclusive scan (single CTA, 1024 threads); out[i] = base + sum_{j<i} in[j]
+__global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v, uint32_t n, uint32_t base) {
+    __shared__ uint32_t part[1024];
+    uint32_t per = (n + 1023u) / 1024u;
+    uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += v[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t x = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += x;
+        __syncthreads();
+    }
+    uint32_t run = base + part[threadIdx.x] - s;
+    for (uint32_t i = lo; i < hi; i++) { uint32_t x = v[i]; v[i] = run; run += x; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: fused scan / encode / probe / count
+// ---------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(SS_THREADS, SS_PROBE_MIN_CTAS)
+ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_tiles,
+                const uint32_t *__restrict__ tile_line, ss_table_view tv,
+                unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
+    __shared__ __align__(128) uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];
+    __shared__ __align__(16) uint64_t s_codes[SS_NRUN + 2];
+    __shared__ uint32_t s_valid[SS_NRUN + 2];
+    __shared__ uint32_t s_wsum[SS_THREADS / 32];
+    __shared__ __align__(8) uint64_t s_full[SS_STAGES];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    constexpr uint32_t kBytes = SS_TILE + SS_HALO;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SS_STAGES; s++) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+        s_codes[SS_NRUN] = 0; s_codes[SS_NRUN + 1] = 0;
+        s_valid[SS_NRUN] = 0; s_valid[SS_NRUN + 1] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SS_STAGES; s++) {
+            uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
+            if (t < n_tiles) {
+                mbar_expect_tx(&s_full[s], kBytes);
+                tma_load_1d(raw[s], text + t * SS_TILE, kBytes, &s_full[s]);
+            }
+        }
+    }
+
+    uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0;
+
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % SS_STAGES, parity = (it / SS_STAGES) & 1u;
+        mbar_wait(&s_full[s], parity);
+        const uint8_t *rt = raw[s];
+        const uint64_t tile_gpos = tile * SS_TILE;
+
+        // ---- phase 1: classify my 32-byte run, find its line index, publish codes + valid bits
+        run_bits rb = classify_run(rt + tid * SS_RUN);
+        uint32_t c = __popc(rb.nl), inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= (uint32_t)o) inc += x;
+        }
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < SS_THREADS / 32; i++) {
+            uint32_t x = s_wsum[i];
+            if ((uint32_t)i < wid) wbase += x;
+            total += x;
+        }
+        const uint32_t line0 = tile_line[tile];
+        uint32_t line = line0 + wbase + inc - c;
+        uint32_t seqm = seq_line_mask(rb.nl, line, rt, tid * SS_RUN, tile_gpos, text_len, true, n_reads, err);
+        s_codes[tid] = rb.codes;
+        s_valid[tid] = rb.ok & seqm;
+        if (tid < 2) {   // the two halo runs
+            run_bits hb = classify_run(rt + (SS_THREADS + tid) * SS_RUN);
+            uint32_t hc = __popc(hb.nl);
+            uint32_t h0 = __shfl_sync(0x3u, hc, 0);
+            uint32_t hline = line0 + total + (tid == 1 ? h0 : 0u);
+            uint32_t dummy = 0;
+            uint32_t hm = seq_line_mask(hb.nl, hline, rt, (SS_THREADS + tid) * SS_RUN, tile_gpos, text_len, false,
+                                        dummy, err);
+            s_codes[SS_THREADS + tid] = hb.codes;
+            s_valid[SS_THREADS + tid] = hb.ok & hm;
+        }
+        __syncthreads();
+
+        // the raw stage is consumed: refill it with the tile STAGES rounds ahead
+        if (tid == 0) {
+            uint64_t nt = tile + (uint64_t)SS_STAGES * gridDim.x;
+            if (nt < n_tiles) {
+                fence_proxy_async();
+                mbar_expect_tx(&s_full[s], kBytes);
+                tma_load_1d(raw[s], text + nt * SS_TILE, kBytes, &s_full[s]);
+            }
+        }
+
+        // ---- phase 2: every window start of the tile; lanes take adjacent positions
+#pragma unroll 1
+        for (uint32_t j = 0; j < SS_TILE / SS_THREADS; j += UNROLL) {
+            unsigned long long km[UNROLL];
+            uint64_t bk[UNROLL];
+            bool ok[UNROLL];
+            unsigned long long q0[UNROLL], q1[UNROLL], q2[UNROLL], q3[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                uint32_t p = (j + u) * SS_THREADS + tid;
+                uint32_t wi = p >> 5, b = p & 31u;
+                uint32_t v = __funnelshift_r(s_valid[wi], s_valid[wi + 1], b);
+                ok[u] = (v & tv.vmask) == tv.vmask;
+                uint64_t lo = s_codes[wi], hi = s_codes[wi + 1];
+                uint32_t sh = 2u * b;
+                km[u] = ((lo >> sh) | ((hi << 1) << (63u - sh))) & tv.kmask;
+                if (tv.k == 32 && km[u] == SS_EMPTY && ok[u]) {   // poly-T 32-mer: lives outside the table
+                    n_kmers++;
+                    if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
+                    ok[u] = false;
+                }
+                bk[u] = ss_bucket_of(km[u], tv.n_buckets);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                q0[u] = q1[u] = q2[u] = q3[u] = 0ull;
+                if (ok[u]) ld_bucket(tv.buckets + bk[u], q0[u], q1[u], q2[u], q3[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (!ok[u]) continue;
+                n_kmers++;
+                uint64_t b = bk[u];
+                unsigned long long a0 = q0[u], a1 = q1[u], a2 = q2[u], a3 = q3[u];
+                while (true) {
+                    int f = (a0 == km[u]) ? 0 : (a1 == km[u]) ? 1 : (a2 == km[u]) ? 2 : (a3 == km[u]) ? 3 : -1;
+                    if (f >= 0) {
+                        red_add_u32(tv.slot_cnt + 4 * b + f, 1u);
+                        n_hits++;
+                        break;
+                    }
+                    if (a3 == SS_EMPTY || a2 == SS_EMPTY || a1 == SS_EMPTY || a0 == SS_EMPTY) break;   // miss
+                    b = (b + 1 == tv.n_buckets) ? 0 : b + 1;   // bucket full: next sector
+                    n_second++;
+                    ld_bucket(tv.buckets + b, a0, a1, a2, a3);
+                }
+            }
+        }
+        __syncthreads();   // codes/valid are rewritten by the next tile's phase 1
+    }
+
+    // ---- per-CTA statistics
+    unsigned long long st[4] = {n_kmers, n_hits, n_second, n_reads};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        unsigned long long x = st[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0 && x) atomicAdd(stats + i, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: table build.  One thread per record; CAS into the first free slot of the home bucket,
+// spilling to the next bucket when all four slots are taken.
+// ---------------------------------------------------------------------------------------------
+__global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ rec_ok, uint64_t n,
+                                 unsigned long long *__restrict__ slots, uint64_t n_buckets,
+                                 uint32_t *__restrict__ slot_of, uint32_t *__restrict__ last_ord,
+                                 unsigned long long *__restrict__ n_distinct) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!rec_ok[i]) { slot_of[i] = SS_NOSLOT; return; }
+    unsigned long long key = keys[i];
+    uint64_t slot;
+    if (key == SS_EMPTY) {                      // k = 32 poly-T
+        slot = 4 * n_buckets;               // counted as distinct by the host
+    } else {
+        uint64_t b = ss_bucket_of(key, n_buckets);
+        while (true) {
+            bool done = false;
+#pragma unroll
+            for (int j = 0; j < 4 && !done; j++) {
+                unsigned long long cur = slots[4 * b + j];
+                if (cur == SS_EMPTY) {
+                    unsigned long long old = atomicCAS(slots + 4 * b + j, SS_EMPTY, key);
+                    if (old == SS_EMPTY) { atomicAdd(n_distinct, 1ull); cur = key; }
+                    else cur = old;
+                }
+                if (cur == key) { slot = 4 * b + j; done = true; }
+            }
+            if (done) break;
+            b = (b + 1 == n_buckets) ? 0 : b + 1;
+        }
+    }
+    slot_of[i] = (uint32_t)slot;
+    atomicMax(last_ord + slot, (uint32_t)i);
+}
+
+// flags[i] |= IS_LAST where record i is the highest ordinal stored at its slot
+__global__ void ss_flags_kernel(const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ last_ord,
+                                uint64_t n, uint8_t *__restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = slot_of[i];
+    if (s == SS_NOSLOT) { flags[i] = 0; return; }
+    uint8_t f = flags[i] | SS_REC_IN_SET;
+    if (last_ord[s] == (uint32_t)i) f |= SS_REC_IS_LAST;
+    flags[i] = f;
+}
+
+// K3b: dense[i] = slot_cnt[slot_of[i]]
+__global__ void ss_gather_kernel(const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ slot_cnt,
+                                 uint64_t n, uint32_t *__restrict__ dense) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = slot_of[i];
+    dense[i] = (s == SS_NOSLOT) ? 0u : slot_cnt[s];
+}
+
+// L2 adapter: py_o[kid-1] = (raw_upper && c != 1) ? c : 0   (remove_1)
+__global__ void ss_l2_finalize_kernel(const uint32_t *__restrict__ dense, const uint8_t *__restrict__ flags,
+                                      const uint32_t *__restrict__ row_of, uint64_t n, long long *__restrict__ py_o) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = (flags[i] & SS_REC_RAW_UPPER) ? dense[i] : 0u;
+    if (c == 1u) c = 0u;
+    uint64_t r = row_of ? row_of[i] : i;
+    py_o[r] = (long long)c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: per-node reducer.  One warp per node walks its ordinal list.
+// The reference intersects a SET of ordinals with valid_kmers, so duplicates inside one node list
+// count once; the host passes de-duplicated lists (strainscan_b200/identify_shim.py).
+// ---------------------------------------------------------------------------------------------
+__global__ void ss_node_reduce_kernel(const uint32_t *__restrict__ dense, const uint8_t *__restrict__ flags,
+                                      const unsigned long long *__restrict__ node_ptr,
+                                      const uint32_t *__restrict__ ordinals, uint32_t n_nodes, uint64_t n_records,
+                                      uint32_t *__restrict__ length, uint32_t *__restrict__ covered,
+                                      unsigned long long *__restrict__ sum) {
+    uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (node >= n_nodes) return;
+    unsigned long long lo = node_ptr[node], hi = node_ptr[node + 1];
+    uint32_t len = 0, cov = 0;
+    unsigned long long s = 0;
+    for (unsigned long long i = lo + lane; i < hi; i += 32) {
+        uint32_t o = ordinals[i];
+        if (o >= n_records) continue;
+        uint8_t f = flags[o];
+        if ((f & (SS_REC_IN_SET | SS_REC_IS_LAST)) == (SS_REC_IN_SET | SS_REC_IS_LAST)) {
+            len++;
+            uint32_t c = dense[o];
+            if (c > 0) { cov++; s += c; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        len += __shfl_xor_sync(0xFFFFFFFFu, len, o);
+        cov += __shfl_xor_sync(0xFFFFFFFFu, cov, o);
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    }
+    if (lane == 0) { length[node] = len; covered[node] = cov; sum[node] = s; }
+}
+
+// K5: per-strain reducer over the CSC form of the 0/1 strain matrix.  One warp per strain column.
+__global__ void ss_strain_reduce_kernel(const unsigned long long *__restrict__ col_ptr,
+                                        const uint32_t *__restrict__ rows, uint32_t n_strains,
+                                        const long long *__restrict__ y, const uint8_t *__restrict__ row_mask,
+                                        unsigned long long *__restrict__ total,
+                                        unsigned long long *__restrict__ covered,
+                                        unsigned long long *__restrict__ sum) {
+    uint32_t col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (col >= n_strains) return;
+    unsigned long long lo = col_ptr[col], hi = col_ptr[col + 1];
+    unsigned long long t = 0, c = 0, s = 0;
+    for (unsigned long long i = lo + lane; i < hi; i += 32) {
+        uint32_t r = rows[i];
+        if (row_mask && !row_mask[r]) continue;
+        t++;
+        long long v = y[r];
+        if (v > 1) { c++; s += (unsigned long long)v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    }
+    if (lane == 0) { total[col] = t; covered[col] = c; sum[col] = s; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: random 32-byte sector gather (the roofline denominator for K3's probes)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ss_random_gather_kernel(const ss_bucket *__restrict__ buf, uint64_t n_sectors,
+                                                                uint64_t n_probes, uint64_t seed,
+                                                                unsigned long long *__restrict__ sink) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (; i + 3 * stride < n_probes; i += 4 * stride) {
+        unsigned long long a[4], b[4], c[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint64_t s = __umul64hi(ss_mix(seed + i + u * stride), n_sectors);
+            ld_bucket(buf + s, a[u], b[u], c[u], d[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc += a[u] ^ b[u] ^ c[u] ^ d[u];
+    }
+    for (; i < n_probes; i += stride) {
+        unsigned long long a, b, c, d;
+        ld_bucket(buf + __umul64hi(ss_mix(seed + i), n_sectors), a, b, c, d);
+        acc += a ^ b ^ c ^ d;
+    }
+    if (acc == 0x123456789ull) *sink = acc;   // keep the loads alive
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers (host)
+// ---------------------------------------------------------------------------------------------
+static int g_probe_ctas_per_sm = 0;
+
+int ss_probe_ctas_per_sm() {
+    if (g_probe_ctas_per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ss_probe_kernel<SS_PROBE_UNROLL>, SS_THREADS, 0) !=
+                cudaSuccess || n < 1)
+            n = 1;
+        g_probe_ctas_per_sm = n;
+    }
+    return g_probe_ctas_per_sm;
+}
+
+cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *tile_line, uint32_t line_base,
+                            int n_sm, cudaStream_t st) {
+    if (n_tiles == 0) return cudaSuccess;
+    uint32_t grid = min(n_tiles, (uint32_t)n_sm * 8u);
+    ss_nl_count_kernel<<<grid, SS_THREADS, 0, st>>>(text, n_tiles, tile_line);
+    ss_scan_kernel<<<1, 1024, 0, st>>>(tile_line, n_tiles, line_base);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *tile_line,
+                            const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
+                            cudaStream_t st) {
+    if (n_tiles == 0) return cudaSuccess;
+    uint32_t grid = min(n_tiles, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
+    ss_probe_kernel<SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, tile_line, tv, stats, err);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_insert(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *slots,
+                             uint64_t n_buckets, uint32_t *slot_of, uint32_t *last_ord,
+                             unsigned long long *n_distinct, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    ss_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, rec_ok, n, slots, n_buckets, slot_of,
+                                                                   last_ord, n_distinct);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_flags(const uint32_t *slot_of, const uint32_t *last_ord, uint64_t n, uint8_t *flags,
+                            cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    ss_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slot_of, last_ord, n, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_gather(const uint32_t *slot_of, const uint32_t *slot_cnt, uint64_t n, uint32_t *dense,
+                             cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    ss_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slot_of, slot_cnt, n, dense);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_l2_finalize(const uint32_t *dense, const uint8_t *flags, const uint32_t *row_of, uint64_t n,
+                                  long long *py_o, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    ss_l2_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dense, flags, row_of, n, py_o);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_node_reduce(const uint32_t *dense, const uint8_t *flags, const unsigned long long *node_ptr,
+                                  const uint32_t *ordinals, uint32_t n_nodes, uint64_t n_records, uint32_t *length,
+                                  uint32_t *covered, unsigned long long *sum, cudaStream_t st) {
+    if (n_nodes == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)(((uint64_t)n_nodes * 32 + 255) / 256);
+    ss_node_reduce_kernel<<<blocks, 256, 0, st>>>(dense, flags, node_ptr, ordinals, n_nodes, n_records, length,
+                                                   covered, sum);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_strain_reduce(const unsigned long long *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                                    const long long *y, const uint8_t *row_mask, unsigned long long *total,
+                                    unsigned long long *covered, unsigned long long *sum, cudaStream_t st) {
+    if (n_strains == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)(((uint64_t)n_strains * 32 + 255) / 256);
+    ss_strain_reduce_kernel<<<blocks, 256, 0, st>>>(col_ptr, rows, n_strains, y, row_mask, total, covered, sum);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_random_gather(const void *buf, uint64_t n_sectors, uint64_t n_probes, uint64_t seed,
+                                    unsigned long long *sink, int n_sm, cudaStream_t st) {
+    ss_random_gather_kernel<<<n_sm * 8, 256, 0, st>>>((const ss_bucket *)buf, n_sectors, n_probes, seed, sink);
+    return cudaGetLastError();
+}

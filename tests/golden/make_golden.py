@@ -120,6 +120,9 @@ def cases():
     g3 = rand_seq(rng, 300)
     out.append(("k32", fasta_db([g3[i:i + 32] for i in range(0, 200, 3)]), [fastq([g3[0:150], g3[100:300]])], 32, "files", 4))
     out.append(("k11", fasta_db([g3[i:i + 11] for i in range(0, 200, 3)]), [fastq([g3[0:150], g3[100:300]])], 11, "files", 4))
+    # 9b k = 32 poly-T packs to all ones in 2 bits/base: a legal key, not an empty marker
+    out.append(("polyT_k32", fasta_db(["T" * 32, "A" * 32, "T" * 31 + "G"]),
+                [fastq(["T" * 40, "A" * 33 + "T" * 31 + "G"])], 32, "files", 4))
     # 10 homopolymers / low complexity (many identical windows in one read)
     out.append(("lowcomplex", fasta_db(["A" * 31, "AC" * 15 + "A", "CA" * 15 + "C", "T" * 31]),
                 [fastq(["A" * 150, "AC" * 75, "T" * 40 + "N" + "T" * 40])], 31, "files", 8))

@@ -1,0 +1,267 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors of
+the reference's own engine.  Integer work: every comparison is bit-exact.  Run with -m gpu."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from oracle import adapters
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from strainscan_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _gold_dense(case):
+    return adapters.count_dense(case["fasta"].encode(), case["k"], [r.encode() for r in case["reads"]])
+
+
+def _supported(case):
+    return case["name"] not in ("wrapped_fastq", "fasta_reads")
+
+
+def _check_against_dump(case, got, flags):
+    """Direct check against the jellyfish dump, not via the oracle."""
+    lines = case["fasta"].split("\n")
+    for i in range(len(got)):
+        s = lines[2 * i + 1].rstrip().upper()
+        if flags[i] & 1:
+            assert case["dump"][s] == int(got[i]), (case["name"], i)
+        else:
+            assert got[i] == 0
+
+
+def test_golden_resident(eng, golden_cases):
+    for case in golden_cases:
+        if not _supported(case):
+            continue
+        ks = eng.kmerset_from_text(case["fasta"], case["k"])
+        reads = eng.reads_from_host([r.encode() for r in case["reads"]])
+        got, st = eng.count(ks, reads)
+        _check_against_dump(case, got, ks.flags)
+        d = _gold_dense(case)
+        assert np.array_equal(got.astype(np.uint64), d.cnt), case["name"]
+        assert np.array_equal(ks.flags & 1, d.in_set), case["name"]
+        assert np.array_equal((ks.flags >> 1) & 1, d.is_last), case["name"]
+        assert np.array_equal((ks.flags >> 2) & 1, d.raw_upper), case["name"]
+        assert np.array_equal(ks.header_ids, d.header_id), case["name"]
+        assert st.n_kmers == adapters.count_windows([r.encode() for r in case["reads"]], case["k"]), case["name"]
+        if case["name"] != "if_oddities":
+            assert ks.n_distinct == d.n_distinct, case["name"]
+
+
+def test_golden_streaming_host(eng, golden_cases):
+    for case in golden_cases:
+        if not _supported(case):
+            continue
+        ks = eng.kmerset_from_text(case["fasta"], case["k"])
+        got, st = eng.count_host(ks, [r.encode() for r in case["reads"]])
+        _check_against_dump(case, got, ks.flags)
+
+
+def test_golden_files_plain_and_gz(eng, golden_cases, tmp_path):
+    for case in golden_cases:
+        if not _supported(case):
+            continue
+        fa = tmp_path / ("%s.fa" % case["name"])
+        fa.write_bytes(case["fasta"].encode())
+        plain, gz = [], []
+        for i, r in enumerate(case["reads"]):
+            p = tmp_path / ("%s_%d.fq" % (case["name"], i))
+            p.write_bytes(r.encode())
+            plain.append(str(p))
+            g = tmp_path / ("%s_%d.fq.gz" % (case["name"], i))
+            with gzip.open(g, "wb") as f:
+                f.write(r.encode())
+            gz.append(str(g))
+        ks = eng.kmerset_from_fasta(str(fa), case["k"])
+        for paths in (plain, gz):
+            got, _ = eng.count_files(ks, paths)
+            _check_against_dump(case, got, ks.flags)
+            reads = eng.reads_from_files(paths)
+            got2, _ = eng.count(ks, reads)
+            assert np.array_equal(got, got2)
+
+
+def test_unsupported_inputs_fail_loudly(eng, golden_cases):
+    from strainscan_b200 import StrainScanB200Error
+    for case in golden_cases:
+        if _supported(case):
+            continue
+        ks = eng.kmerset_from_text(case["fasta"], case["k"])
+        with pytest.raises(StrainScanB200Error) as ei:
+            reads = eng.reads_from_host([r.encode() for r in case["reads"]])
+            eng.count(ks, reads)
+        assert ei.value.code == 4   # SS_ERR_FORMAT
+    with pytest.raises(StrainScanB200Error):
+        eng.kmerset_from_text(">1\nACGT\n", 33)
+    with pytest.raises(StrainScanB200Error):
+        eng.kmerset_from_fasta("/nonexistent/kmer.fa", 31)
+
+
+@pytest.mark.parametrize("k", [11, 21, 31, 32])
+def test_random_vs_oracle(eng, k):
+    rng = np.random.default_rng(1000 + k)
+    G = util.rand_genome(rng, 200_000)
+    fa = util.make_db(rng, G, k, 20_000, both_strands=True, lower_frac=0.02, junk=40)
+    fq1 = util.make_reads(rng, G, 6000, 150, var_len=False, lower_frac=0.05, offtarget=0.3)
+    fq2 = util.make_reads(rng, G, 3000, 100, var_len=True, crlf=(k == 21))
+    ks = eng.kmerset_from_text(fa, k)
+    d = adapters.count_dense(fa, k, [fq1, fq2])
+    for got, st in (eng.count(ks, eng.reads_from_host([fq1, fq2])), eng.count_host(ks, [fq1, fq2])):
+        assert np.array_equal(got.astype(np.uint64), d.cnt)
+        assert st.n_kmers == adapters.count_windows([fq1, fq2], k)
+        assert st.n_reads == 9000
+    assert np.array_equal(ks.flags & 1, d.in_set)
+    assert np.array_equal((ks.flags >> 1) & 1, d.is_last)
+    assert d.cnt.sum() > 1000
+
+
+def test_poly_t_32mer(eng):
+    """k = 32 all-T packs to 0xFFFF...F, the table's empty marker: it lives in a side slot."""
+    fa = b">1\n" + b"T" * 32 + b"\n>1\n" + b"A" * 32 + b"\n>1\n" + b"T" * 31 + b"G\n"
+    fq = b"@a\n" + b"T" * 40 + b"\n+\n" + b"I" * 40 + b"\n@b\n" + b"A" * 33 + b"T" * 31 + b"G\n+\n" + b"I" * 65 + b"\n"
+    ks = eng.kmerset_from_text(fa, 32)
+    got, _ = eng.count(ks, eng.reads_from_host(fq))
+    d = adapters.count_dense(fa, 32, [fq])
+    assert np.array_equal(got.astype(np.uint64), d.cnt) and got[0] == 9 and got[1] == 2 and got[2] == 1
+    assert ks.n_distinct == 3
+
+
+def test_empty_and_degenerate(eng):
+    ks = eng.kmerset_from_text(b">1\nACGTACGTACGTACGTACGTACGTACGTACG\n", 31)
+    for fq in (b"", b"\n\n", b"@r\n\n+\n\n", b"@r\nACGT\n+\nIIII"):
+        got, st = eng.count(ks, eng.reads_from_host(fq))
+        assert got.tolist() == [0] and st.n_kmers == 0
+        got, st = eng.count_host(ks, [fq])
+        assert got.tolist() == [0]
+    empty = eng.kmerset_from_text(b"", 31)
+    assert empty.n_records == 0
+    got, st = eng.count(empty, eng.reads_from_host(b"@r\nACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"))
+    assert got.size == 0 and st.n_kmers == 4
+    # no trailing newline on the last record, and on the first of two files
+    fq = b"@r\nACGTACGTACGTACGTACGTACGTACGTACGA\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII"
+    got, _ = eng.count(ks, eng.reads_from_host([fq, fq]))
+    assert got.tolist() == [2]
+
+
+def test_linearity_and_sharding(eng, tmp_path):
+    """counts(A + B) == counts(A) + counts(B); record-aligned shards of one file sum to the whole."""
+    rng = np.random.default_rng(5)
+    G = util.rand_genome(rng, 100_000)
+    fa = util.make_db(rng, G, 31, 10_000)
+    fq = util.make_reads(rng, G, 8000, 150, var_len=True)
+    p = tmp_path / "r.fq"
+    p.write_bytes(fq)
+    ks = eng.kmerset_from_text(fa, 31)
+    whole, st = eng.count_files(ks, [str(p)])
+    for n in (2, 3, 8):
+        acc = np.zeros_like(whole)
+        kmers = 0
+        for s in range(n):
+            part, sp = eng.count_files(ks, [str(p)], shard=s, n_shards=n)
+            acc += part
+            kmers += sp.n_kmers
+        assert np.array_equal(acc, whole) and kmers == st.n_kmers
+    d = adapters.count_dense(fa, 31, [fq])
+    assert np.array_equal(whole.astype(np.uint64), d.cnt)
+
+
+def test_l2_finalize_and_reducers(eng):
+    import torch
+    rng = np.random.default_rng(77)
+    k = 31
+    G = util.rand_genome(rng, 60_000)
+    fa = util.make_db(rng, G, k, 6000, both_strands=True, header=None, lower_frac=0.01)
+    fq = util.make_reads(rng, G, 4000, 150)
+    ks = eng.kmerset_from_text(fa, k)
+    reads = eng.reads_from_host(fq)
+    dev = torch.zeros(ks.n_records, dtype=torch.int32, device="cuda:0")
+    eng.count_device(ks, reads, dev.data_ptr())
+    d = adapters.count_dense(fa, k, [fq])
+    assert np.array_equal(dev.cpu().numpy().astype(np.uint64), d.cnt)
+    # L2 adapter (remove_1, kid order)
+    py_o = eng.l2_finalize(ks, dev.data_ptr())
+    assert np.array_equal(py_o, adapters.l2_py_o(d))
+    assert (py_o == 1).sum() == 0 and (py_o > 1).sum() > 100
+    # per-node reducer vs match_node
+    mr = adapters.l1_match_results(d)
+    valid = set(mr)
+    n_nodes = 9
+    lists = [np.unique(rng.integers(0, ks.n_records, int(rng.integers(1, 3000)))) for _ in range(n_nodes)]
+    lists[3] = np.zeros(0, dtype=np.int64)
+    ptr = np.zeros(n_nodes + 1, dtype=np.uint64)
+    ptr[1:] = np.cumsum([len(x) for x in lists])
+    length, covered, total = eng.node_reduce(ks, dev.data_ptr(), ptr, np.concatenate(lists))
+    for v in range(n_nodes):
+        vk = valid & set(int(x) for x in lists[v])
+        prof = [mr[x] for x in vk if mr[x] > 0]
+        assert length[v] == len(vk) and covered[v] == len(prof) and total[v] == sum(prof)
+    # per-strain reducer vs stat_cov / get_remainc / get_candidate_arr
+    n_rows, n_str = ks.n_records, 7
+    X = (rng.random((n_rows, n_str)) < 0.3).astype(np.int8)
+    used = (rng.random(n_rows) < 0.4).astype(np.uint8)
+    col_ptr = np.zeros(n_str + 1, dtype=np.uint64)
+    rows = []
+    for j in range(n_str):
+        r = np.nonzero(X[:, j])[0]
+        rows.append(r)
+        col_ptr[j + 1] = col_ptr[j] + len(r)
+    rows = np.concatenate(rows)
+    tot, cov, _ = eng.strain_reduce(col_ptr, rows, py_o)
+    ref = adapters.stat_cov_all(X, py_o)
+    assert [(int(c), int(t)) for c, t in zip(cov, tot)] == ref
+    assert [int(c) for c in cov] == adapters.candidate_counts(X, py_o)
+    tot2, cov2, _ = eng.strain_reduce(col_ptr, rows, py_o, row_mask=1 - used)
+    assert [(int(c), int(t)) for c, t in zip(cov2, tot2)] == adapters.remain_cov(used, X, py_o)
+
+
+def test_synthetic_workload_sample_vs_oracle(eng):
+    """The bench's generators: a small instance end to end against the oracle, plus the
+    size-independent invariants used at full size (sum of counts == hits; halves add up)."""
+    import torch
+    from strainscan_b200 import synth
+    p = synth.default_params(n_leaves=16, genome_len=200_000, seed=11)
+    sizes = synth.node_sizes(p, lo=200, hi=2000, seed=3)
+    text, node_of = eng.synth_db_host(p, sizes)
+    ks = eng.kmerset_from_text(text, p.k)
+    assert ks.n_records == int(sizes.sum())
+    n_reads = 20_000
+    rec = eng.synth_read_record_bytes(p)
+    cap = eng.reads_device_capacity(n_reads * rec)
+    buf = torch.empty(cap, dtype=torch.uint8, device="cuda:0")
+    eng.synth_reads_device(p, buf.data_ptr(), n_reads, 0)
+    reads = eng.reads_from_device(buf.data_ptr(), n_reads * rec, cap, keepalive=buf)
+    got, st = eng.count(ks, reads)
+    fq = buf[:n_reads * rec].cpu().numpy().tobytes()
+    d = adapters.count_dense(text.tobytes(), p.k, [fq])
+    assert np.array_equal(got.astype(np.uint64), d.cnt)
+    assert st.n_reads == n_reads and int(got[ks.valid].sum()) == st.n_hits and st.n_hits > 1000
+    # the same reads generated in two halves
+    half = n_reads // 2
+    acc = np.zeros_like(got)
+    for first in (0, half):
+        b2 = torch.empty(eng.reads_device_capacity(half * rec), dtype=torch.uint8, device="cuda:0")
+        eng.synth_reads_device(p, b2.data_ptr(), half, first)
+        r2 = eng.reads_from_device(b2.data_ptr(), half * rec, b2.numel(), keepalive=b2)
+        acc += eng.count(ks, r2)[0]
+    assert np.array_equal(acc, got)
+    # hits land on the nodes of the source leaves' root paths only
+    hit_nodes = set(np.unique(node_of[got > 0]).tolist())
+    allowed = set()
+    for i in range(p.n_sources):
+        v = p.n_leaves - 1 + p.source_leaf[i]
+        while True:
+            allowed.add(v)
+            if v == 0:
+                break
+            v = (v - 1) // 2
+    assert hit_nodes and hit_nodes <= allowed

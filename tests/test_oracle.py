@@ -27,7 +27,7 @@ def _dense_to_dump(case, d):
 def test_golden_present(golden_cases):
     names = {c["name"] for c in golden_cases}
     for need in ("strand", "nbreak_lower", "if_oddities", "short_reads", "crlf", "qual_at", "pe_files",
-                 "pe_zcat", "wrapped_fastq", "fasta_reads", "l2_k21", "k32", "k11", "lowcomplex",
+                 "pe_zcat", "wrapped_fastq", "fasta_reads", "l2_k21", "k32", "k11", "polyT_k32", "lowcomplex",
                  "medium_random"):
         assert need in names
 
