@@ -64,6 +64,8 @@ typedef struct ss_stats {
     double   ms_total;        /* wall time of the call */
     uint32_t probe_launches;  /* launches of the probe kernel inside this call */
     uint32_t total_launches;  /* all kernel launches inside this call */
+    uint64_t n_table_probes;  /* k-mers that passed the L2-resident prefilter and probed the HBM table
+                                 (0 when the set is small enough to need no filter) */
 } ss_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -104,6 +106,11 @@ int ss_kmerset_header_ids(const ss_kmerset *set, uint64_t *ids);
  * paths, concatenated exactly as the reference does (identify.py:75-76, Vote_...:367,371). */
 int ss_reads_from_files(ss_ctx *ctx, const char *const *paths, int n_paths, int shard, int n_shards,
                         ss_reads **reads);
+/* Host-only helper (no GPU needed): the record-aligned byte range [lo, hi) that shard `shard` of
+ * `n_shards` owns in FASTQ text `buf`.  A record start is a line opening with '@' whose line + 2
+ * opens with '+' (a quality line may open with '@'; its line + 2 is a sequence line).  The ranges
+ * of all shards partition [0, len).  Used by ss_reads_from_files / ss_count_files. */
+int ss_fastq_shard_range(const char *buf, size_t len, int shard, int n_shards, size_t *lo, size_t *hi);
 /* Same from in-memory FASTQ text (each buffer = one file's uncompressed contents). */
 int ss_reads_from_host(ss_ctx *ctx, const char *const *bufs, const size_t *lens, int n_bufs,
                        ss_reads **reads);

@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 ("n_hits", C.c_uint64), ("n_second_probe", C.c_uint64),
                 ("ms_index", C.c_double), ("ms_probe", C.c_double), ("ms_gather", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_total", C.c_double),
-                ("probe_launches", C.c_uint32), ("total_launches", C.c_uint32)]
+                ("probe_launches", C.c_uint32), ("total_launches", C.c_uint32),
+                ("n_table_probes", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -66,6 +67,7 @@ SIGNATURES = {
     "ss_kmerset_flags": (C.c_int, [_P, _P]),
     "ss_kmerset_header_ids": (C.c_int, [_P, _P]),
     "ss_reads_from_files": (C.c_int, [_P, _CSTRS, C.c_int, C.c_int, C.c_int, _PP]),
+    "ss_fastq_shard_range": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _SIZES, _SIZES]),
     "ss_reads_from_host": (C.c_int, [_P, _CSTRS, _SIZES, C.c_int, _PP]),
     "ss_reads_from_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _PP]),
     "ss_reads_device_capacity": (C.c_size_t, [C.c_size_t]),

@@ -48,7 +48,7 @@ struct ss_ctx {
     int n_sm = 0;
     cudaDeviceProp prop;
     cudaStream_t stream = nullptr, copy_stream = nullptr, own_stream = nullptr;
-    unsigned long long *d_stats = nullptr;   // [0..3] kmers, hits, second, reads; [4] first bad byte
+    unsigned long long *d_stats = nullptr;   // [0..3] kmers, hits, second, reads; [4] first bad byte; [5] table probes; [6] sink
     unsigned long long *h_stats = nullptr;   // pinned mirror
     uint32_t *d_dense = nullptr;             // scratch dense vector for host-output counts
     uint64_t dense_cap = 0;
@@ -69,6 +69,8 @@ struct ss_kmerset {
     uint32_t *d_slot_of = nullptr;    // n_records
     uint8_t *d_flags = nullptr;       // n_records
     uint32_t *d_row_of = nullptr;     // n_records or null (kid order == ordinal order)
+    unsigned long long *d_filter = nullptr;   // L2-resident prefilter (64-bit blocks) or null
+    uint32_t n_filter_words = 0;
     std::vector<uint8_t> flags;
     std::vector<uint64_t> header_ids;
     int has_ones = 0;
@@ -78,6 +80,7 @@ struct ss_kmerset {
         v.kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
         v.vmask = (k == 32) ? ~0u : ((1u << k) - 1u);
         v.k = k; v.has_ones = has_ones;
+        v.filter = d_filter; v.n_filter_words = n_filter_words;
         return v;
     }
 };
@@ -410,6 +413,21 @@ static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset 
     }
     SS_TRY(ss_launch_insert(d_keys, d_ok, n, (unsigned long long *)s->d_buckets, s->n_buckets, s->d_slot_of, d_last,
                             d_nd, c->stream));
+    {   // L2-resident prefilter for tables that cannot live in L2 themselves ("filter")
+        double bits_per_key = 16.0, max_mb = 48.0, min_table_mb = 32.0;
+        int force = -1;
+        if (const char *e = getenv("SS_FILTER")) force = atoi(e);
+        if (const char *e = getenv("SS_FILTER_BITS")) { double v = atof(e); if (v >= 4 && v <= 64) bits_per_key = v; }
+        if (const char *e = getenv("SS_FILTER_MAX_MB")) { double v = atof(e); if (v >= 1 && v <= 1024) max_mb = v; }
+        bool want = force >= 0 ? force != 0 : (double)s->n_buckets * sizeof(ss_bucket) > min_table_mb * 1e6;
+        if (want && n_ok > 0) {
+            double words = std::min((double)n_ok * bits_per_key / 64.0, max_mb * 1e6 / 8.0);
+            s->n_filter_words = (uint32_t)std::max(1024.0, words);
+            SS_TRY(cudaMalloc(&s->d_filter, (uint64_t)s->n_filter_words * 8));
+            SS_TRY(cudaMemsetAsync(s->d_filter, 0, (uint64_t)s->n_filter_words * 8, c->stream));
+            SS_TRY(ss_launch_filter_build(d_keys, d_ok, n, s->d_filter, s->n_filter_words, c->stream));
+        }
+    }
     SS_TRY(ss_launch_flags(s->d_slot_of, d_last, n, s->d_flags, c->stream));
     s->flags.assign(n, 0);
     unsigned long long nd = 0;
@@ -462,7 +480,7 @@ extern "C" int ss_kmerset_free(ss_kmerset *s) {
     if (!s) return SS_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_buckets); cudaFree(s->d_slot_cnt); cudaFree(s->d_slot_of); cudaFree(s->d_flags);
-    cudaFree(s->d_row_of);
+    cudaFree(s->d_row_of); cudaFree(s->d_filter);
     delete s;
     return SS_OK;
 }
@@ -470,7 +488,8 @@ extern "C" uint64_t ss_kmerset_records(const ss_kmerset *s) { return s ? s->n_re
 extern "C" uint64_t ss_kmerset_distinct(const ss_kmerset *s) { return s ? s->n_distinct : 0; }
 extern "C" int ss_kmerset_k(const ss_kmerset *s) { return s ? s->k : 0; }
 extern "C" uint64_t ss_kmerset_table_bytes(const ss_kmerset *s) {
-    return s ? s->n_buckets * sizeof(ss_bucket) + (4 * s->n_buckets + 1) * 4 + s->n_records * 5 : 0;
+    return s ? s->n_buckets * sizeof(ss_bucket) + (4 * s->n_buckets + 1) * 4 + s->n_records * 5 +
+                   (uint64_t)s->n_filter_words * 8 : 0;
 }
 extern "C" int ss_kmerset_flags(const ss_kmerset *s, uint8_t *flags) {
     if (!s || !flags) return fail(SS_ERR_ARG, "ss_kmerset_flags: NULL argument");
@@ -504,7 +523,7 @@ static int finish_reads(ss_ctx *c, ss_reads *r, size_t capacity) {
     size_t need = ss_reads_device_capacity(r->len);
     if (capacity < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
     SS_CUDA(cudaMemsetAsync(r->d_text + r->len, '\n', need - r->len, c->stream));
-    SS_CUDA(cudaMalloc(&r->d_tile_line, std::max<uint32_t>(r->n_tiles, 1) * sizeof(uint32_t)));
+    SS_CUDA(cudaMalloc(&r->d_tile_line, (uint64_t)(r->n_tiles + 1) * (SS_TILE / SS_SUB) * sizeof(uint32_t)));
     SS_CUDA(ss_launch_index(r->d_text, r->n_tiles, r->d_tile_line, 0, c->n_sm, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
     return SS_OK;
@@ -571,6 +590,14 @@ static int load_files_sharded(const char *const *paths, int n_paths, int shard, 
     return SS_OK;
 }
 
+extern "C" int ss_fastq_shard_range(const char *buf, size_t len, int shard, int n_shards, size_t *lo, size_t *hi) {
+    if (!lo || !hi || (!buf && len)) return fail(SS_ERR_ARG, "ss_fastq_shard_range: NULL argument");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(SS_ERR_ARG, "ss_fastq_shard_range: bad shard / n_shards");
+    *lo = find_record_start(buf, len, (size_t)((unsigned __int128)len * shard / n_shards));
+    *hi = (shard + 1 == n_shards) ? len : find_record_start(buf, len, (size_t)((unsigned __int128)len * (shard + 1) / n_shards));
+    return SS_OK;
+}
+
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
@@ -615,12 +642,14 @@ static int reset_pass(ss_ctx *c, const ss_kmerset *s) {
     SS_CUDA(cudaMemsetAsync(s->d_slot_cnt, 0, (4 * s->n_buckets + 1) * sizeof(uint32_t), c->stream));
     SS_CUDA(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
     SS_CUDA(cudaMemsetAsync(c->d_stats + 4, 0xFF, sizeof(unsigned long long), c->stream));
+    SS_CUDA(cudaMemsetAsync(c->d_stats + 5, 0, sizeof(unsigned long long), c->stream));
     return SS_OK;
 }
 
 static void fill_stats(ss_ctx *c, ss_stats *st) {
     st->n_kmers = c->h_stats[0]; st->n_hits = c->h_stats[1];
     st->n_second_probe = c->h_stats[2]; st->n_reads = c->h_stats[3];
+    st->n_table_probes = c->h_stats[5];   // 0 when the set has no filter: every k-mer probes the table
 }
 
 extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *dev_counts, ss_stats *st) {
@@ -636,7 +665,7 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
     SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
     SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, dev_counts, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
-    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
     rc = check_format_result(c, "ss_count");
     if (rc) return rc;
@@ -673,7 +702,7 @@ static int ensure_chunks(ss_ctx *c) {
     uint32_t tiles = (uint32_t)(SS_CHUNK_BYTES / SS_TILE) + 2;
     for (int i = 0; i < 2; i++) {
         SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
-        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], tiles * sizeof(uint32_t)));
+        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 1) * (SS_TILE / SS_SUB) * sizeof(uint32_t)));
     }
     return SS_OK;
 }
@@ -744,7 +773,7 @@ static int count_streamed(ss_ctx *c, const ss_kmerset *s, const char *const *buf
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
     if (s->n_records)
         SS_CUDA(cudaMemcpyAsync(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
-    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
     rc = check_format_result(c, "ss_count_host");
     if (rc) return rc;
@@ -875,7 +904,7 @@ extern "C" int ss_bench_random_gather(ss_ctx *c, uint64_t bytes, uint64_t n_prob
     double best = 0;
     for (int i = 0; i < iters + 1; i++) {
         SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
-        SS_CUDA(ss_launch_random_gather(buf.p, n_sectors, n_probes, 0x1234 + 7919ull * i, c->d_stats + 5, c->n_sm, c->stream));
+        SS_CUDA(ss_launch_random_gather(buf.p, n_sectors, n_probes, 0x1234 + 7919ull * i, c->d_stats + 6, c->n_sm, c->stream));
         SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
         SS_CUDA(cudaStreamSynchronize(c->stream));
         float ms = 0;

@@ -14,6 +14,7 @@
 #define SS_RUN      32                               // text bytes classified per thread
 #define SS_THREADS  (SS_TILE / SS_RUN)               // 256
 #define SS_NRUN     ((SS_TILE + SS_HALO) / SS_RUN)   // 258 runs incl. halo
+#define SS_SUB      1024                             // line-index granularity: one entry per warp of K3
 #define SS_STAGES   2
 #define SS_TEXT_PAD (SS_TILE + 256)                  // '\n' padding after the text on device
 
@@ -31,11 +32,21 @@ __host__ __device__ __forceinline__ uint64_t ss_mix(uint64_t x) {
     return x;
 }
 
-#ifdef __CUDACC__
-__device__ __forceinline__ uint64_t ss_bucket_of(uint64_t key, uint64_t n_buckets) {
-    return __umul64hi(ss_mix(key), n_buckets);
+// The probe path's hash: one xorshift-multiply round, split into two 32-bit words.
+//   hi -> table bucket   = mulhi32(hi, n_buckets)
+//   lo -> filter word    = mulhi32(lo, n_filter_words), filter bits from (lo * golden) top bits
+__host__ __device__ __forceinline__ uint64_t ss_mix1(uint64_t x) {
+    x ^= x >> 29; x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32; x *= 0x9e3779b97f4a7c15ull;
+    return x;
 }
-#endif
+// 4 bits of a 64-bit filter word: two in each 32-bit half
+__host__ __device__ __forceinline__ uint64_t ss_filter_mask(uint32_t lo) {
+    uint32_t m = lo * 0x9E3779B1u;
+    uint32_t a = (1u << (m >> 27)) | (1u << ((m >> 22) & 31u));
+    uint32_t b = (1u << ((m >> 17) & 31u)) | (1u << ((m >> 12) & 31u));
+    return (uint64_t)a | ((uint64_t)b << 32);
+}
 
 struct ss_table_view {
     const ss_bucket *buckets;      // n_buckets x 32 B
@@ -45,6 +56,8 @@ struct ss_table_view {
     uint32_t vmask;                // low k bits
     int k;
     int has_ones;                  // the key 0xFFFF...F (k = 32 poly-T) is in the set
+    const unsigned long long *filter;   // L2-resident blocked Bloom filter (64-bit blocks) or NULL
+    uint32_t n_filter_words;
 };
 
 void ss_set_error(const std::string &msg);

@@ -46,6 +46,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -55,6 +63,12 @@ __device__ __forceinline__ void ld_bucket(const ss_bucket *p, unsigned long long
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                  : "l"(p));
+}
+// one filter word (8 bytes of an L2-resident blocked Bloom filter), kept in L2 with evict_last
+__device__ __forceinline__ unsigned long long ld_filter(const unsigned long long *p, uint64_t policy) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
 }
 __device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -133,36 +147,29 @@ __device__ __forceinline__ uint32_t seq_line_mask(uint32_t nlmask, uint32_t line
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1a / K1b: line index of every tile start
+// K1a / K1b: line index at every 1 KiB sub-block start (8 per tile, one per warp of K3)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SS_THREADS) ss_nl_count_kernel(const uint8_t *__restrict__ text, uint32_t n_tiles,
-                                                                   uint32_t *__restrict__ tile_nl) {
-    __shared__ uint32_t wsum[SS_THREADS / 32];
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(text + (uint64_t)t * SS_TILE);
-        // 512 x 16 B per tile: thread i takes chunks i and i + 256 (coalesced)
+__global__ void __launch_bounds__(256) ss_nl_count_kernel(const uint8_t *__restrict__ text, uint32_t n_sub,
+                                                          uint32_t *__restrict__ sub_nl) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_sub; b += warps) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(text + (uint64_t)b * SS_SUB);
         uint32_t c = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint4 v = __ldg(p + threadIdx.x + h * SS_THREADS);
+        for (int h = 0; h < 2; h++) {   // 64 x 16 B per sub-block: lane takes chunks lane and lane + 32
+            uint4 v = __ldg(p + lane + h * 32);
             c += __popc(~nz7(v.x, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.y, 0x0A0A0A0Au) & 0x80808080u) +
                  __popc(~nz7(v.z, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.w, 0x0A0A0A0Au) & 0x80808080u);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t s = 0;
-#pragma unroll
-            for (int i = 0; i < SS_THREADS / 32; i++) s += wsum[i];
-            tile_nl[t] = s;
-        }
-        __syncthreads();
+        if (lane == 0) sub_nl[b] = c;
     }
 }
 
-// in-place exclusive scan (single CTA, 1024 threads); out[i] = base + sum_{j<i} in[j]
+// in-place exclusive scan (single CTA, 1024 threads); out[i] = base + sum_{j<i} in[j].
+// Only the low two bits of a line index are ever used, so 32-bit wrap-around is harmless.
 __global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v, uint32_t n, uint32_t base) {
     __shared__ uint32_t part[1024];
     uint32_t per = (n + 1023u) / 1024u;
@@ -171,8 +178,7 @@ __global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v,
     for (uint32_t i = lo; i < hi; i++) s += v[i];
     part[threadIdx.x] = s;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (uint32_t o = 1; o < 1024; o <<= 1) {
+    for (uint32_t o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan over the partials
         uint32_t x = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0;
         __syncthreads();
         part[threadIdx.x] += x;
@@ -183,21 +189,43 @@ __global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: fused scan / encode / probe / count
+// K3: fused scan / encode / filter / probe / count
 // ---------------------------------------------------------------------------------------------
-template <int UNROLL>
+// bit L of the result = bytes p+L .. p+L+k-1 are all valid, for V = valid bits of bytes p .. p+63
+__device__ __forceinline__ uint32_t window_mask(uint64_t V, int k) {
+    uint64_t R = ~0ull, X = V;
+    int shift = 0;
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+        if (k & (1 << b)) { R &= X >> shift; shift += (1 << b); }
+        X &= X >> (1 << b);
+    }
+    return (uint32_t)R;
+}
+
+// hash of a packed k-mer: two well-mixed 32-bit words (hi -> table bucket, lo -> filter word + bits)
+__device__ __forceinline__ void ss_hash2(uint64_t key, uint32_t &hi, uint32_t &lo) {
+    uint64_t h = ss_mix1(key);
+    hi = (uint32_t)(h >> 32);
+    lo = (uint32_t)h ^ hi;
+}
+
+template <bool FILTER, int UNROLL>
 __global__ void __launch_bounds__(SS_THREADS, SS_PROBE_MIN_CTAS)
 ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_tiles,
-                const uint32_t *__restrict__ tile_line, ss_table_view tv,
+                const uint32_t *__restrict__ sub_line, ss_table_view tv,
                 unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
     __shared__ __align__(128) uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];
     __shared__ __align__(16) uint64_t s_codes[SS_NRUN + 2];
     __shared__ uint32_t s_valid[SS_NRUN + 2];
-    __shared__ uint32_t s_wsum[SS_THREADS / 32];
     __shared__ __align__(8) uint64_t s_full[SS_STAGES];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     constexpr uint32_t kBytes = SS_TILE + SS_HALO;
+
+    uint64_t pol_stream = 0, pol_keep = 0;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
 
     if (tid == 0) {
 #pragma unroll
@@ -213,12 +241,12 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
             uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
             if (t < n_tiles) {
                 mbar_expect_tx(&s_full[s], kBytes);
-                tma_load_1d(raw[s], text + t * SS_TILE, kBytes, &s_full[s]);
+                tma_load_1d_hint(raw[s], text + t * SS_TILE, kBytes, &s_full[s], pol_stream);
             }
         }
     }
 
-    uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0;
+    uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0;
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -227,38 +255,30 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
         const uint8_t *rt = raw[s];
         const uint64_t tile_gpos = tile * SS_TILE;
 
-        // ---- phase 1: classify my 32-byte run, find its line index, publish codes + valid bits
-        run_bits rb = classify_run(rt + tid * SS_RUN);
-        uint32_t c = __popc(rb.nl), inc = c;
+        // ---- phase 1: classify my 32-byte run; line index from the per-warp (1 KiB) index
+        {
+            run_bits rb = classify_run(rt + tid * SS_RUN);
+            uint32_t c = __popc(rb.nl), inc = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= (uint32_t)o) inc += x;
-        }
-        if (lane == 31) s_wsum[wid] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < SS_THREADS / 32; i++) {
-            uint32_t x = s_wsum[i];
-            if ((uint32_t)i < wid) wbase += x;
-            total += x;
-        }
-        const uint32_t line0 = tile_line[tile];
-        uint32_t line = line0 + wbase + inc - c;
-        uint32_t seqm = seq_line_mask(rb.nl, line, rt, tid * SS_RUN, tile_gpos, text_len, true, n_reads, err);
-        s_codes[tid] = rb.codes;
-        s_valid[tid] = rb.ok & seqm;
-        if (tid < 2) {   // the two halo runs
-            run_bits hb = classify_run(rt + (SS_THREADS + tid) * SS_RUN);
-            uint32_t hc = __popc(hb.nl);
-            uint32_t h0 = __shfl_sync(0x3u, hc, 0);
-            uint32_t hline = line0 + total + (tid == 1 ? h0 : 0u);
-            uint32_t dummy = 0;
-            uint32_t hm = seq_line_mask(hb.nl, hline, rt, (SS_THREADS + tid) * SS_RUN, tile_gpos, text_len, false,
-                                        dummy, err);
-            s_codes[SS_THREADS + tid] = hb.codes;
-            s_valid[SS_THREADS + tid] = hb.ok & hm;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += x;
+            }
+            uint32_t line = sub_line[tile * (SS_TILE / SS_SUB) + wid] + inc - c;
+            uint32_t seqm = seq_line_mask(rb.nl, line, rt, tid * SS_RUN, tile_gpos, text_len, true, n_reads, err);
+            s_codes[tid] = rb.codes;
+            s_valid[tid] = rb.ok & seqm;
+            if (tid < 2) {   // the two halo runs continue into the next tile's first sub-block
+                run_bits hb = classify_run(rt + (SS_THREADS + tid) * SS_RUN);
+                uint32_t hc = __popc(hb.nl);
+                uint32_t h0 = __shfl_sync(0x3u, hc, 0);
+                uint32_t hline = sub_line[(tile + 1) * (SS_TILE / SS_SUB)] + (tid == 1 ? h0 : 0u);
+                uint32_t dummy = 0;
+                uint32_t hm = seq_line_mask(hb.nl, hline, rt, (SS_THREADS + tid) * SS_RUN, tile_gpos, text_len, false,
+                                            dummy, err);
+                s_codes[SS_THREADS + tid] = hb.codes;
+                s_valid[SS_THREADS + tid] = hb.ok & hm;
+            }
         }
         __syncthreads();
 
@@ -268,44 +288,67 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
             if (nt < n_tiles) {
                 fence_proxy_async();
                 mbar_expect_tx(&s_full[s], kBytes);
-                tma_load_1d(raw[s], text + nt * SS_TILE, kBytes, &s_full[s]);
+                tma_load_1d_hint(raw[s], text + nt * SS_TILE, kBytes, &s_full[s], pol_stream);
             }
         }
 
-        // ---- phase 2: every window start of the tile; lanes take adjacent positions
-#pragma unroll 1
-        for (uint32_t j = 0; j < SS_TILE / SS_THREADS; j += UNROLL) {
-            unsigned long long km[UNROLL];
-            uint64_t bk[UNROLL];
+        // ---- phase 2: warp w owns window starts [1024 w, 1024 w + 1024) = 32 groups of 32 positions.
+        // Lane j first derives the window-valid mask of group j; groups with no valid window are
+        // skipped warp-uniformly, the others are probed with lane = position inside the group.
+        const uint32_t g0 = wid * 32u;
+        uint32_t my_w;
+        {
+            uint64_t V = (uint64_t)s_valid[g0 + lane] | ((uint64_t)s_valid[g0 + lane + 1] << 32);
+            my_w = window_mask(V, tv.k);
+        }
+        uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
+        while (nonempty) {
+            uint64_t km[UNROLL];
+            uint32_t hh[UNROLL], hl[UNROLL], grp[UNROLL];
             bool ok[UNROLL];
-            unsigned long long q0[UNROLL], q1[UNROLL], q2[UNROLL], q3[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                uint32_t p = (j + u) * SS_THREADS + tid;
-                uint32_t wi = p >> 5, b = p & 31u;
-                uint32_t v = __funnelshift_r(s_valid[wi], s_valid[wi + 1], b);
-                ok[u] = (v & tv.vmask) == tv.vmask;
-                uint64_t lo = s_codes[wi], hi = s_codes[wi + 1];
-                uint32_t sh = 2u * b;
+                ok[u] = false; grp[u] = 0;
+                if (nonempty) {
+                    uint32_t j = (uint32_t)__ffs(nonempty) - 1u;
+                    nonempty &= nonempty - 1u;
+                    uint32_t w = __shfl_sync(0xFFFFFFFFu, my_w, j);
+                    ok[u] = (w >> lane) & 1u;
+                    grp[u] = g0 + j;
+                }
+                uint64_t lo = s_codes[grp[u]], hi = s_codes[grp[u] + 1];
+                uint32_t sh = 2u * lane;
                 km[u] = ((lo >> sh) | ((hi << 1) << (63u - sh))) & tv.kmask;
-                if (tv.k == 32 && km[u] == SS_EMPTY && ok[u]) {   // poly-T 32-mer: lives outside the table
+                if (tv.k == 32 && ok[u] && km[u] == SS_EMPTY) {   // poly-T 32-mer: lives outside the table
                     n_kmers++;
                     if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
                     ok[u] = false;
                 }
-                bk[u] = ss_bucket_of(km[u], tv.n_buckets);
+                ss_hash2(km[u], hh[u], hl[u]);
             }
+            if (FILTER) {
+                uint64_t fw[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                q0[u] = q1[u] = q2[u] = q3[u] = 0ull;
-                if (ok[u]) ld_bucket(tv.buckets + bk[u], q0[u], q1[u], q2[u], q3[u]);
+                for (int u = 0; u < UNROLL; u++) {
+                    fw[u] = 0ull;
+                    if (ok[u]) fw[u] = ld_filter(tv.filter + __umulhi(hl[u], tv.n_filter_words), pol_keep);
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    if (ok[u]) {
+                        n_kmers++;
+                        uint64_t m = ss_filter_mask(hl[u]);
+                        ok[u] = (fw[u] & m) == m;
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 if (!ok[u]) continue;
-                n_kmers++;
-                uint64_t b = bk[u];
-                unsigned long long a0 = q0[u], a1 = q1[u], a2 = q2[u], a3 = q3[u];
+                if (FILTER) n_table++; else n_kmers++;
+                uint64_t b = (uint64_t)__umulhi(hh[u], (uint32_t)tv.n_buckets);
+                unsigned long long a0, a1, a2, a3;
+                ld_bucket(tv.buckets + b, a0, a1, a2, a3);
                 while (true) {
                     int f = (a0 == km[u]) ? 0 : (a1 == km[u]) ? 1 : (a2 == km[u]) ? 2 : (a3 == km[u]) ? 3 : -1;
                     if (f >= 0) {
@@ -324,13 +367,13 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
     }
 
     // ---- per-CTA statistics
-    unsigned long long st[4] = {n_kmers, n_hits, n_second, n_reads};
+    unsigned long long st[5] = {n_kmers, n_hits, n_second, n_reads, n_table};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 5; i++) {
         unsigned long long x = st[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
-        if (lane == 0 && x) atomicAdd(stats + i, x);
+        if (lane == 0 && x) atomicAdd(stats + (i < 4 ? i : 5), x);
     }
 }
 
@@ -350,7 +393,7 @@ __global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_
     if (key == SS_EMPTY) {                      // k = 32 poly-T
         slot = 4 * n_buckets;               // counted as distinct by the host
     } else {
-        uint64_t b = ss_bucket_of(key, n_buckets);
+        uint64_t b = (uint64_t)__umulhi((uint32_t)(ss_mix1(key) >> 32), (uint32_t)n_buckets);
         while (true) {
             bool done = false;
 #pragma unroll
@@ -369,6 +412,16 @@ __global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_
     }
     slot_of[i] = (uint32_t)slot;
     atomicMax(last_ord + slot, (uint32_t)i);
+}
+
+// L2-resident prefilter: every key sets 4 bits of one 64-bit word
+__global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ rec_ok, uint64_t n,
+                                       unsigned long long *__restrict__ filter, uint32_t n_words) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !rec_ok[i] || keys[i] == SS_EMPTY) return;
+    uint64_t h = ss_mix1(keys[i]);
+    uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h ^ hi;
+    atomicOr(filter + __umulhi(lo, n_words), (unsigned long long)ss_filter_mask(lo));
 }
 
 // flags[i] |= IS_LAST where record i is the highest ordinal stored at its slot
@@ -498,30 +551,45 @@ static int g_probe_ctas_per_sm = 0;
 
 int ss_probe_ctas_per_sm() {
     if (g_probe_ctas_per_sm == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ss_probe_kernel<SS_PROBE_UNROLL>, SS_THREADS, 0) !=
+        int n = 0, m = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ss_probe_kernel<true, SS_PROBE_UNROLL>, SS_THREADS, 0) !=
                 cudaSuccess || n < 1)
             n = 1;
-        g_probe_ctas_per_sm = n;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, ss_probe_kernel<false, SS_PROBE_UNROLL>, SS_THREADS, 0) !=
+                cudaSuccess || m < 1)
+            m = 1;
+        g_probe_ctas_per_sm = n < m ? n : m;
     }
     return g_probe_ctas_per_sm;
 }
 
-cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *tile_line, uint32_t line_base,
+// sub_line must hold (n_tiles + 1) * SS_TILE / SS_SUB entries; the text buffer is padded by one tile
+cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *sub_line, uint32_t line_base,
                             int n_sm, cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
-    uint32_t grid = min(n_tiles, (uint32_t)n_sm * 8u);
-    ss_nl_count_kernel<<<grid, SS_THREADS, 0, st>>>(text, n_tiles, tile_line);
-    ss_scan_kernel<<<1, 1024, 0, st>>>(tile_line, n_tiles, line_base);
+    uint32_t n_sub = (n_tiles + 1) * (SS_TILE / SS_SUB);
+    uint32_t grid = min((n_sub + 7u) / 8u, (uint32_t)n_sm * 8u);
+    ss_nl_count_kernel<<<grid, 256, 0, st>>>(text, n_sub, sub_line);
+    ss_scan_kernel<<<1, 1024, 0, st>>>(sub_line, n_sub, line_base);
     return cudaGetLastError();
 }
 
-cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *tile_line,
+cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *sub_line,
                             const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
                             cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
     uint32_t grid = min(n_tiles, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
-    ss_probe_kernel<SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, tile_line, tv, stats, err);
+    if (tv.filter)
+        ss_probe_kernel<true, SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    else
+        ss_probe_kernel<false, SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *filter,
+                                   uint32_t n_words, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    ss_filter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, rec_ok, n, filter, n_words);
     return cudaGetLastError();
 }
 

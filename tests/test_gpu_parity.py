@@ -107,8 +107,13 @@ def test_unsupported_inputs_fail_loudly(eng, golden_cases):
         eng.kmerset_from_fasta("/nonexistent/kmer.fa", 31)
 
 
-@pytest.mark.parametrize("k", [11, 21, 31, 32])
-def test_random_vs_oracle(eng, k):
+@pytest.mark.parametrize("k,filt", [(11, None), (21, None), (31, None), (32, None), (31, "16"), (21, "4"), (32, "6")])
+def test_random_vs_oracle(eng, k, filt, monkeypatch):
+    """filt: force the L2-resident prefilter on with that many bits per key (4 = many false
+    positives, which must all be rejected by the exact table probe)."""
+    if filt:
+        monkeypatch.setenv("SS_FILTER", "1")
+        monkeypatch.setenv("SS_FILTER_BITS", filt)
     rng = np.random.default_rng(1000 + k)
     G = util.rand_genome(rng, 200_000)
     fa = util.make_db(rng, G, k, 20_000, both_strands=True, lower_frac=0.02, junk=40)
@@ -120,9 +125,24 @@ def test_random_vs_oracle(eng, k):
         assert np.array_equal(got.astype(np.uint64), d.cnt)
         assert st.n_kmers == adapters.count_windows([fq1, fq2], k)
         assert st.n_reads == 9000
+        if filt:
+            assert st.n_hits <= st.n_table_probes < st.n_kmers    # the filter rejected most misses
+        else:
+            assert st.n_table_probes == 0
     assert np.array_equal(ks.flags & 1, d.in_set)
     assert np.array_equal((ks.flags >> 1) & 1, d.is_last)
     assert d.cnt.sum() > 1000
+
+
+def test_golden_with_filter_forced(eng, golden_cases, monkeypatch):
+    monkeypatch.setenv("SS_FILTER", "1")
+    for case in golden_cases:
+        if not _supported(case):
+            continue
+        ks = eng.kmerset_from_text(case["fasta"], case["k"])
+        got, st = eng.count(ks, eng.reads_from_host([r.encode() for r in case["reads"]]))
+        _check_against_dump(case, got, ks.flags)
+        assert st.n_kmers == adapters.count_windows([r.encode() for r in case["reads"]], case["k"]), case["name"]
 
 
 def test_poly_t_32mer(eng):
@@ -145,8 +165,8 @@ def test_empty_and_degenerate(eng):
         assert got.tolist() == [0]
     empty = eng.kmerset_from_text(b"", 31)
     assert empty.n_records == 0
-    got, st = eng.count(empty, eng.reads_from_host(b"@r\nACGTACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"))
-    assert got.size == 0 and st.n_kmers == 4
+    got, st = eng.count(empty, eng.reads_from_host(b"@r\n" + b"ACGT" * 9 + b"\n+\n" + b"I" * 36 + b"\n"))
+    assert got.size == 0 and st.n_kmers == 6
     # no trailing newline on the last record, and on the first of two files
     fq = b"@r\nACGTACGTACGTACGTACGTACGTACGTACGA\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII"
     got, _ = eng.count(ks, eng.reads_from_host([fq, fq]))

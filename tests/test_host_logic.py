@@ -1,0 +1,109 @@
+"""Host-side mirrors of the reference interface (identify_shim / l2_shim) against the oracle's
+restatement of the reference's dict/list code.  CPU only: count vectors come from the oracle here;
+the GPU tests check that the CUDA path produces the same vectors."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from oracle import adapters
+from strainscan_b200 import identify_shim, l2_shim
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def l1_case():
+    rng = np.random.default_rng(42)
+    G = util.rand_genome(rng, 80_000)
+    fa = util.make_db(rng, G, 31, 9000, both_strands=True, lower_frac=0.02, junk=24)
+    fq = util.make_reads(rng, G, 5000, 150)
+    d = adapters.count_dense(fa, 31, [fq])
+    valid = (d.in_set & d.is_last).astype(bool)
+    cv = identify_shim.CountVector(d.cnt.astype(np.uint32), valid)
+    return d, cv, adapters.l1_match_results(d)
+
+
+def test_count_vector_is_the_reference_dict(l1_case):
+    d, cv, ref = l1_case
+    assert len(cv) == len(ref)
+    assert cv.to_dict() == ref
+    assert set(cv.keys()) == set(ref.keys())
+    some = list(ref)[:50]
+    assert all(cv[k] == ref[k] for k in some)
+    invalid = int(np.nonzero(~cv.valid_mask)[0][0])
+    with pytest.raises(KeyError):
+        cv[invalid]
+    with pytest.raises(KeyError):
+        cv[10 ** 9]
+    assert invalid not in cv and some[0] in cv
+
+
+def test_valid_kmers_intersection_matches_set_semantics(l1_case):
+    d, cv, ref = l1_case
+    vk = cv.valid_kmers()
+    ref_valid = set(ref.keys())
+    rng = np.random.default_rng(1)
+    dset = set(int(x) for x in rng.integers(0, len(d.cnt), 3000))
+    assert (vk & dset) == (ref_valid & dset)
+    assert (dset & vk) == (ref_valid & dset)
+    assert len(vk) == len(ref_valid)
+
+
+def test_match_node_equals_reference(l1_case, tmp_path):
+    d, cv, ref = l1_case
+    ref_valid = set(ref.keys())
+    rng = np.random.default_rng(2)
+    os.makedirs(tmp_path / "kmers")
+    # hot k-mer to trigger the 100x-median outlier trim
+    cv.counts[int(np.nonzero(cv.valid_mask & (cv.counts > 0))[0][0])] = 100000
+    ref = {k: int(cv.counts[k]) for k in ref}
+    for node, n in enumerate([1, 50, 1500, 4000, 0]):
+        ords = rng.integers(0, len(d.cnt), n)
+        if node == 3:
+            ords = np.concatenate([ords, ords[:100], np.nonzero(cv.counts == 100000)[0]])   # duplicates + hot k-mer
+        with open(tmp_path / "kmers" / str(node), "w") as f:
+            f.write("".join("%d " % x for x in ords))
+        if n == 0:
+            open(tmp_path / "kmers" / str(node), "w").close()
+            with pytest.raises(IndexError):
+                identify_shim.match_node(cv, str(tmp_path), node, cv.valid_kmers())
+            assert identify_shim.match_node_low_depth(cv, str(tmp_path), node) == (0, [])
+            continue
+        length, prof = identify_shim.match_node(cv, str(tmp_path), node, cv.valid_kmers())
+        rl, rp = adapters.match_node(ref, ords, ref_valid)
+        assert length == rl and sorted(prof) == rp
+        ll, lp = identify_shim.match_node_low_depth(cv, str(tmp_path), node)
+        rl2, rp2 = adapters.match_node(ref, ords, ref_valid, min_valid=1000)
+        assert ll == rl2 and sorted(lp) == rp2
+    ptr, ordinals = identify_shim.load_node_csr(str(tmp_path), [0, 1, 2, 3, 4])
+    assert ptr[-1] == ordinals.size and ptr[5] == ptr[4]
+
+
+def test_del_outlier_equals_reference():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        prof = rng.integers(1, 5, 200).tolist() + [1000, 500, 399, 400]
+        assert sorted(identify_shim.del_outlier(prof).tolist()) == sorted(adapters.del_outlier(prof))
+
+
+def test_remove_1_and_kid_order(golden_cases):
+    case = [c for c in golden_cases if c["name"] == "l2_k21"][0]
+    # shuffle the records so that header kids are a non-identity permutation
+    lines = case["fasta"].strip().split("\n")
+    recs = [(lines[i], lines[i + 1]) for i in range(0, len(lines), 2)]
+    rng = np.random.default_rng(4)
+    recs = [recs[i] for i in rng.permutation(len(recs))]
+    fa = "".join("%s\n%s\n" % r for r in recs)
+    d = adapters.count_dense(fa.encode(), case["k"], [r.encode() for r in case["reads"]])
+    kset = types.SimpleNamespace(flags=(d.in_set | (d.is_last << 1) | (d.raw_upper << 2)).astype(np.uint8),
+                                 header_ids=d.header_id)
+    py_o = l2_shim.remove_1(d.cnt.astype(np.uint32), kset)
+    assert np.array_equal(py_o, adapters.l2_py_o_from_dump(fa, case["dump"]))
+    assert np.array_equal(py_o, adapters.l2_py_o_from_dump(case["fasta"], case["dump"]))
+
+
+def test_read_paths_follow_reference_convention():
+    assert identify_shim.read_paths(("a.fq", "")) == ["a.fq"]
+    assert identify_shim.read_paths(("a.fq.gz", "b.fq.gz")) == ["a.fq.gz", "b.fq.gz"]
+    assert identify_shim.read_paths("a.fq b.fq") == ["a.fq", "b.fq"]
