@@ -8,14 +8,17 @@
 
 // ---- tiling of the FASTQ text ---------------------------------------------------------------
 // A tile owns SS_TILE window-start positions; SS_HALO more bytes are staged with it so that a
-// window that starts in the tile can finish (k-1 <= 31 bytes needed; 64 keeps 32-byte runs).
+// window that starts in the tile can finish (k-1 <= 31 bytes needed).
 #define SS_TILE     8192
-#define SS_HALO     64
+#define SS_HALO     32                               // >= k-1 bytes after the tile (one more run)
 #define SS_RUN      32                               // text bytes classified per thread
-#define SS_THREADS  (SS_TILE / SS_RUN)               // 256
-#define SS_NRUN     ((SS_TILE + SS_HALO) / SS_RUN)   // 258 runs incl. halo
-#define SS_SUB      1024                             // line-index granularity: one entry per warp of K3
-#define SS_STAGES   2
+#define SS_THREADS  (SS_TILE / SS_RUN)               // 256 consumer threads
+#define SS_CONSUMERS (SS_THREADS / 32)               // 8 consumer warps, each owns SS_SUB bytes of a tile
+#define SS_CTA_THREADS (SS_THREADS + 32)             // + 1 producer warp
+#define SS_SUB      1024                             // line-index granularity = one consumer warp's slice
+#define SS_WRUNS    33                               // runs a warp classifies: 32 + 1 halo
+#define SS_QCAP     (32 + 32)                        // deferred table-probe queue entries per warp
+#define SS_STAGES   3
 #define SS_TEXT_PAD (SS_TILE + 256)                  // '\n' padding after the text on device
 
 #define SS_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -36,8 +39,7 @@ __host__ __device__ __forceinline__ uint64_t ss_mix(uint64_t x) {
 //   hi -> table bucket   = mulhi32(hi, n_buckets)
 //   lo -> filter word    = mulhi32(lo, n_filter_words), filter bits from (lo * golden) top bits
 __host__ __device__ __forceinline__ uint64_t ss_mix1(uint64_t x) {
-    x ^= x >> 29; x *= 0xd6e8feb86659fd93ull;
-    x ^= x >> 32; x *= 0x9e3779b97f4a7c15ull;
+    x ^= x >> 31; x *= 0xd6e8feb86659fd93ull;
     return x;
 }
 // 4 bits of a 64-bit filter word: two in each 32-bit half

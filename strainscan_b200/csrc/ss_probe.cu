@@ -14,6 +14,7 @@
 // library/identify.py:82-101 and library/Vote_Strain_L2_Lasso_new_sp.py:357-403.
 #include "ss_common.cuh"
 #include "ss_kernels.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk TMA (cp.async.bulk -> UBLKCP), 256-bit sector load, RED
@@ -146,6 +147,13 @@ __device__ __forceinline__ uint32_t seq_line_mask(uint32_t nlmask, uint32_t line
     return seqmask;
 }
 
+// hash of a packed k-mer: two 32-bit words (hi -> table bucket, lo -> filter word + bits)
+__device__ __forceinline__ void ss_hash2(uint64_t key, uint32_t &hi, uint32_t &lo) {
+    uint64_t h = ss_mix1(key);
+    hi = (uint32_t)(h >> 32);
+    lo = (uint32_t)h ^ hi;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1a / K1b: line index at every 1 KiB sub-block start (8 per tile, one per warp of K3)
 // ---------------------------------------------------------------------------------------------
@@ -190,6 +198,12 @@ __global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v,
 
 // ---------------------------------------------------------------------------------------------
 // K3: fused scan / encode / filter / probe / count
+//
+// CTA = 8 autonomous consumer warps + 1 producer warp.  The producer streams 8 KiB text tiles into a
+// shared-memory ring with 1-D bulk TMA (full/empty mbarriers).  Consumer warp w owns bytes
+// [1024 w, 1024 w + 1024) of every tile (+ 32 bytes of halo): it classifies them, keeps its 2-bit
+// codes / valid bits in its own shared-memory slice, releases the raw stage, and probes its own
+// window starts -- no CTA-wide barrier anywhere in the loop.
 // ---------------------------------------------------------------------------------------------
 // bit L of the result = bytes p+L .. p+L+k-1 are all valid, for V = valid bits of bytes p .. p+63
 __device__ __forceinline__ uint32_t window_mask(uint64_t V, int k) {
@@ -203,126 +217,148 @@ __device__ __forceinline__ uint32_t window_mask(uint64_t V, int k) {
     return (uint32_t)R;
 }
 
-// hash of a packed k-mer: two well-mixed 32-bit words (hi -> table bucket, lo -> filter word + bits)
-__device__ __forceinline__ void ss_hash2(uint64_t key, uint32_t &hi, uint32_t &lo) {
-    uint64_t h = ss_mix1(key);
-    hi = (uint32_t)(h >> 32);
-    lo = (uint32_t)h ^ hi;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool FILTER, int UNROLL>
-__global__ void __launch_bounds__(SS_THREADS, SS_PROBE_MIN_CTAS)
+struct ss_warp_smem {
+    uint64_t codes[SS_WRUNS + 2];        // 2-bit codes of my 33 runs (+ zero pad)
+    uint32_t valid[SS_WRUNS + 3];        // valid bits of my 33 runs (+ zero pad)
+    uint64_t q_key[SS_QCAP];             // deferred table probes: k-mer
+    uint32_t q_bkt[SS_QCAP];             //                        home bucket
+};
+
+// exact table probe of one k-mer (one 32-byte sector, next sector only when the bucket is full)
+__device__ __forceinline__ void table_probe(const ss_table_view &tv, uint64_t km, uint32_t bucket, uint32_t &n_hits,
+                                            uint32_t &n_second) {
+    uint64_t b = bucket;
+    unsigned long long a0, a1, a2, a3;
+    ld_bucket(tv.buckets + b, a0, a1, a2, a3);
+    while (true) {
+        int f = (a0 == km) ? 0 : (a1 == km) ? 1 : (a2 == km) ? 2 : (a3 == km) ? 3 : -1;
+        if (f >= 0) {
+            red_add_u32(tv.slot_cnt + 4 * b + f, 1u);
+            n_hits++;
+            return;
+        }
+        if (a3 == SS_EMPTY || a2 == SS_EMPTY || a1 == SS_EMPTY || a0 == SS_EMPTY) return;   // miss
+        b = (b + 1 == tv.n_buckets) ? 0 : b + 1;   // bucket full: next sector
+        n_second++;
+        ld_bucket(tv.buckets + b, a0, a1, a2, a3);
+    }
+}
+
+template <bool FILTER, bool K32, int UNROLL, int MINCTAS>
+__global__ void __launch_bounds__(SS_CTA_THREADS, MINCTAS)
 ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_tiles,
                 const uint32_t *__restrict__ sub_line, ss_table_view tv,
                 unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
     __shared__ __align__(128) uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];
-    __shared__ __align__(16) uint64_t s_codes[SS_NRUN + 2];
-    __shared__ uint32_t s_valid[SS_NRUN + 2];
+    __shared__ __align__(16) ss_warp_smem s_warp[SS_CONSUMERS];
     __shared__ __align__(8) uint64_t s_full[SS_STAGES];
+    __shared__ __align__(8) uint64_t s_empty[SS_STAGES];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     constexpr uint32_t kBytes = SS_TILE + SS_HALO;
 
-    uint64_t pol_stream = 0, pol_keep = 0;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < SS_STAGES; s++) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < SS_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], SS_CONSUMERS); }
         fence_mbar_init();
-        s_codes[SS_NRUN] = 0; s_codes[SS_NRUN + 1] = 0;
-        s_valid[SS_NRUN] = 0; s_valid[SS_NRUN + 1] = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < SS_STAGES; s++) {
-            uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x;
-            if (t < n_tiles) {
+
+    if (wid == SS_CONSUMERS) {
+        // ===== producer warp: one elected lane feeds the ring =====
+        if (lane == 0) {
+            uint64_t pol_stream;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            uint32_t it = 0;
+            for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % SS_STAGES;
+                if (it >= SS_STAGES) mbar_wait(&s_empty[s], ((it / SS_STAGES) - 1u) & 1u);   // all 8 warps released it
                 mbar_expect_tx(&s_full[s], kBytes);
-                tma_load_1d_hint(raw[s], text + t * SS_TILE, kBytes, &s_full[s], pol_stream);
+                tma_load_1d_hint(raw[s], text + tile * SS_TILE, kBytes, &s_full[s], pol_stream);
             }
         }
+        return;
     }
 
+    // ===== consumer warps =====
+    ss_warp_smem &ws = s_warp[wid];
+    uint64_t pol_keep = 0;
+    if (FILTER) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    if (lane < 2) { ws.codes[SS_WRUNS + lane] = 0; ws.valid[SS_WRUNS + lane] = 0; }
+    if (lane == 0) ws.valid[SS_WRUNS + 2] = 0;
+
     uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0;
+    uint32_t qn = 0;                                    // deferred table probes queued (warp-uniform)
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % SS_STAGES, parity = (it / SS_STAGES) & 1u;
-        mbar_wait(&s_full[s], parity);
+        const uint32_t s = it % SS_STAGES;
+        mbar_wait(&s_full[s], (it / SS_STAGES) & 1u);
         const uint8_t *rt = raw[s];
         const uint64_t tile_gpos = tile * SS_TILE;
+        const uint32_t run0 = wid * 32u;                // my first run inside the tile
 
-        // ---- phase 1: classify my 32-byte run; line index from the per-warp (1 KiB) index
+        // ---- phase 1: classify my 32 runs (+ 1 halo run, lane 0), line index from my sub_line entry
         {
-            run_bits rb = classify_run(rt + tid * SS_RUN);
+            const uint32_t sub = (uint32_t)tile * (SS_TILE / SS_SUB) + wid;
+            run_bits rb = classify_run(rt + (run0 + lane) * SS_RUN);
             uint32_t c = __popc(rb.nl), inc = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                 if (lane >= (uint32_t)o) inc += x;
             }
-            uint32_t line = sub_line[tile * (SS_TILE / SS_SUB) + wid] + inc - c;
-            uint32_t seqm = seq_line_mask(rb.nl, line, rt, tid * SS_RUN, tile_gpos, text_len, true, n_reads, err);
-            s_codes[tid] = rb.codes;
-            s_valid[tid] = rb.ok & seqm;
-            if (tid < 2) {   // the two halo runs continue into the next tile's first sub-block
-                run_bits hb = classify_run(rt + (SS_THREADS + tid) * SS_RUN);
-                uint32_t hc = __popc(hb.nl);
-                uint32_t h0 = __shfl_sync(0x3u, hc, 0);
-                uint32_t hline = sub_line[(tile + 1) * (SS_TILE / SS_SUB)] + (tid == 1 ? h0 : 0u);
+            uint32_t line = sub_line[sub] + inc - c;
+            uint32_t seqm = seq_line_mask(rb.nl, line, rt, (run0 + lane) * SS_RUN, tile_gpos, text_len, true, n_reads, err);
+            ws.codes[lane] = rb.codes;
+            ws.valid[lane] = rb.ok & seqm;
+            if (lane == 0) {   // halo run: the first run of the next warp's slice / of the next tile
+                run_bits hb = classify_run(rt + (run0 + 32u) * SS_RUN);
                 uint32_t dummy = 0;
-                uint32_t hm = seq_line_mask(hb.nl, hline, rt, (SS_THREADS + tid) * SS_RUN, tile_gpos, text_len, false,
-                                            dummy, err);
-                s_codes[SS_THREADS + tid] = hb.codes;
-                s_valid[SS_THREADS + tid] = hb.ok & hm;
+                uint32_t hm = seq_line_mask(hb.nl, sub_line[sub + 1], rt, (run0 + 32u) * SS_RUN, tile_gpos, text_len,
+                                            false, dummy, err);
+                ws.codes[32] = hb.codes;
+                ws.valid[32] = hb.ok & hm;
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);        // my reads of the raw stage are done
 
-        // the raw stage is consumed: refill it with the tile STAGES rounds ahead
-        if (tid == 0) {
-            uint64_t nt = tile + (uint64_t)SS_STAGES * gridDim.x;
-            if (nt < n_tiles) {
-                fence_proxy_async();
-                mbar_expect_tx(&s_full[s], kBytes);
-                tma_load_1d_hint(raw[s], text + nt * SS_TILE, kBytes, &s_full[s], pol_stream);
-            }
-        }
-
-        // ---- phase 2: warp w owns window starts [1024 w, 1024 w + 1024) = 32 groups of 32 positions.
-        // Lane j first derives the window-valid mask of group j; groups with no valid window are
-        // skipped warp-uniformly, the others are probed with lane = position inside the group.
-        const uint32_t g0 = wid * 32u;
+        // ---- phase 2: 32 groups of 32 window starts; lane j derives the window mask of group j,
+        // empty groups (header / '+' / quality text) are skipped warp-uniformly
         uint32_t my_w;
         {
-            uint64_t V = (uint64_t)s_valid[g0 + lane] | ((uint64_t)s_valid[g0 + lane + 1] << 32);
+            uint64_t V = (uint64_t)ws.valid[lane] | ((uint64_t)ws.valid[lane + 1] << 32);
             my_w = window_mask(V, tv.k);
         }
         uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
         while (nonempty) {
             uint64_t km[UNROLL];
-            uint32_t hh[UNROLL], hl[UNROLL], grp[UNROLL];
+            uint32_t hh[UNROLL], hl[UNROLL];
             bool ok[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                ok[u] = false; grp[u] = 0;
+                ok[u] = false;
+                uint32_t j = 0;
                 if (nonempty) {
-                    uint32_t j = (uint32_t)__ffs(nonempty) - 1u;
+                    j = (uint32_t)__ffs(nonempty) - 1u;
                     nonempty &= nonempty - 1u;
-                    uint32_t w = __shfl_sync(0xFFFFFFFFu, my_w, j);
-                    ok[u] = (w >> lane) & 1u;
-                    grp[u] = g0 + j;
+                    ok[u] = (__shfl_sync(0xFFFFFFFFu, my_w, j) >> lane) & 1u;
                 }
-                uint64_t lo = s_codes[grp[u]], hi = s_codes[grp[u] + 1];
-                uint32_t sh = 2u * lane;
+                uint64_t lo = ws.codes[j], hi = ws.codes[j + 1];
+                const uint32_t sh = 2u * lane;
                 km[u] = ((lo >> sh) | ((hi << 1) << (63u - sh))) & tv.kmask;
-                if (tv.k == 32 && ok[u] && km[u] == SS_EMPTY) {   // poly-T 32-mer: lives outside the table
-                    n_kmers++;
-                    if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
-                    ok[u] = false;
+                if (K32) {
+                    if (ok[u] && km[u] == SS_EMPTY) {   // poly-T 32-mer: lives outside the table
+                        n_kmers++;
+                        if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
+                        ok[u] = false;
+                    }
                 }
                 ss_hash2(km[u], hh[u], hl[u]);
             }
@@ -335,38 +371,52 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
+                    bool pass = false;
                     if (ok[u]) {
                         n_kmers++;
                         uint64_t m = ss_filter_mask(hl[u]);
-                        ok[u] = (fw[u] & m) == m;
+                        pass = (fw[u] & m) == m;
+                    }
+                    // compact the survivors into my warp's queue; probe the table 32 at a time
+                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+                    if (bal) {
+                        if (pass) {
+                            uint32_t p = qn + __popc(bal & lt_mask);
+                            ws.q_key[p] = km[u];
+                            ws.q_bkt[p] = __umulhi(hh[u], (uint32_t)tv.n_buckets);
+                        }
+                        qn += __popc(bal);
+                        __syncwarp();
+                        if (qn >= 32u) {
+                            qn -= 32u;
+                            uint64_t qk = ws.q_key[qn + lane];
+                            uint32_t qb = ws.q_bkt[qn + lane];
+                            n_table++;
+                            table_probe(tv, qk, qb, n_hits, n_second);
+                            __syncwarp();
+                        }
                     }
                 }
-            }
+            } else {
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                if (!ok[u]) continue;
-                if (FILTER) n_table++; else n_kmers++;
-                uint64_t b = (uint64_t)__umulhi(hh[u], (uint32_t)tv.n_buckets);
-                unsigned long long a0, a1, a2, a3;
-                ld_bucket(tv.buckets + b, a0, a1, a2, a3);
-                while (true) {
-                    int f = (a0 == km[u]) ? 0 : (a1 == km[u]) ? 1 : (a2 == km[u]) ? 2 : (a3 == km[u]) ? 3 : -1;
-                    if (f >= 0) {
-                        red_add_u32(tv.slot_cnt + 4 * b + f, 1u);
-                        n_hits++;
-                        break;
-                    }
-                    if (a3 == SS_EMPTY || a2 == SS_EMPTY || a1 == SS_EMPTY || a0 == SS_EMPTY) break;   // miss
-                    b = (b + 1 == tv.n_buckets) ? 0 : b + 1;   // bucket full: next sector
-                    n_second++;
-                    ld_bucket(tv.buckets + b, a0, a1, a2, a3);
+                for (int u = 0; u < UNROLL; u++) {
+                    if (!ok[u]) continue;
+                    n_kmers++;
+                    table_probe(tv, km[u], __umulhi(hh[u], (uint32_t)tv.n_buckets), n_hits, n_second);
                 }
             }
         }
-        __syncthreads();   // codes/valid are rewritten by the next tile's phase 1
+        __syncwarp();   // my codes/valid are rewritten by my next tile's phase 1
+    }
+    if (FILTER) {       // drain the queue
+        __syncwarp();
+        if (lane < qn) {
+            n_table++;
+            table_probe(tv, ws.q_key[lane], ws.q_bkt[lane], n_hits, n_second);
+        }
     }
 
-    // ---- per-CTA statistics
+    // ---- statistics
     unsigned long long st[5] = {n_kmers, n_hits, n_second, n_reads, n_table};
 #pragma unroll
     for (int i = 0; i < 5; i++) {
@@ -549,16 +599,20 @@ __global__ void __launch_bounds__(256) ss_random_gather_kernel(const ss_bucket *
 // ---------------------------------------------------------------------------------------------
 static int g_probe_ctas_per_sm = 0;
 
+#define SS_KERNEL(F, K) ss_probe_kernel<F, K, SS_PROBE_UNROLL, SS_PROBE_MIN_CTAS>
+
 int ss_probe_ctas_per_sm() {
     if (g_probe_ctas_per_sm == 0) {
-        int n = 0, m = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ss_probe_kernel<true, SS_PROBE_UNROLL>, SS_THREADS, 0) !=
-                cudaSuccess || n < 1)
-            n = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, ss_probe_kernel<false, SS_PROBE_UNROLL>, SS_THREADS, 0) !=
-                cudaSuccess || m < 1)
-            m = 1;
-        g_probe_ctas_per_sm = n < m ? n : m;
+        int best = 1 << 30;
+        const void *fns[4] = {(const void *)SS_KERNEL(true, false), (const void *)SS_KERNEL(true, true),
+                              (const void *)SS_KERNEL(false, false), (const void *)SS_KERNEL(false, true)};
+        for (int i = 0; i < 4; i++) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[i], SS_CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+            best = n < best ? n : best;
+        }
+        if (const char *e = getenv("SS_PROBE_CTAS")) { int v = atoi(e); if (v >= 1 && v <= best) best = v; }
+        g_probe_ctas_per_sm = best;
     }
     return g_probe_ctas_per_sm;
 }
@@ -579,10 +633,14 @@ cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_t
                             cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
     uint32_t grid = min(n_tiles, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
-    if (tv.filter)
-        ss_probe_kernel<true, SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
-    else
-        ss_probe_kernel<false, SS_PROBE_UNROLL><<<grid, SS_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    const bool k32 = tv.k == 32;
+    if (tv.filter) {
+        if (k32) SS_KERNEL(true, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+        else SS_KERNEL(true, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    } else {
+        if (k32) SS_KERNEL(false, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+        else SS_KERNEL(false, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    }
     return cudaGetLastError();
 }
 
