@@ -523,7 +523,7 @@ static int finish_reads(ss_ctx *c, ss_reads *r, size_t capacity) {
     size_t need = ss_reads_device_capacity(r->len);
     if (capacity < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
     SS_CUDA(cudaMemsetAsync(r->d_text + r->len, '\n', need - r->len, c->stream));
-    SS_CUDA(cudaMalloc(&r->d_tile_line, (uint64_t)(r->n_tiles + 1) * (SS_TILE / SS_SUB) * sizeof(uint32_t)));
+    SS_CUDA(cudaMalloc(&r->d_tile_line, (uint64_t)(r->n_tiles + 2) * sizeof(uint32_t)));
     SS_CUDA(ss_launch_index(r->d_text, r->n_tiles, r->d_tile_line, 0, c->n_sm, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
     return SS_OK;
@@ -702,7 +702,7 @@ static int ensure_chunks(ss_ctx *c) {
     uint32_t tiles = (uint32_t)(SS_CHUNK_BYTES / SS_TILE) + 2;
     for (int i = 0; i < 2; i++) {
         SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
-        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 1) * (SS_TILE / SS_SUB) * sizeof(uint32_t)));
+        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 2) * sizeof(uint32_t)));
     }
     return SS_OK;
 }

@@ -7,19 +7,19 @@
 #include "../../include/strainscan_b200.h"
 
 // ---- tiling of the FASTQ text ---------------------------------------------------------------
-// A tile owns SS_TILE window-start positions; SS_HALO more bytes are staged with it so that a
-// window that starts in the tile can finish (k-1 <= 31 bytes needed).
-#define SS_TILE     8192
-#define SS_HALO     32                               // >= k-1 bytes after the tile (one more run)
-#define SS_RUN      32                               // text bytes classified per thread
-#define SS_THREADS  (SS_TILE / SS_RUN)               // 256 consumer threads
-#define SS_CONSUMERS (SS_THREADS / 32)               // 8 consumer warps, each owns SS_SUB bytes of a tile
-#define SS_CTA_THREADS (SS_THREADS + 32)             // + 1 producer warp
-#define SS_SUB      1024                             // line-index granularity = one consumer warp's slice
-#define SS_WRUNS    33                               // runs a warp classifies: 32 + 1 halo
+// A unit ("tile") owns SS_TILE window-start positions = 31 runs of 32 bytes; one more run (SS_HALO,
+// >= k-1 bytes) is staged with it so that a window that starts in the unit can finish.  Unit + halo
+// = 1024 bytes = one bulk TMA copy, 32 runs = one classification pass of a warp (lane = run).
+#define SS_RUN      32                               // text bytes classified per lane
+#define SS_TILE     992                              // window starts per unit (31 runs)
+#define SS_HALO     32
+#define SS_SUB      SS_TILE                          // line-index granularity = one unit
+#define SS_WRUNS    32                               // runs classified per unit (31 + halo)
+#define SS_CTA_WARPS 8
+#define SS_CTA_THREADS (SS_CTA_WARPS * 32)
 #define SS_QCAP     (32 + 32)                        // deferred table-probe queue entries per warp
-#define SS_STAGES   3
-#define SS_TEXT_PAD (SS_TILE + 256)                  // '\n' padding after the text on device
+#define SS_STAGES   2                                // per-warp TMA ring depth
+#define SS_TEXT_PAD (8192 + 256)                     // '\n' padding after the text on device
 
 #define SS_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SS_NOSLOT 0xFFFFFFFFu
@@ -35,20 +35,24 @@ __host__ __device__ __forceinline__ uint64_t ss_mix(uint64_t x) {
     return x;
 }
 
-// The probe path's hash: one xorshift-multiply round, split into two 32-bit words.
-//   hi -> table bucket   = mulhi32(hi, n_buckets)
-//   lo -> filter word    = mulhi32(lo, n_filter_words), filter bits from (lo * golden) top bits
-__host__ __device__ __forceinline__ uint64_t ss_mix1(uint64_t x) {
-    x ^= x >> 31; x *= 0xd6e8feb86659fd93ull;
-    return x;
+// The probe path's hash of a packed k-mer (k0 = low 32 bits, k1 = high 32 bits): two 32x32->64
+// multiplies (FMA pipe) folded crosswise.  hh -> table bucket = mulhi32(hh, n_buckets);
+// hl -> filter word = mulhi32(hl, n_filter_words) and the four filter bits.
+#ifdef __CUDACC__
+__device__ __forceinline__ void ss_hash2(uint32_t k0, uint32_t k1, uint32_t &hh, uint32_t &hl) {
+    uint64_t t = (uint64_t)(k0 ^ 0x9E3779B9u) * 0xD6E8FEB9ull;
+    uint64_t u = (uint64_t)(k1 ^ 0x85EBCA6Bu) * 0xC2B2AE35ull;
+    hh = (uint32_t)(t >> 32) ^ (uint32_t)u;
+    hl = (uint32_t)t ^ (uint32_t)(u >> 32);
 }
-// 4 bits of a 64-bit filter word: two in each 32-bit half
-__host__ __device__ __forceinline__ uint64_t ss_filter_mask(uint32_t lo) {
-    uint32_t m = lo * 0x9E3779B1u;
-    uint32_t a = (1u << (m >> 27)) | (1u << ((m >> 22) & 31u));
-    uint32_t b = (1u << ((m >> 17) & 31u)) | (1u << ((m >> 12) & 31u));
-    return (uint64_t)a | ((uint64_t)b << 32);
+// 4 bits of a 64-bit filter word, two in each 32-bit half; bit positions = low 5 bits of four
+// high-half products (shift amounts wrap mod 32)
+__device__ __forceinline__ void ss_filter_mask2(uint32_t hl, uint32_t &ma, uint32_t &mb) {
+    uint32_t p = __umulhi(hl, 0x9E3779B1u), q = __umulhi(hl, 0x85EBCA77u);
+    ma = __funnelshift_l(0u, 1u, p) | __funnelshift_l(0u, 1u, p >> 5);
+    mb = __funnelshift_l(0u, 1u, q) | __funnelshift_l(0u, 1u, q >> 5);
 }
+#endif
 
 struct ss_table_view {
     const ss_bucket *buckets;      // n_buckets x 32 B

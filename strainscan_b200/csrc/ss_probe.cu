@@ -147,13 +147,6 @@ __device__ __forceinline__ uint32_t seq_line_mask(uint32_t nlmask, uint32_t line
     return seqmask;
 }
 
-// hash of a packed k-mer: two 32-bit words (hi -> table bucket, lo -> filter word + bits)
-__device__ __forceinline__ void ss_hash2(uint64_t key, uint32_t &hi, uint32_t &lo) {
-    uint64_t h = ss_mix1(key);
-    hi = (uint32_t)(h >> 32);
-    lo = (uint32_t)h ^ hi;
-}
-
 // ---------------------------------------------------------------------------------------------
 // K1a / K1b: line index at every 1 KiB sub-block start (8 per tile, one per warp of K3)
 // ---------------------------------------------------------------------------------------------
@@ -165,7 +158,8 @@ __global__ void __launch_bounds__(256) ss_nl_count_kernel(const uint8_t *__restr
         const uint4 *p = reinterpret_cast<const uint4 *>(text + (uint64_t)b * SS_SUB);
         uint32_t c = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {   // 64 x 16 B per sub-block: lane takes chunks lane and lane + 32
+        for (int h = 0; h < 2; h++) {   // 62 x 16 B per unit: lane takes chunks lane and lane + 32
+            if (lane + h * 32 >= SS_SUB / 16) break;
             uint4 v = __ldg(p + lane + h * 32);
             c += __popc(~nz7(v.x, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.y, 0x0A0A0A0Au) & 0x80808080u) +
                  __popc(~nz7(v.z, 0x0A0A0A0Au) & 0x80808080u) + __popc(~nz7(v.w, 0x0A0A0A0Au) & 0x80808080u);
@@ -199,11 +193,11 @@ __global__ void __launch_bounds__(1024) ss_scan_kernel(uint32_t *__restrict__ v,
 // ---------------------------------------------------------------------------------------------
 // K3: fused scan / encode / filter / probe / count
 //
-// CTA = 8 autonomous consumer warps + 1 producer warp.  The producer streams 8 KiB text tiles into a
-// shared-memory ring with 1-D bulk TMA (full/empty mbarriers).  Consumer warp w owns bytes
-// [1024 w, 1024 w + 1024) of every tile (+ 32 bytes of halo): it classifies them, keeps its 2-bit
-// codes / valid bits in its own shared-memory slice, releases the raw stage, and probes its own
-// window starts -- no CTA-wide barrier anywhere in the loop.
+// Every WARP is an autonomous pipeline over 992-byte text units (31 runs of 32 bytes + one halo run
+// = one 1024-byte bulk TMA copy): it prefetches its own units into its own shared-memory ring
+// (lane 0 issues cp.async.bulk, completion on the warp's own mbarriers), classifies the 32 runs in
+// ONE pass (lane = run), keeps the 2-bit codes / valid bits in its own slice, and probes its own
+// window starts.  No CTA-wide barrier, no cross-warp coupling: warps never wait for each other.
 // ---------------------------------------------------------------------------------------------
 // bit L of the result = bytes p+L .. p+L+k-1 are all valid, for V = valid bits of bytes p .. p+63
 __device__ __forceinline__ uint32_t window_mask(uint64_t V, int k) {
@@ -217,15 +211,13 @@ __device__ __forceinline__ uint32_t window_mask(uint64_t V, int k) {
     return (uint32_t)R;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-struct ss_warp_smem {
-    uint64_t codes[SS_WRUNS + 2];        // 2-bit codes of my 33 runs (+ zero pad)
-    uint32_t valid[SS_WRUNS + 3];        // valid bits of my 33 runs (+ zero pad)
-    uint64_t q_key[SS_QCAP];             // deferred table probes: k-mer
-    uint32_t q_bkt[SS_QCAP];             //                        home bucket
+struct __align__(16) ss_warp_smem {
+    uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];   // 1024-byte units
+    uint32_t codes[2 * SS_WRUNS + 4];            // 2-bit codes of my 32 runs, 2 words per run (+ zero pad)
+    uint32_t valid[SS_WRUNS + 2];                // valid bits of my 32 runs (+ zero pad)
+    uint64_t q_key[SS_QCAP];                     // deferred table probes: k-mer
+    uint32_t q_bkt[SS_QCAP];                     //                        home bucket
+    uint64_t full[SS_STAGES];                    // my mbarriers
 };
 
 // exact table probe of one k-mer (one 32-byte sector, next sector only when the bucket is full)
@@ -250,96 +242,88 @@ __device__ __forceinline__ void table_probe(const ss_table_view &tv, uint64_t km
 
 template <bool FILTER, bool K32, int UNROLL, int MINCTAS>
 __global__ void __launch_bounds__(SS_CTA_THREADS, MINCTAS)
-ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_tiles,
+ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_units,
                 const uint32_t *__restrict__ sub_line, ss_table_view tv,
                 unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
-    __shared__ __align__(128) uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];
-    __shared__ __align__(16) ss_warp_smem s_warp[SS_CONSUMERS];
-    __shared__ __align__(8) uint64_t s_full[SS_STAGES];
-    __shared__ __align__(8) uint64_t s_empty[SS_STAGES];
+    __shared__ ss_warp_smem s_warp[SS_CTA_WARPS];
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint64_t gw = (uint64_t)blockIdx.x * SS_CTA_WARPS + wid;      // my global warp id
+    const uint64_t nw = (uint64_t)gridDim.x * SS_CTA_WARPS;            // unit stride
     constexpr uint32_t kBytes = SS_TILE + SS_HALO;
+    ss_warp_smem &ws = s_warp[wid];
 
-    if (tid == 0) {
+    uint64_t pol_stream = 0, pol_keep = 0;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    if (FILTER) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < SS_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], SS_CONSUMERS); }
+        for (int s = 0; s < SS_STAGES; s++) mbar_init(&ws.full[s], 1);
         fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (wid == SS_CONSUMERS) {
-        // ===== producer warp: one elected lane feeds the ring =====
-        if (lane == 0) {
-            uint64_t pol_stream;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-            uint32_t it = 0;
-            for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % SS_STAGES;
-                if (it >= SS_STAGES) mbar_wait(&s_empty[s], ((it / SS_STAGES) - 1u) & 1u);   // all 8 warps released it
-                mbar_expect_tx(&s_full[s], kBytes);
-                tma_load_1d_hint(raw[s], text + tile * SS_TILE, kBytes, &s_full[s], pol_stream);
+#pragma unroll
+        for (int s = 0; s < SS_STAGES; s++) {
+            uint64_t u = gw + (uint64_t)s * nw;
+            if (u < n_units) {
+                mbar_expect_tx(&ws.full[s], kBytes);
+                tma_load_1d_hint(ws.raw[s], text + u * SS_TILE, kBytes, &ws.full[s], pol_stream);
             }
         }
-        return;
     }
-
-    // ===== consumer warps =====
-    ss_warp_smem &ws = s_warp[wid];
-    uint64_t pol_keep = 0;
-    if (FILTER) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-    if (lane < 2) { ws.codes[SS_WRUNS + lane] = 0; ws.valid[SS_WRUNS + lane] = 0; }
-    if (lane == 0) ws.valid[SS_WRUNS + 2] = 0;
+    // zero pad behind the 32 runs (read by the last groups' funnel shifts / window masks)
+    if (lane < 4) ws.codes[2 * SS_WRUNS + lane] = 0;
+    if (lane < 2) ws.valid[SS_WRUNS + lane] = 0;
+    __syncwarp();
 
     uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0;
     uint32_t qn = 0;                                    // deferred table probes queued (warp-uniform)
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t half = lane >> 4;                    // which 32-bit word my window starts in
+    const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside it
+    const uint32_t khi_mask = (uint32_t)(tv.kmask >> 32), klo_mask = (uint32_t)tv.kmask;
 
     uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint64_t unit = gw; unit < n_units; unit += nw, ++it) {
         const uint32_t s = it % SS_STAGES;
-        mbar_wait(&s_full[s], (it / SS_STAGES) & 1u);
-        const uint8_t *rt = raw[s];
-        const uint64_t tile_gpos = tile * SS_TILE;
-        const uint32_t run0 = wid * 32u;                // my first run inside the tile
+        mbar_wait(&ws.full[s], (it / SS_STAGES) & 1u);
+        const uint8_t *rt = ws.raw[s];
 
-        // ---- phase 1: classify my 32 runs (+ 1 halo run, lane 0), line index from my sub_line entry
+        // ---- phase 1: lane = run (31 own runs + the halo run), one pass
         {
-            const uint32_t sub = (uint32_t)tile * (SS_TILE / SS_SUB) + wid;
-            run_bits rb = classify_run(rt + (run0 + lane) * SS_RUN);
+            run_bits rb = classify_run(rt + lane * SS_RUN);
             uint32_t c = __popc(rb.nl), inc = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                 if (lane >= (uint32_t)o) inc += x;
             }
-            uint32_t line = sub_line[sub] + inc - c;
-            uint32_t seqm = seq_line_mask(rb.nl, line, rt, (run0 + lane) * SS_RUN, tile_gpos, text_len, true, n_reads, err);
-            ws.codes[lane] = rb.codes;
+            uint32_t line = sub_line[unit] + inc - c;
+            uint32_t seqm = seq_line_mask(rb.nl, line, rt, lane * SS_RUN, unit * SS_TILE, text_len, lane < 31u, n_reads, err);
+            ws.codes[2 * lane] = (uint32_t)rb.codes;
+            ws.codes[2 * lane + 1] = (uint32_t)(rb.codes >> 32);
             ws.valid[lane] = rb.ok & seqm;
-            if (lane == 0) {   // halo run: the first run of the next warp's slice / of the next tile
-                run_bits hb = classify_run(rt + (run0 + 32u) * SS_RUN);
-                uint32_t dummy = 0;
-                uint32_t hm = seq_line_mask(hb.nl, sub_line[sub + 1], rt, (run0 + 32u) * SS_RUN, tile_gpos, text_len,
-                                            false, dummy, err);
-                ws.codes[32] = hb.codes;
-                ws.valid[32] = hb.ok & hm;
-            }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[s]);        // my reads of the raw stage are done
+        if (lane == 0) {   // the raw stage is consumed: prefetch the unit SS_STAGES rounds ahead into it
+            uint64_t nu = unit + (uint64_t)SS_STAGES * nw;
+            if (nu < n_units) {
+                fence_proxy_async();
+                mbar_expect_tx(&ws.full[s], kBytes);
+                tma_load_1d_hint(ws.raw[s], text + nu * SS_TILE, kBytes, &ws.full[s], pol_stream);
+            }
+        }
 
-        // ---- phase 2: 32 groups of 32 window starts; lane j derives the window mask of group j,
+        // ---- phase 2: 31 groups of 32 window starts; lane j derives the window mask of group j,
         // empty groups (header / '+' / quality text) are skipped warp-uniformly
-        uint32_t my_w;
-        {
+        uint32_t my_w = 0;
+        if (lane < 31u) {
             uint64_t V = (uint64_t)ws.valid[lane] | ((uint64_t)ws.valid[lane + 1] << 32);
             my_w = window_mask(V, tv.k);
+            n_kmers += __popc(my_w);
         }
         uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
         while (nonempty) {
-            uint64_t km[UNROLL];
-            uint32_t hh[UNROLL], hl[UNROLL];
+            uint32_t k0[UNROLL], k1[UNROLL], hh[UNROLL], hl[UNROLL];
             bool ok[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
@@ -350,17 +334,18 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                     nonempty &= nonempty - 1u;
                     ok[u] = (__shfl_sync(0xFFFFFFFFu, my_w, j) >> lane) & 1u;
                 }
-                uint64_t lo = ws.codes[j], hi = ws.codes[j + 1];
-                const uint32_t sh = 2u * lane;
-                km[u] = ((lo >> sh) | ((hi << 1) << (63u - sh))) & tv.kmask;
+                // my window = 2k bits starting at bit 2*lane of the group's codes: three 32-bit words
+                const uint32_t *cw = ws.codes + 2u * j + half;
+                uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2];
+                k0[u] = __funnelshift_r(w0, w1, fsh) & klo_mask;
+                k1[u] = __funnelshift_r(w1, w2, fsh) & khi_mask;
                 if (K32) {
-                    if (ok[u] && km[u] == SS_EMPTY) {   // poly-T 32-mer: lives outside the table
-                        n_kmers++;
+                    if (ok[u] && (k0[u] & k1[u]) == 0xFFFFFFFFu) {   // poly-T 32-mer: lives outside the table
                         if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
                         ok[u] = false;
                     }
                 }
-                ss_hash2(km[u], hh[u], hl[u]);
+                ss_hash2(k0[u], k1[u], hh[u], hl[u]);
             }
             if (FILTER) {
                 uint64_t fw[UNROLL];
@@ -373,16 +358,16 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                 for (int u = 0; u < UNROLL; u++) {
                     bool pass = false;
                     if (ok[u]) {
-                        n_kmers++;
-                        uint64_t m = ss_filter_mask(hl[u]);
-                        pass = (fw[u] & m) == m;
+                        uint32_t ma, mb;
+                        ss_filter_mask2(hl[u], ma, mb);
+                        pass = (((uint32_t)fw[u] & ma) == ma) & (((uint32_t)(fw[u] >> 32) & mb) == mb);
                     }
                     // compact the survivors into my warp's queue; probe the table 32 at a time
                     uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
                     if (bal) {
                         if (pass) {
                             uint32_t p = qn + __popc(bal & lt_mask);
-                            ws.q_key[p] = km[u];
+                            ws.q_key[p] = (uint64_t)k0[u] | ((uint64_t)k1[u] << 32);
                             ws.q_bkt[p] = __umulhi(hh[u], (uint32_t)tv.n_buckets);
                         }
                         qn += __popc(bal);
@@ -401,12 +386,12 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     if (!ok[u]) continue;
-                    n_kmers++;
-                    table_probe(tv, km[u], __umulhi(hh[u], (uint32_t)tv.n_buckets), n_hits, n_second);
+                    table_probe(tv, (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), __umulhi(hh[u], (uint32_t)tv.n_buckets),
+                                n_hits, n_second);
                 }
             }
         }
-        __syncwarp();   // my codes/valid are rewritten by my next tile's phase 1
+        __syncwarp();   // my codes/valid are rewritten by my next unit's phase 1
     }
     if (FILTER) {       // drain the queue
         __syncwarp();
@@ -443,7 +428,9 @@ __global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_
     if (key == SS_EMPTY) {                      // k = 32 poly-T
         slot = 4 * n_buckets;               // counted as distinct by the host
     } else {
-        uint64_t b = (uint64_t)__umulhi((uint32_t)(ss_mix1(key) >> 32), (uint32_t)n_buckets);
+        uint32_t hh, hl;
+        ss_hash2((uint32_t)key, (uint32_t)(key >> 32), hh, hl);
+        uint64_t b = (uint64_t)__umulhi(hh, (uint32_t)n_buckets);
         while (true) {
             bool done = false;
 #pragma unroll
@@ -469,9 +456,10 @@ __global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const 
                                        unsigned long long *__restrict__ filter, uint32_t n_words) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !rec_ok[i] || keys[i] == SS_EMPTY) return;
-    uint64_t h = ss_mix1(keys[i]);
-    uint32_t hi = (uint32_t)(h >> 32), lo = (uint32_t)h ^ hi;
-    atomicOr(filter + __umulhi(lo, n_words), (unsigned long long)ss_filter_mask(lo));
+    uint32_t hh, hl, ma, mb;
+    ss_hash2((uint32_t)keys[i], (uint32_t)(keys[i] >> 32), hh, hl);
+    ss_filter_mask2(hl, ma, mb);
+    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ma | ((unsigned long long)mb << 32));
 }
 
 // flags[i] |= IS_LAST where record i is the highest ordinal stored at its slot
@@ -621,7 +609,7 @@ int ss_probe_ctas_per_sm() {
 cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *sub_line, uint32_t line_base,
                             int n_sm, cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
-    uint32_t n_sub = (n_tiles + 1) * (SS_TILE / SS_SUB);
+    uint32_t n_sub = n_tiles + 1;
     uint32_t grid = min((n_sub + 7u) / 8u, (uint32_t)n_sm * 8u);
     ss_nl_count_kernel<<<grid, 256, 0, st>>>(text, n_sub, sub_line);
     ss_scan_kernel<<<1, 1024, 0, st>>>(sub_line, n_sub, line_base);
@@ -632,7 +620,7 @@ cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_t
                             const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
                             cudaStream_t st) {
     if (n_tiles == 0) return cudaSuccess;
-    uint32_t grid = min(n_tiles, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
+    uint32_t grid = min((n_tiles + SS_CTA_WARPS - 1) / SS_CTA_WARPS, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
     const bool k32 = tv.k == 32;
     if (tv.filter) {
         if (k32) SS_KERNEL(true, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
