@@ -1,0 +1,52 @@
+"""End-to-end report parity: the reference's own StrainScan.py host code (baseline/_ref, unmodified
+apart from the two documented call-site edits of INTEGRATION.md, applied at import time by
+baseline/run_pipeline.py) driven by the CUDA counts must write final_report.txt,
+C*/StrainVote.report and strain_prob.txt BYTE-IDENTICAL to the reference run with its bundled
+jellyfish-linux (golden reports in tests/golden/pipeline/, made by tests/golden/make_pipeline_golden.py).
+
+Covers single-end / paired-end + gz, two clusters, two strains in one cluster (ElasticNet path),
+an all-singleton result, -l 2 -b 1 (low depth + probability report) and -e 1 (extraRegion_mode).
+Needs baseline/_ref (git-ignored, travels to the GPU box with gpurun); skipped when it is absent."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from tests import synth_db  # noqa: E402
+import make_pipeline_golden as mpg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+HAVE_REF = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "library"))
+
+
+@pytest.fixture(scope="module")
+def db_dir(tmp_path_factory):
+    return synth_db.SynthDB().write(str(tmp_path_factory.mktemp("db") / "DB"))
+
+
+def _golden(name):
+    base = os.path.join(ROOT, "tests", "golden", "pipeline", name)
+    return mpg.collect_reports(base)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not present (python baseline/setup_ref.py)")
+@pytest.mark.parametrize("name", sorted(synth_db.CASES))
+def test_reports_byte_identical_to_reference(name, db_dir, tmp_path):
+    gold = _golden(name)
+    assert "final_report.txt" in gold, "golden reports missing for %s" % name
+    got, log = mpg.run_case("b200", db_dir, name, str(tmp_path))
+    assert sorted(got) == sorted(gold), log[-2000:]
+    for rel in gold:
+        assert got[rel] == gold[rel], "%s/%s differs\n--- reference\n%s\n--- b200\n%s" % (
+            name, rel, gold[rel].decode(), got[rel].decode())
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not present")
+def test_live_reference_matches_golden(db_dir, tmp_path):
+    """The committed goldens are what the reference engine produces on this box too."""
+    if not os.access(os.path.join(ROOT, "baseline", "_ref", "library", "jellyfish-linux"), os.X_OK):
+        pytest.skip("bundled engine not executable here")
+    got, log = mpg.run_case("reference", db_dir, "two_clusters_se", str(tmp_path))
+    assert got == _golden("two_clusters_se"), log[-2000:]
