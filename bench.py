@@ -428,7 +428,8 @@ def main():
                        "text_bytes_per_gpu": n_bytes, "reads_total": tot_reads,
                        "l2": "inputs exceed L2: %.2f GB text + %.2f GB table per GPU vs 126 MB" % (
                            n_bytes / 1e9, kset.table_bytes / 1e9),
-                       "hit_rate": h, "second_sector_rate": p2, "db_build_s": t_db, "seed": args.seed,
+                       "hit_rate": h, "second_sector_rate": p2,
+                       "table_probe_rate": st.n_table_probes / max(st.n_kmers, 1), "db_build_s": t_db, "seed": args.seed,
                        "collective": "NCCL all-reduce(sum) of the dense int32 count vector" if world > 1 else "none (1 GPU)"},
             "reads_per_s": tot_reads / (ms_per_step * 1e-3),
             "wall_ms_per_step": float(t[1]) / args.steps,

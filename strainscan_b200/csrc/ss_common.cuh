@@ -17,8 +17,13 @@
 #define SS_WRUNS    32                               // runs classified per unit (31 + halo)
 #define SS_CTA_WARPS 8
 #define SS_CTA_THREADS (SS_CTA_WARPS * 32)
-#define SS_QCAP     (32 + 32)                        // deferred table-probe queue entries per warp
-#define SS_STAGES   2                                // per-warp TMA ring depth
+#ifndef SS_PROBE_UNROLL
+#define SS_PROBE_UNROLL 3                                // groups (filter / table probes) in flight per warp iteration
+#endif
+#define SS_QCAP     (32 + 32 * SS_PROBE_UNROLL)          // deferred table-probe queue entries per warp
+#ifndef SS_STAGES
+#define SS_STAGES   1                                // per-warp TMA ring depth: the next unit is requested right after
+#endif                                               // classification and lands during the (long) probe phase
 #define SS_TEXT_PAD (8192 + 256)                     // '\n' padding after the text on device
 
 #define SS_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -39,18 +44,23 @@ __host__ __device__ __forceinline__ uint64_t ss_mix(uint64_t x) {
 // multiplies (FMA pipe) folded crosswise.  hh -> table bucket = mulhi32(hh, n_buckets);
 // hl -> filter word = mulhi32(hl, n_filter_words) and the four filter bits.
 #ifdef __CUDACC__
+// two chained 32x32+64 multiply-adds (IMAD.WIDE, FMA pipe; no ALU-pipe work): the second folds the
+// first product in with its halves swapped, so both output words depend on every key bit
 __device__ __forceinline__ void ss_hash2(uint32_t k0, uint32_t k1, uint32_t &hh, uint32_t &hl) {
-    uint64_t t = (uint64_t)(k0 ^ 0x9E3779B9u) * 0xD6E8FEB9ull;
-    uint64_t u = (uint64_t)(k1 ^ 0x85EBCA6Bu) * 0xC2B2AE35ull;
-    hh = (uint32_t)(t >> 32) ^ (uint32_t)u;
-    hl = (uint32_t)t ^ (uint32_t)(u >> 32);
+    uint64_t t = (uint64_t)k0 * 0xD6E8FEB9ull + 0x9E3779B97F4A7C15ull;
+    uint64_t u = (uint64_t)k1 * 0xC2B2AE35ull + ((t << 32) | (t >> 32));
+    hh = (uint32_t)u;
+    hl = (uint32_t)(u >> 32);
 }
-// 4 bits of a 64-bit filter word, two in each 32-bit half; bit positions = low 5 bits of four
-// high-half products (shift amounts wrap mod 32)
-__device__ __forceinline__ void ss_filter_mask2(uint32_t hl, uint32_t &ma, uint32_t &mb) {
-    uint32_t p = __umulhi(hl, 0x9E3779B1u), q = __umulhi(hl, 0x85EBCA77u);
-    ma = __funnelshift_l(0u, 1u, p) | __funnelshift_l(0u, 1u, p >> 5);
-    mb = __funnelshift_l(0u, 1u, q) | __funnelshift_l(0u, 1u, q >> 5);
+// Pattern-based blocked Bloom filter: a key sets the 4 bits of pattern (hl mod SS_NPAT) in its 64-bit
+// word; the probe kernel keeps the SS_NPAT patterns in shared memory (one LDS instead of ~8 ALU ops).
+#define SS_NPAT 1024
+__device__ __forceinline__ uint64_t ss_filter_pattern(uint32_t i) {
+    uint32_t x = (i + 1u) * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+    uint32_t a = (1u << (x & 31u)) | (1u << ((x >> 5) & 31u));
+    uint32_t b = (1u << ((x >> 10) & 31u)) | (1u << ((x >> 15) & 31u));
+    return (uint64_t)a | ((uint64_t)b << 32);
 }
 #endif
 

@@ -2,11 +2,8 @@
 #pragma once
 #include "ss_common.cuh"
 
-#ifndef SS_PROBE_UNROLL
-#define SS_PROBE_UNROLL 4        // groups (filter / table probes) in flight per warp iteration
-#endif
 #ifndef SS_PROBE_MIN_CTAS
-#define SS_PROBE_MIN_CTAS 4      // __launch_bounds__ min CTAs/SM (256 threads each)
+#define SS_PROBE_MIN_CTAS 5      // __launch_bounds__ min CTAs/SM (256 threads each)
 #endif
 
 int ss_probe_ctas_per_sm();

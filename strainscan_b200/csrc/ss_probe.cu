@@ -215,15 +215,18 @@ struct __align__(16) ss_warp_smem {
     uint8_t raw[SS_STAGES][SS_TILE + SS_HALO];   // 1024-byte units
     uint32_t codes[2 * SS_WRUNS + 4];            // 2-bit codes of my 32 runs, 2 words per run (+ zero pad)
     uint32_t valid[SS_WRUNS + 2];                // valid bits of my 32 runs (+ zero pad)
-    uint64_t q_key[SS_QCAP];                     // deferred table probes: k-mer
-    uint32_t q_bkt[SS_QCAP];                     //                        home bucket
+    uint64_t q_key[SS_QCAP];                     // deferred table probes: the k-mers that passed the filter
+    uint32_t g_mask[32 + 8];                     // window masks of the non-empty groups of the unit
+    uint32_t g_off[32 + 8];                      // their word offsets into codes
     uint64_t full[SS_STAGES];                    // my mbarriers
+    uint32_t qn, pad_;                           // queued survivors
 };
 
 // exact table probe of one k-mer (one 32-byte sector, next sector only when the bucket is full)
-__device__ __forceinline__ void table_probe(const ss_table_view &tv, uint64_t km, uint32_t bucket, uint32_t &n_hits,
-                                            uint32_t &n_second) {
-    uint64_t b = bucket;
+__device__ __forceinline__ void table_probe(const ss_table_view &tv, uint64_t km, uint32_t &n_hits, uint32_t &n_second) {
+    uint32_t hh, hl;
+    ss_hash2((uint32_t)km, (uint32_t)(km >> 32), hh, hl);
+    uint64_t b = __umulhi(hh, (uint32_t)tv.n_buckets);
     unsigned long long a0, a1, a2, a3;
     ld_bucket(tv.buckets + b, a0, a1, a2, a3);
     while (true) {
@@ -245,7 +248,13 @@ __global__ void __launch_bounds__(SS_CTA_THREADS, MINCTAS)
 ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_units,
                 const uint32_t *__restrict__ sub_line, ss_table_view tv,
                 unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
+    static_assert(32 + 32 * UNROLL <= SS_QCAP, "survivor queue too small for this UNROLL");
     __shared__ ss_warp_smem s_warp[SS_CTA_WARPS];
+    __shared__ uint64_t s_pat[FILTER ? SS_NPAT : 1];     // filter bit patterns (4 bits of a 64-bit word)
+    if (FILTER) {
+        for (uint32_t i = threadIdx.x; i < SS_NPAT; i += SS_CTA_THREADS) s_pat[i] = ss_filter_pattern(i);
+        __syncthreads();
+    }
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint64_t gw = (uint64_t)blockIdx.x * SS_CTA_WARPS + wid;      // my global warp id
@@ -273,10 +282,10 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
     // zero pad behind the 32 runs (read by the last groups' funnel shifts / window masks)
     if (lane < 4) ws.codes[2 * SS_WRUNS + lane] = 0;
     if (lane < 2) ws.valid[SS_WRUNS + lane] = 0;
+    if (lane == 0) ws.qn = 0;
     __syncwarp();
 
     uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0;
-    uint32_t qn = 0;                                    // deferred table probes queued (warp-uniform)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t half = lane >> 4;                    // which 32-bit word my window starts in
     const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside it
@@ -313,29 +322,34 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
             }
         }
 
-        // ---- phase 2: 31 groups of 32 window starts; lane j derives the window mask of group j,
-        // empty groups (header / '+' / quality text) are skipped warp-uniformly
-        uint32_t my_w = 0;
-        if (lane < 31u) {
-            uint64_t V = (uint64_t)ws.valid[lane] | ((uint64_t)ws.valid[lane + 1] << 32);
-            my_w = window_mask(V, tv.k);
-            n_kmers += __popc(my_w);
+        // ---- phase 2: 31 groups of 32 window starts; lane j derives the window mask of group j and
+        // the non-empty groups (header / '+' / quality text has none) are listed in shared memory
+        uint32_t n_groups;
+        {
+            uint32_t my_w = 0;
+            if (lane < 31u) {
+                uint64_t V = (uint64_t)ws.valid[lane] | ((uint64_t)ws.valid[lane + 1] << 32);
+                my_w = window_mask(V, tv.k);
+                n_kmers += __popc(my_w);
+            }
+            uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
+            n_groups = __popc(nonempty);
+            if (my_w) {
+                uint32_t r = __popc(nonempty & lt_mask);
+                ws.g_mask[r] = my_w;
+                ws.g_off[r] = 2u * lane;              // word offset of the group's codes
+            }
+            if (lane < UNROLL) { ws.g_mask[n_groups + lane] = 0; ws.g_off[n_groups + lane] = 0; }
+            __syncwarp();
         }
-        uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
-        while (nonempty) {
+        for (uint32_t g = 0; g < n_groups; g += UNROLL) {
             uint32_t k0[UNROLL], k1[UNROLL], hh[UNROLL], hl[UNROLL];
             bool ok[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                ok[u] = false;
-                uint32_t j = 0;
-                if (nonempty) {
-                    j = (uint32_t)__ffs(nonempty) - 1u;
-                    nonempty &= nonempty - 1u;
-                    ok[u] = (__shfl_sync(0xFFFFFFFFu, my_w, j) >> lane) & 1u;
-                }
+                ok[u] = (ws.g_mask[g + u] >> lane) & 1u;
                 // my window = 2k bits starting at bit 2*lane of the group's codes: three 32-bit words
-                const uint32_t *cw = ws.codes + 2u * j + half;
+                const uint32_t *cw = ws.codes + ws.g_off[g + u] + half;
                 uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2];
                 k0[u] = __funnelshift_r(w0, w1, fsh) & klo_mask;
                 k1[u] = __funnelshift_r(w1, w2, fsh) & khi_mask;
@@ -354,40 +368,37 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                     fw[u] = 0ull;
                     if (ok[u]) fw[u] = ld_filter(tv.filter + __umulhi(hl[u], tv.n_filter_words), pol_keep);
                 }
+                bool pass[UNROLL], any = false;
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    bool pass = false;
-                    if (ok[u]) {
-                        uint32_t ma, mb;
-                        ss_filter_mask2(hl[u], ma, mb);
-                        pass = (((uint32_t)fw[u] & ma) == ma) & (((uint32_t)(fw[u] >> 32) & mb) == mb);
-                    }
-                    // compact the survivors into my warp's queue; probe the table 32 at a time
-                    uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-                    if (bal) {
-                        if (pass) {
-                            uint32_t p = qn + __popc(bal & lt_mask);
-                            ws.q_key[p] = (uint64_t)k0[u] | ((uint64_t)k1[u] << 32);
-                            ws.q_bkt[p] = __umulhi(hh[u], (uint32_t)tv.n_buckets);
-                        }
-                        qn += __popc(bal);
-                        __syncwarp();
-                        if (qn >= 32u) {
-                            qn -= 32u;
-                            uint64_t qk = ws.q_key[qn + lane];
-                            uint32_t qb = ws.q_bkt[qn + lane];
-                            n_table++;
-                            table_probe(tv, qk, qb, n_hits, n_second);
-                            __syncwarp();
+                    uint64_t m = s_pat[hl[u] & (SS_NPAT - 1)];
+                    pass[u] = ok[u] && (fw[u] & m) == m;
+                    any |= pass[u];
+                }
+                if (any) {                              // rare per lane: queue survivors for an exact table probe
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        if (pass[u]) {
+                            uint32_t p = atomicAdd(&ws.qn, 1u);
+                            ws.q_key[p] = (uint64_t)k0[u] | ((uint64_t)k1[u] << 32);   // re-hashed at probe time
                         }
                     }
+                }
+                __syncwarp();
+                uint32_t qn = ws.qn;                    // <= 31 + 32 * UNROLL
+                while (qn >= 32u) {                     // probe the table 32 survivors at a time
+                    qn -= 32u;
+                    n_table++;
+                    table_probe(tv, ws.q_key[qn + lane], n_hits, n_second);
+                    __syncwarp();
+                    if (lane == 0) ws.qn = qn;
+                    __syncwarp();
                 }
             } else {
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     if (!ok[u]) continue;
-                    table_probe(tv, (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), __umulhi(hh[u], (uint32_t)tv.n_buckets),
-                                n_hits, n_second);
+                    table_probe(tv, (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), n_hits, n_second);
                 }
             }
         }
@@ -395,9 +406,9 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
     }
     if (FILTER) {       // drain the queue
         __syncwarp();
-        if (lane < qn) {
+        if (lane < ws.qn) {
             n_table++;
-            table_probe(tv, ws.q_key[lane], ws.q_bkt[lane], n_hits, n_second);
+            table_probe(tv, ws.q_key[lane], n_hits, n_second);
         }
     }
 
@@ -456,10 +467,9 @@ __global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const 
                                        unsigned long long *__restrict__ filter, uint32_t n_words) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !rec_ok[i] || keys[i] == SS_EMPTY) return;
-    uint32_t hh, hl, ma, mb;
+    uint32_t hh, hl;
     ss_hash2((uint32_t)keys[i], (uint32_t)(keys[i] >> 32), hh, hl);
-    ss_filter_mask2(hl, ma, mb);
-    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ma | ((unsigned long long)mb << 32));
+    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
 }
 
 // flags[i] |= IS_LAST where record i is the highest ordinal stored at its slot
@@ -596,6 +606,13 @@ int ss_probe_ctas_per_sm() {
                               (const void *)SS_KERNEL(false, false), (const void *)SS_KERNEL(false, true)};
         for (int i = 0; i < 4; i++) {
             int n = 0;
+            // shared-memory carve-out (percent of 228 KB).  The rest of the 256 KB is L1, whose lines are the
+            // landing slots of the in-flight filter loads: a kernel that takes all of it for shared memory
+            // loses its memory-level parallelism (measured: 1.6e11 -> 1.0e11 k-mers/s at 100 %).
+            if (const char *e = getenv("SS_CARVEOUT")) {
+                int pct = atoi(e);
+                if (pct >= 0 && pct <= 100) cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            }
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[i], SS_CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
             best = n < best ? n : best;
         }
