@@ -111,6 +111,12 @@ int ss_reads_from_files(ss_ctx *ctx, const char *const *paths, int n_paths, int 
  * opens with '+' (a quality line may open with '@'; its line + 2 is a sequence line).  The ranges
  * of all shards partition [0, len).  Used by ss_reads_from_files / ss_count_files. */
 int ss_fastq_shard_range(const char *buf, size_t len, int shard, int n_shards, size_t *lo, size_t *hi);
+/* Host-only helper (no GPU needed): run the read-file ingest that feeds ss_reads_from_files /
+ * ss_count_files -- producer threads, the library's own gzip inflate (replaces the `zcat a b |` of
+ * identify.py:82), record-aligned chunking, sharding -- and write the delivered chunks back to back
+ * into `out` (chunk order is arbitrary; every chunk holds whole records).  out may be NULL to size. */
+int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n_shards, size_t chunk_bytes,
+                         int n_threads, char *out, size_t out_cap, size_t *out_len, uint32_t *n_chunks);
 /* Same from in-memory FASTQ text (each buffer = one file's uncompressed contents). */
 int ss_reads_from_host(ss_ctx *ctx, const char *const *bufs, const size_t *lens, int n_bufs,
                        ss_reads **reads);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "ss_kmerset_header_ids": (C.c_int, [_P, _P]),
     "ss_reads_from_files": (C.c_int, [_P, _CSTRS, C.c_int, C.c_int, C.c_int, _PP]),
     "ss_fastq_shard_range": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _SIZES, _SIZES]),
+    "ss_ingest_files_host": (C.c_int, [_CSTRS, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, C.c_size_t, _SIZES,
+                                       C.POINTER(C.c_uint32)]),
     "ss_reads_from_host": (C.c_int, [_P, _CSTRS, _SIZES, C.c_int, _PP]),
     "ss_reads_from_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _PP]),
     "ss_reads_device_capacity": (C.c_size_t, [C.c_size_t]),

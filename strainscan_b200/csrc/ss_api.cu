@@ -4,8 +4,6 @@
 // Replaces the process/file protocol around library/jellyfish-linux at
 //   library/identify.py:73-103, library/identify_low_mem.py:67-90, library/identify_low_depth.py:46-74,
 //   library/Vote_Strain_L2_Lasso_new_sp.py:354-403.
-#include <zlib.h>
-
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -17,8 +15,10 @@
 #include <vector>
 
 #include "ss_common.cuh"
+#include "ss_ingest.cuh"
 #include "ss_kernels.cuh"
 #include "ss_synth.cuh"
+#include "ss_inflate.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -41,7 +41,9 @@ static double now_ms() {
 // ---------------------------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------------------------
-#define SS_CHUNK_BYTES (64ull << 20)   // streaming chunk of FASTQ text (host -> device)
+#define SS_CHUNK_DEFAULT (32ull << 20)   // streaming chunk of FASTQ text (host -> device); env SS_CHUNK_BYTES
+#define SS_SEG_DEFAULT (1ull << 30)      // read-cache segment when the total size is unknown (gzip); env SS_SEG_BYTES
+#define SS_NPEND 4                       // host chunks whose H2D copy may be in flight
 
 struct ss_ctx {
     int device = 0;
@@ -58,6 +60,9 @@ struct ss_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint8_t *h_pinned[2] = {nullptr, nullptr};   // staging for pageable sources
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    size_t chunk_bytes = SS_CHUNK_DEFAULT, seg_bytes = SS_SEG_DEFAULT;
+    ss_text_source *src = nullptr;               // file ingest: producer threads + pinned chunk pool (lazy)
+    cudaEvent_t ev_pend[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ss_kmerset {
@@ -85,13 +90,19 @@ struct ss_kmerset {
     }
 };
 
-struct ss_reads {
-    ss_ctx *ctx = nullptr;
+// The read cache: FASTQ text resident in HBM as one or more segments, each whole records ending in '\n'
+// (files of unknown inflated size are appended segment by segment; one probe launch per segment).
+struct ss_segment {
     uint8_t *d_text = nullptr;
-    uint64_t len = 0;
+    uint64_t len = 0, cap = 0;
     uint32_t n_tiles = 0;
     uint32_t *d_tile_line = nullptr;
     bool owns_text = false;
+};
+struct ss_reads {
+    ss_ctx *ctx = nullptr;
+    std::vector<ss_segment> seg;
+    uint64_t len = 0;
 };
 
 static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
@@ -130,6 +141,9 @@ extern "C" int ss_init(int device, ss_ctx **out) {
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < SS_NPEND; i++) SS_CUDA(cudaEventCreateWithFlags(&c->ev_pend[i], cudaEventDisableTiming));
+    if (const char *e = getenv("SS_CHUNK_BYTES")) { long long v = atoll(e); if (v >= (256 << 10) && v <= (1ll << 30)) c->chunk_bytes = (size_t)v; }
+    if (const char *e = getenv("SS_SEG_BYTES")) { long long v = atoll(e); if (v >= (256 << 10)) c->seg_bytes = (size_t)v; }
     *out = c;
     return SS_OK;
 }
@@ -143,6 +157,8 @@ extern "C" int ss_shutdown(ss_ctx *c) {
         if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
         cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]);
     }
+    delete c->src;
+    for (int i = 0; i < SS_NPEND; i++) cudaEventDestroy(c->ev_pend[i]);
     cudaFree(c->d_dense); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d);
     cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
@@ -177,82 +193,41 @@ static int ensure_dense(ss_ctx *c, uint64_t n) {
 // ---------------------------------------------------------------------------------------------
 // file helpers
 // ---------------------------------------------------------------------------------------------
-static bool ends_with_gz(const char *path) {   // identify.py:81: re.split('\.', path)[-1] == 'gz'
-    const char *dot = strrchr(path, '.');
-    return dot && strcmp(dot + 1, "gz") == 0;
-}
-
+// whole file into memory (k-mer FASTA databases; gzip'ed ones are inflated by ss_inflate.cuh)
 static int read_file(const char *path, std::vector<char> &out) {
     FILE *f = fopen(path, "rb");
     if (!f) return fail(SS_ERR_IO, std::string("cannot open ") + path);
-    unsigned char magic[2] = {0, 0};
-    size_t got = fread(magic, 1, 2, f);
-    bool gz = ends_with_gz(path) || (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b);
-    if (!gz) {
-        fseek(f, 0, SEEK_END);
-        long sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        size_t base = out.size();
-        out.resize(base + (size_t)sz);
-        size_t rd = sz ? fread(out.data() + base, 1, (size_t)sz, f) : 0;
-        fclose(f);
-        if (rd != (size_t)sz) return fail(SS_ERR_IO, std::string("short read on ") + path);
-        return SS_OK;
-    }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> raw((size_t)sz);
+    size_t rd = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
     fclose(f);
-    gzFile g = gzopen(path, "rb");   // handles concatenated members, like zcat
-    if (!g) return fail(SS_ERR_IO, std::string("cannot gzopen ") + path);
-    gzbuffer(g, 1 << 20);
-    const size_t step = 16u << 20;
-    while (true) {
-        size_t base = out.size();
-        out.resize(base + step);
-        int n = gzread(g, out.data() + base, (unsigned)step);
-        if (n < 0) {
-            int en = 0;
-            std::string m = std::string("inflate failed on ") + path + ": " + gzerror(g, &en);
-            gzclose(g);
-            return fail(SS_ERR_IO, m);
-        }
-        out.resize(base + (size_t)n);
-        if ((size_t)n < step) break;
-    }
-    gzclose(g);
+    if (rd != (size_t)sz) return fail(SS_ERR_IO, std::string("short read on ") + path);
+    const char *dot = strrchr(path, '.');
+    bool gz = (dot && strcmp(dot + 1, "gz") == 0) || (sz >= 2 && (unsigned char)raw[0] == 0x1f && (unsigned char)raw[1] == 0x8b);
+    if (!gz) { out.insert(out.end(), raw.begin(), raw.end()); return SS_OK; }
+    ssi_gz_stream *g = new ssi_gz_stream;
+    ssi_gz_init(*g, (const uint8_t *)raw.data(), raw.size());
+    const size_t win = 8u << 20;
+    std::vector<uint8_t> buf(SS_INGEST_HIST + win);
+    uint8_t *text = buf.data() + SS_INGEST_HIST;
+    int rc;
+    do {
+        uint8_t *pos = text;
+        rc = ssi_gz_read(*g, &pos, text + win);
+        size_t got = (size_t)(pos - text);
+        out.insert(out.end(), (char *)text, (char *)pos);
+        if (got >= SS_INGEST_HIST) memcpy(text - SS_INGEST_HIST, pos - SS_INGEST_HIST, SS_INGEST_HIST);
+        else if (got) { memmove(text - SS_INGEST_HIST, text - SS_INGEST_HIST + got, SS_INGEST_HIST - got); memcpy(text - got, text, got); }
+    } while (rc == SSI_MORE_OUTPUT);
+    delete g;
+    if (rc != SSI_OK) return fail(SS_ERR_IO, std::string("inflate failed on ") + path);
     return SS_OK;
 }
 
-// length of buf without trailing blank lines / whitespace
-static size_t trim_tail(const char *buf, size_t len) {
-    while (len > 0 && (buf[len - 1] == '\n' || buf[len - 1] == '\r' || buf[len - 1] == ' ' || buf[len - 1] == '\t'))
-        len--;
-    return len;
-}
-
-// first byte >= from that starts a FASTQ record: a line opening with '@' whose line+2 opens with '+'
-// (a quality line may open with '@', but then line+2 is a sequence line, never '+')
-static size_t find_record_start(const char *buf, size_t len, size_t from) {
-    if (from == 0) return 0;
-    if (from >= len) return len;
-    size_t p = from;
-    if (buf[p - 1] != '\n') {
-        const char *nl = (const char *)memchr(buf + p, '\n', len - p);
-        if (!nl) return len;
-        p = (size_t)(nl - buf) + 1;
-    }
-    while (p < len) {
-        const char *n1 = (const char *)memchr(buf + p, '\n', len - p);
-        if (!n1) return len;
-        size_t l1 = (size_t)(n1 - buf) + 1;
-        if (buf[p] == '@' && l1 < len) {
-            const char *n2 = (const char *)memchr(buf + l1, '\n', len - l1);
-            if (!n2) return len;
-            size_t l2 = (size_t)(n2 - buf) + 1;
-            if (l2 < len && buf[l2] == '+') return p;
-        }
-        p = l1;
-    }
-    return len;
-}
+static size_t trim_tail(const char *buf, size_t len) { return ss_trim_tail(buf, len); }
+static size_t find_record_start(const char *buf, size_t len, size_t from) { return ss_find_record_start(buf, len, from); }
 
 static int check_fastq_head(const char *buf, size_t len, const char *what) {
     if (len == 0) return SS_OK;
@@ -508,24 +483,38 @@ extern "C" int ss_kmerset_header_ids(const ss_kmerset *s, uint64_t *ids) {
 extern "C" size_t ss_reads_device_capacity(size_t len) { return round_up(len, SS_TILE) + SS_TEXT_PAD; }
 extern "C" uint64_t ss_reads_bytes(const ss_reads *r) { return r ? r->len : 0; }
 
+static void free_segment(ss_segment &g) {
+    if (g.owns_text) cudaFree(g.d_text);
+    cudaFree(g.d_tile_line);
+    g = ss_segment();
+}
+
 extern "C" int ss_reads_free(ss_reads *r) {
     if (!r) return SS_OK;
     cudaSetDevice(r->ctx->device);
-    if (r->owns_text) cudaFree(r->d_text);
-    cudaFree(r->d_tile_line);
+    for (auto &g : r->seg) free_segment(g);
     delete r;
     return SS_OK;
 }
 
-// pad + index a device text buffer; line_base = line index of its first byte
-static int finish_reads(ss_ctx *c, ss_reads *r, size_t capacity) {
-    r->n_tiles = (uint32_t)((r->len + SS_TILE - 1) / SS_TILE);
-    size_t need = ss_reads_device_capacity(r->len);
-    if (capacity < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
-    SS_CUDA(cudaMemsetAsync(r->d_text + r->len, '\n', need - r->len, c->stream));
-    SS_CUDA(cudaMalloc(&r->d_tile_line, (uint64_t)(r->n_tiles + 2) * sizeof(uint32_t)));
-    SS_CUDA(ss_launch_index(r->d_text, r->n_tiles, r->d_tile_line, 0, c->n_sm, c->stream));
+// pad + index one segment whose text (whole records) is already on the device
+static int finish_segment(ss_ctx *c, ss_segment &g) {
+    g.n_tiles = (uint32_t)((g.len + SS_TILE - 1) / SS_TILE);
+    size_t need = ss_reads_device_capacity(g.len);
+    if (g.cap < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
+    SS_CUDA(cudaMemsetAsync(g.d_text + g.len, '\n', need - g.len, c->stream));
+    SS_CUDA(cudaMalloc(&g.d_tile_line, (uint64_t)(g.n_tiles + 2) * sizeof(uint32_t)));
+    SS_CUDA(ss_launch_index(g.d_text, g.n_tiles, g.d_tile_line, 0, c->n_sm, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+static int alloc_segment(ss_segment &g, uint64_t text_bytes) {
+    g = ss_segment();
+    g.cap = ss_reads_device_capacity(text_bytes);
+    g.owns_text = true;
+    cudaError_t e = cudaMalloc(&g.d_text, g.cap);
+    if (e != cudaSuccess) { g = ss_segment(); return ss_cuda_fail(e, "cudaMalloc(read cache segment)", __FILE__, __LINE__); }
     return SS_OK;
 }
 
@@ -547,15 +536,17 @@ static int gather_host_text(const char *const *bufs, const size_t *lens, int n, 
 
 static int reads_from_vector(ss_ctx *c, const char *data, size_t len, ss_reads **out) {
     ss_reads *r = new ss_reads();
-    r->ctx = c; r->len = len; r->owns_text = true;
-    size_t cap = ss_reads_device_capacity(len);
-    cudaError_t e = cudaMalloc(&r->d_text, cap);
-    if (e != cudaSuccess) { delete r; return ss_cuda_fail(e, "cudaMalloc(reads)", __FILE__, __LINE__); }
+    r->ctx = c; r->len = len;
+    r->seg.emplace_back();
+    ss_segment &g = r->seg.back();
+    int rc = alloc_segment(g, len);
+    if (rc) { delete r; return rc; }
+    g.len = len;
     if (len) {
-        e = cudaMemcpyAsync(r->d_text, data, len, cudaMemcpyHostToDevice, c->stream);
+        cudaError_t e = cudaMemcpyAsync(g.d_text, data, len, cudaMemcpyHostToDevice, c->stream);
         if (e != cudaSuccess) { ss_reads_free(r); return ss_cuda_fail(e, "H2D reads", __FILE__, __LINE__); }
     }
-    int rc = finish_reads(c, r, cap);
+    rc = finish_segment(c, g);
     if (rc) { ss_reads_free(r); return rc; }
     *out = r;
     return SS_OK;
@@ -571,25 +562,6 @@ extern "C" int ss_reads_from_host(ss_ctx *c, const char *const *bufs, const size
     return reads_from_vector(c, all.data(), all.size(), out);
 }
 
-static int load_files_sharded(const char *const *paths, int n_paths, int shard, int n_shards, std::vector<char> &all,
-                              size_t &lo, size_t &hi) {
-    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(SS_ERR_ARG, "reads: bad shard / n_shards");
-    for (int i = 0; i < n_paths; i++) {
-        size_t base = all.size();
-        int rc = read_file(paths[i], all);
-        if (rc) return rc;
-        size_t l = trim_tail(all.data() + base, all.size() - base);
-        rc = check_fastq_head(all.data() + base, l, paths[i]);
-        if (rc) return rc;
-        all.resize(base + l);
-        if (l) all.push_back('\n');
-    }
-    size_t T = all.size();
-    lo = find_record_start(all.data(), T, (size_t)((unsigned __int128)T * shard / n_shards));
-    hi = (shard + 1 == n_shards) ? T : find_record_start(all.data(), T, (size_t)((unsigned __int128)T * (shard + 1) / n_shards));
-    return SS_OK;
-}
-
 extern "C" int ss_fastq_shard_range(const char *buf, size_t len, int shard, int n_shards, size_t *lo, size_t *hi) {
     if (!lo || !hi || (!buf && len)) return fail(SS_ERR_ARG, "ss_fastq_shard_range: NULL argument");
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(SS_ERR_ARG, "ss_fastq_shard_range: bad shard / n_shards");
@@ -598,16 +570,123 @@ extern "C" int ss_fastq_shard_range(const char *buf, size_t len, int shard, int 
     return SS_OK;
 }
 
+// the context's file ingest (producer threads + pinned chunk pool), created at first use
+static int ensure_source(ss_ctx *c) {
+    if (c->src && c->src->ready()) return SS_OK;
+    if (!c->src) c->src = new ss_text_source();
+    unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    int threads = (int)std::min(8u, std::max(2u, hw / 2));
+    if (const char *e = getenv("SS_INGEST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) threads = v; }
+    int rc = c->src->init(c->chunk_bytes, threads + 3, threads);
+    if (rc) return fail(rc, c->src->error());
+    return SS_OK;
+}
+
+// host chunks whose H2D copy is still in flight: released back to the producers once their event fires
+struct pending_ring {
+    ss_ctx *c;
+    ss_chunk *chunk[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
+    int at = 0;
+    explicit pending_ring(ss_ctx *ctx) : c(ctx) {}
+    // call right after the copy of `ch` was issued on `st`
+    cudaError_t push(ss_chunk *ch, cudaStream_t st) {
+        if (chunk[at]) {
+            cudaError_t e = cudaEventSynchronize(c->ev_pend[at]);
+            if (e != cudaSuccess) return e;
+            c->src->release(chunk[at]);
+            chunk[at] = nullptr;
+        }
+        cudaError_t e = cudaEventRecord(c->ev_pend[at], st);
+        if (e != cudaSuccess) return e;
+        chunk[at] = ch;
+        at = (at + 1) % SS_NPEND;
+        return cudaSuccess;
+    }
+    void drain() {
+        for (int i = 0; i < SS_NPEND; i++)
+            if (chunk[i]) { cudaEventSynchronize(c->ev_pend[i]); c->src->release(chunk[i]); chunk[i] = nullptr; }
+    }
+};
+
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
     *out = nullptr;
     SS_CUDA(cudaSetDevice(c->device));
-    std::vector<char> all;
-    size_t lo = 0, hi = 0;
-    int rc = load_files_sharded(paths, n_paths, shard, n_shards, all, lo, hi);
+    int rc = ensure_source(c);
     if (rc) return rc;
-    return reads_from_vector(c, all.data() + lo, hi - lo, out);
+    ss_text_source &src = *c->src;
+    rc = src.start(paths, n_paths, shard, n_shards);
+    if (rc) return fail(rc, src.error());
+    ss_reads *r = new ss_reads();
+    r->ctx = c;
+    // plain inputs have a known size (one segment); gzip streams grow segment by segment
+    const uint64_t known = src.plain_bytes() + 64 * (uint64_t)n_paths + 4096;
+    const uint64_t seg_default = src.gz_bytes() ? std::max<uint64_t>(c->seg_bytes, c->chunk_bytes) : known;
+    pending_ring pend(c);
+    cudaError_t ce = cudaSuccess;
+    while (ss_chunk *ch = src.next()) {
+        if (r->seg.empty() || r->seg.back().len + ch->len > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
+            r->seg.emplace_back();
+            rc = alloc_segment(r->seg.back(), std::max<uint64_t>(seg_default, ch->len));
+            if (rc) { r->seg.pop_back(); src.release(ch); break; }
+        }
+        ss_segment &g = r->seg.back();
+        ce = cudaMemcpyAsync(g.d_text + g.len, ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
+        if (ce == cudaSuccess) ce = pend.push(ch, c->copy_stream);
+        else src.release(ch);
+        if (ce != cudaSuccess) break;
+        g.len += ch->len;
+        r->len += ch->len;
+    }
+    pend.drain();
+    int src_rc = src.finish();
+    if (ce != cudaSuccess) { ss_reads_free(r); return ss_cuda_fail(ce, "H2D reads", __FILE__, __LINE__); }
+    if (rc) { ss_reads_free(r); return rc; }
+    if (src_rc) { ss_reads_free(r); return fail(src_rc, src.error()); }
+    SS_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (auto &g : r->seg) {
+        if (g.cap > ss_reads_device_capacity(g.len) + (64ull << 20)) {      // shrink a mostly empty segment
+            ss_segment small;
+            if (alloc_segment(small, g.len) == SS_OK) {
+                small.len = g.len;
+                if (g.len) cudaMemcpy(small.d_text, g.d_text, g.len, cudaMemcpyDeviceToDevice);
+                free_segment(g);
+                g = small;
+            }
+        }
+        rc = finish_segment(c, g);
+        if (rc) { ss_reads_free(r); return rc; }
+    }
+    *out = r;
+    return SS_OK;
+}
+
+// host-only: the ingest without a GPU (tools, CPU tests of the chunker / inflate)
+extern "C" int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n_shards, size_t chunk_bytes,
+                                    int n_threads, char *out, size_t out_cap, size_t *out_len, uint32_t *n_chunks) {
+    if ((n_paths > 0 && !paths) || !out_len) return fail(SS_ERR_ARG, "ss_ingest_files_host: NULL argument");
+    ss_text_source src;
+    int rc = src.init(chunk_bytes, std::max(1, n_threads) + 3, n_threads, false);
+    if (rc) return fail(rc, src.error());
+    rc = src.start(paths, n_paths, shard, n_shards);
+    if (rc) return fail(rc, src.error());
+    size_t total = 0;
+    uint32_t n = 0;
+    bool overflow = false;
+    while (ss_chunk *ch = src.next()) {
+        if (out && total + ch->len <= out_cap) memcpy(out + total, ch->text, ch->len);
+        else if (out) overflow = true;
+        total += ch->len;
+        n++;
+        src.release(ch);
+    }
+    rc = src.finish();
+    if (rc) return fail(rc, src.error());
+    *out_len = total;
+    if (n_chunks) *n_chunks = n;
+    if (overflow) return fail(SS_ERR_ARG, "ss_ingest_files_host: output buffer too small");
+    return SS_OK;
 }
 
 extern "C" int ss_reads_from_device(ss_ctx *c, void *dev_ptr, size_t len, size_t capacity, ss_reads **out) {
@@ -616,8 +695,11 @@ extern "C" int ss_reads_from_device(ss_ctx *c, void *dev_ptr, size_t len, size_t
     if (((uintptr_t)dev_ptr & 255u) != 0) return fail(SS_ERR_ARG, "ss_reads_from_device: pointer must be 256-byte aligned");
     SS_CUDA(cudaSetDevice(c->device));
     ss_reads *r = new ss_reads();
-    r->ctx = c; r->d_text = (uint8_t *)dev_ptr; r->len = len; r->owns_text = false;
-    int rc = finish_reads(c, r, capacity);
+    r->ctx = c; r->len = len;
+    r->seg.emplace_back();
+    ss_segment &g = r->seg.back();
+    g.d_text = (uint8_t *)dev_ptr; g.len = len; g.cap = capacity; g.owns_text = false;
+    int rc = finish_segment(c, g);
     if (rc) { ss_reads_free(r); return rc; }
     *out = r;
     return SS_OK;
@@ -630,8 +712,8 @@ static int check_format_result(ss_ctx *c, const char *what) {
     if (c->h_stats[4] != ~0ull) {
         char buf[256];
         snprintf(buf, sizeof buf,
-                 "%s: input is not 4-line FASTQ (line framing breaks at text byte %llu); wrapped FASTQ / FASTA "
-                 "reads are not supported",
+                 "%s: input is not 4-line FASTQ (line framing breaks at text byte %llu of a chunk); wrapped FASTQ / "
+                 "FASTA reads are not supported",
                  what, c->h_stats[4]);
         return fail(SS_ERR_FORMAT, buf);
     }
@@ -660,8 +742,13 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
     int rc = reset_pass(c, s);
     if (rc) return rc;
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
-    SS_CUDA(ss_launch_probe(r->d_text, r->len, r->n_tiles, r->d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
-                            c->n_sm, c->stream));
+    uint32_t launches = 0;
+    for (const ss_segment &g : r->seg) {
+        if (!g.n_tiles) continue;
+        SS_CUDA(ss_launch_probe(g.d_text, g.len, g.n_tiles, g.d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
+                                c->n_sm, c->stream));
+        launches++;
+    }
     SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
     SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, dev_counts, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
@@ -676,7 +763,7 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;
         cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
-        st->probe_launches = r->n_tiles ? 1 : 0;
+        st->probe_launches = launches;
         st->total_launches = st->probe_launches + (s->n_records ? 1 : 0);
         st->ms_total = now_ms() - t0;
     }
@@ -698,8 +785,8 @@ extern "C" int ss_count(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint3
 
 static int ensure_chunks(ss_ctx *c) {
     if (c->d_chunk[0]) return SS_OK;
-    size_t cap = ss_reads_device_capacity(SS_CHUNK_BYTES);
-    uint32_t tiles = (uint32_t)(SS_CHUNK_BYTES / SS_TILE) + 2;
+    size_t cap = ss_reads_device_capacity(c->chunk_bytes);
+    uint32_t tiles = (uint32_t)(c->chunk_bytes / SS_TILE) + 2;
     for (int i = 0; i < 2; i++) {
         SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
         SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 2) * sizeof(uint32_t)));
@@ -713,38 +800,74 @@ static bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// stream `len` bytes of whole FASTQ records through the double-buffered chunk pipeline
+// the double-buffered device side of the streaming drivers
 struct stream_state { int slot = 0; uint32_t probe_launches = 0, total_launches = 0; uint64_t bytes = 0; bool used[2] = {false, false}; };
 
+// copy one record-aligned chunk (n bytes at src, host) into device slot ss.slot and scan it
+static int stream_chunk(ss_ctx *c, const ss_kmerset *s, const char *src, size_t n, stream_state &ss) {
+    int b = ss.slot;
+    if (ss.used[b]) SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));   // kernels done with it
+    SS_CUDA(cudaMemcpyAsync(c->d_chunk[b], src, n, cudaMemcpyHostToDevice, c->copy_stream));
+    SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
+    SS_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    SS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
+    SS_CUDA(ss_launch_index(c->d_chunk[b], tiles, c->d_chunk_line[b], 0, c->n_sm, c->stream));
+    SS_CUDA(ss_launch_probe(c->d_chunk[b], n, tiles, c->d_chunk_line[b], s->view(), c->d_stats, c->d_stats + 4,
+                            c->n_sm, c->stream));
+    SS_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
+    ss.used[b] = true;
+    ss.probe_launches++; ss.total_launches += 3; ss.bytes += n;
+    ss.slot ^= 1;
+    return SS_OK;
+}
+
+// stream `len` bytes of whole FASTQ records (caller's host memory) through the chunk pipeline
 static int stream_text(ss_ctx *c, const ss_kmerset *s, const char *buf, size_t len, stream_state &ss) {
     size_t pos = 0;
     const bool pinned = len ? is_pinned(buf) : true;
+    const size_t chunk = c->chunk_bytes;
     while (pos < len) {
-        size_t end = pos + SS_CHUNK_BYTES >= len ? len : find_record_start(buf, len, pos + SS_CHUNK_BYTES - (1u << 16));
-        if (end > pos + SS_CHUNK_BYTES || end <= pos) return fail(SS_ERR_FORMAT, "reads: no FASTQ record boundary within 64 KiB");
+        size_t end = pos + chunk >= len ? len : find_record_start(buf, len, pos + chunk - SS_INGEST_BOUNDARY);
+        if (end > pos + chunk || end <= pos) return fail(SS_ERR_FORMAT, "reads: no FASTQ record boundary within 64 KiB");
         size_t n = end - pos;
         int b = ss.slot;
-        if (ss.used[b]) SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));   // kernels done with it
         const char *src = buf + pos;
         if (!pinned) {   // stage pageable memory through our own pinned buffer so the copy stays asynchronous
-            if (!c->h_pinned[b]) SS_CUDA(cudaMallocHost(&c->h_pinned[b], SS_CHUNK_BYTES));
+            if (!c->h_pinned[b]) SS_CUDA(cudaMallocHost(&c->h_pinned[b], chunk));
             if (ss.used[b]) SS_CUDA(cudaEventSynchronize(c->ev_copied[b]));
             memcpy(c->h_pinned[b], src, n);
             src = (const char *)c->h_pinned[b];
         }
-        SS_CUDA(cudaMemcpyAsync(c->d_chunk[b], src, n, cudaMemcpyHostToDevice, c->copy_stream));
-        SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
-        SS_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-        SS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-        uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
-        SS_CUDA(ss_launch_index(c->d_chunk[b], tiles, c->d_chunk_line[b], 0, c->n_sm, c->stream));
-        SS_CUDA(ss_launch_probe(c->d_chunk[b], n, tiles, c->d_chunk_line[b], s->view(), c->d_stats, c->d_stats + 4,
-                                c->n_sm, c->stream));
-        SS_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
-        ss.used[b] = true;
-        ss.probe_launches++; ss.total_launches += 3; ss.bytes += n;
-        ss.slot ^= 1;
+        int rc = stream_chunk(c, s, src, n, ss);
+        if (rc) return rc;
         pos = end;
+    }
+    return SS_OK;
+}
+
+// common tail of the streaming drivers: gather, copy out, statistics
+static int finish_streamed(ss_ctx *c, const ss_kmerset *s, stream_state &ss, uint32_t *counts, ss_stats *st, double t0,
+                           const char *what) {
+    SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, c->d_dense, c->stream));
+    SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
+    if (s->n_records)
+        SS_CUDA(cudaMemcpyAsync(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
+    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = check_format_result(c, what);
+    if (rc) return rc;
+    if (st) {
+        memset(st, 0, sizeof *st);
+        fill_stats(c, st);
+        st->text_bytes = ss.bytes;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;   // copies + index + probe, overlapped
+        cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
+        st->probe_launches = ss.probe_launches;
+        st->total_launches = ss.total_launches + 1;
+        st->ms_total = now_ms() - t0;
     }
     return SS_OK;
 }
@@ -768,27 +891,7 @@ static int count_streamed(ss_ctx *c, const ss_kmerset *s, const char *const *buf
         rc = stream_text(c, s, bufs[i], l, ss);   // every buffer starts a record: line index restarts at 0
         if (rc) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); return rc; }
     }
-    SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
-    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, c->d_dense, c->stream));
-    SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
-    if (s->n_records)
-        SS_CUDA(cudaMemcpyAsync(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
-    SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaStreamSynchronize(c->stream));
-    rc = check_format_result(c, "ss_count_host");
-    if (rc) return rc;
-    if (st) {
-        memset(st, 0, sizeof *st);
-        fill_stats(c, st);
-        st->text_bytes = ss.bytes;
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;   // copies + index + probe, overlapped
-        cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
-        st->probe_launches = ss.probe_launches;
-        st->total_launches = ss.total_launches + 1;
-        st->ms_total = now_ms() - t0;
-    }
-    return SS_OK;
+    return finish_streamed(c, s, ss, counts, st, t0, "ss_count_host");
 }
 
 extern "C" int ss_count_host(ss_ctx *c, const ss_kmerset *s, const char *const *bufs, const size_t *lens, int n,
@@ -798,17 +901,41 @@ extern "C" int ss_count_host(ss_ctx *c, const ss_kmerset *s, const char *const *
     return count_streamed(c, s, bufs, lens, n, counts, st);
 }
 
+// End to end from files: producer threads read / inflate into pinned chunks while earlier chunks are
+// copied and scanned; nothing but two device chunk buffers is resident.
 extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const *paths, int n_paths, int shard,
                               int n_shards, uint32_t *counts, ss_stats *st) {
     if (!c || !s || !counts || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_count_files: NULL argument");
     if (s->ctx != c) return fail(SS_ERR_ARG, "ss_count_files: set belongs to another context");
-    std::vector<char> all;
-    size_t lo = 0, hi = 0;
-    int rc = load_files_sharded(paths, n_paths, shard, n_shards, all, lo, hi);
+    double t0 = now_ms();
+    SS_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_chunks(c);
     if (rc) return rc;
-    const char *b = all.data() + lo;
-    size_t l = hi - lo;
-    return count_streamed(c, s, &b, &l, 1, counts, st);
+    rc = ensure_dense(c, s->n_records);
+    if (rc) return rc;
+    rc = ensure_source(c);
+    if (rc) return rc;
+    ss_text_source &src = *c->src;
+    rc = src.start(paths, n_paths, shard, n_shards);
+    if (rc) return fail(rc, src.error());
+    rc = reset_pass(c, s);
+    if (rc) { src.finish(); return rc; }
+    SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    stream_state ss;
+    pending_ring pend(c);
+    while (ss_chunk *ch = src.next()) {
+        rc = stream_chunk(c, s, (const char *)ch->text, ch->len, ss);
+        if (rc) { src.release(ch); break; }
+        cudaError_t e = pend.push(ch, c->copy_stream);
+        if (e != cudaSuccess) { rc = ss_cuda_fail(e, "ingest event", __FILE__, __LINE__); break; }
+    }
+    pend.drain();
+    int src_rc = src.finish();
+    if (rc || src_rc) {
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        return rc ? rc : fail(src_rc, src.error());
+    }
+    return finish_streamed(c, s, ss, counts, st, t0, "ss_count_files");
 }
 
 extern "C" int ss_l2_finalize(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, int64_t *py_o) {

@@ -285,3 +285,48 @@ def test_synthetic_workload_sample_vs_oracle(eng):
                 break
             v = (v - 1) // 2
     assert hit_nodes and hit_nodes <= allowed
+
+
+def test_file_ingest_many_chunks_and_segments(tmp_path, monkeypatch):
+    """Read files through the producer-thread ingest with tiny chunks (256 KiB) and tiny read-cache
+    segments (1 MiB): paired plain + gz inputs, the resident cache (ss_reads_from_files, several
+    segments -> several probe launches) and the streaming driver (ss_count_files), whole and sharded."""
+    from strainscan_b200 import Engine
+    monkeypatch.setenv("SS_CHUNK_BYTES", str(256 << 10))
+    monkeypatch.setenv("SS_SEG_BYTES", str(1 << 20))
+    monkeypatch.setenv("SS_INGEST_THREADS", "4")
+    e = Engine(0)
+    try:
+        rng = np.random.default_rng(77)
+        G = util.rand_genome(rng, 150_000)
+        fa = util.make_db(rng, G, 31, 15_000)
+        fq1 = util.make_reads(rng, G, 12_000, 150, var_len=True)         # ~4 MB
+        fq2 = util.make_reads(rng, G, 9_000, 150, var_len=False, lower_frac=0.1)
+        p1, p2 = tmp_path / "r1.fq.gz", tmp_path / "r2.fq"
+        p1.write_bytes(gzip.compress(fq1, 6))
+        p2.write_bytes(fq2)
+        ks = e.kmerset_from_text(fa, 31)
+        d = adapters.count_dense(fa, 31, [fq1, fq2])
+        reads = e.reads_from_files([str(p1), str(p2)])
+        got, st = e.count(ks, reads)
+        assert np.array_equal(got.astype(np.uint64), d.cnt)
+        assert st.n_reads == 21_000 and st.probe_launches >= 4          # one launch per cache segment
+        got2, st2 = e.count_files(ks, [str(p1), str(p2)])
+        assert np.array_equal(got2, got) and st2.n_kmers == st.n_kmers and st2.probe_launches >= 16
+        for n in (2, 5):
+            acc = np.zeros_like(got)
+            acc_c = np.zeros_like(got)
+            for s in range(n):
+                acc += e.count_files(ks, [str(p1), str(p2)], shard=s, n_shards=n)[0]
+                acc_c += e.count(ks, e.reads_from_files([str(p1), str(p2)], shard=s, n_shards=n))[0]
+            assert np.array_equal(acc, got) and np.array_equal(acc_c, got)
+        # errors surface from the producer threads
+        bad = tmp_path / "bad.fq.gz"
+        bad.write_bytes(gzip.compress(fq1)[:100_000])
+        with pytest.raises(Exception, match="inflate failed"):
+            e.reads_from_files([str(bad)])
+        with pytest.raises(Exception, match="inflate failed"):
+            e.count_files(ks, [str(p2), str(bad)])
+        assert np.array_equal(e.count_files(ks, [str(p1), str(p2)])[0], got)   # the context stays usable
+    finally:
+        e.close()

@@ -1,0 +1,173 @@
+"""Read-file ingest on the host (no GPU): the library's own gzip inflate (strainscan_b200/csrc/ss_inflate.cuh,
+the same code the device BGZF kernel runs), record-aligned chunking, producer threads and sharding,
+checked against Python's zlib/gzip -- the stand-in for the `zcat a b |` of library/identify.py:82 and
+library/Vote_Strain_L2_Lasso_new_sp.py:359,367.  Calls go through the C ABI (ss_ingest_files_host)."""
+import ctypes as C
+import gzip
+import io
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from strainscan_b200 import _lib
+from tests import util
+
+CHUNK = 256 << 10      # smallest legal chunk: forces many chunks on ~MB inputs
+
+
+def ingest(paths, shard=0, n_shards=1, chunk=CHUNK, threads=3):
+    lib = _lib.load()
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    total = sum(os.path.getsize(p) for p in paths if os.path.exists(p)) * 40 + (1 << 20)
+    out = C.create_string_buffer(total)
+    n, nch = C.c_size_t(), C.c_uint32()
+    rc = lib.ss_ingest_files_host(arr, len(paths), shard, n_shards, chunk, threads, out, total, C.byref(n), C.byref(nch))
+    if rc:
+        raise _lib.StrainScanB200Error(rc, lib.ss_last_error().decode())
+    return out.raw[:n.value], nch.value
+
+
+def records(text):
+    lines = text.split(b"\n")
+    assert lines[-1] == b"", "chunks must end with a newline"
+    lines = lines[:-1]
+    assert len(lines) % 4 == 0
+    return sorted(tuple(lines[i:i + 4]) for i in range(0, len(lines), 4))
+
+
+@pytest.fixture(scope="module")
+def fastq():
+    rng = np.random.default_rng(7)
+    g = util.rand_genome(rng, 50_000)
+    return util.make_reads(rng, g, 6000, read_len=150, var_len=True)      # ~2 MB, '@'/'+' qualities included
+
+
+def _variants(fq):
+    v = {}
+    for lvl in (1, 6, 9):
+        v["level%d" % lvl] = gzip.compress(fq, lvl)
+    v["stored"] = gzip.compress(fq, 0)
+    v["multi_member"] = b"".join(gzip.compress(fq[i:i + 70_001], 6) for i in range(0, len(fq), 70_001))
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, zlib.Z_FIXED)
+    v["fixed_huffman"] = co.compress(fq) + co.flush()
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, zlib.Z_HUFFMAN_ONLY)
+    v["huffman_only"] = co.compress(fq) + co.flush()
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 1)
+    v["memlevel1"] = co.compress(fq) + co.flush()              # a new dynamic block every ~100 symbols
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = []
+    for i in range(0, len(fq), 9973):
+        parts += [co.compress(fq[i:i + 9973]), co.flush(zlib.Z_SYNC_FLUSH)]
+    v["sync_flush"] = b"".join(parts) + co.flush()
+    b = io.BytesIO()
+    with gzip.GzipFile(filename="reads_R1.fastq", mode="wb", fileobj=b, mtime=1) as gz:
+        gz.write(fq)
+    v["fname_header"] = b.getvalue()
+    v["trailing_garbage"] = gzip.compress(fq) + b"\0\0\0not a member"
+    return v
+
+
+def test_gz_stream_matches_zlib_bytewise(fastq, tmp_path):
+    """One gz file, one producer: chunks arrive in stream order, so the bytes must equal zlib's output."""
+    for name, data in _variants(fastq).items():
+        p = str(tmp_path / ("%s.fq.gz" % name))
+        open(p, "wb").write(data)
+        got, n_chunks = ingest([p], threads=1)
+        assert got == fastq, name
+        assert n_chunks >= len(fastq) // CHUNK, name
+
+
+def test_gz_by_magic_and_plain_by_content(fastq, tmp_path):
+    p1, p2 = str(tmp_path / "a.fq"), str(tmp_path / "b.dat")
+    open(p1, "wb").write(fastq)
+    open(p2, "wb").write(gzip.compress(fastq))            # gzip without the .gz suffix: detected by its magic
+    assert records(ingest([p1])[0]) == records(fastq)
+    assert records(ingest([p2])[0]) == records(fastq)
+
+
+def test_paired_files_mixed_and_tail_normalisation(fastq, tmp_path):
+    half = fastq.index(b"\n@", len(fastq) // 2) + 1
+    while not fastq[half:].split(b"\n", 3)[2].startswith(b"+"):     # a real record start ('@' may open a quality line)
+        half = fastq.index(b"\n@", half) + 1
+    a, b = fastq[:half], fastq[half:]
+    p1, p2 = str(tmp_path / "r1.fq.gz"), str(tmp_path / "r2.fq")
+    open(p1, "wb").write(gzip.compress(a[:-1]))                       # no final newline
+    open(p2, "wb").write(b + b"\n\n  \n")                             # trailing blank lines
+    got, _ = ingest([p1, p2], threads=4)
+    assert records(got) == records(fastq)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_shards_partition_the_reads(fastq, tmp_path, gz, n_shards):
+    p = str(tmp_path / ("s.fq.gz" if gz else "s.fq"))
+    open(p, "wb").write(gzip.compress(fastq) if gz else fastq)
+    parts = [ingest([p], s, n_shards)[0] for s in range(n_shards)]
+    assert sum(len(x) for x in parts) == len(fastq)
+    assert records(b"".join(parts)) == records(fastq)
+    assert sum(1 for x in parts if x) >= 2          # the work really is spread
+
+
+def test_large_chunk_single_delivery(fastq, tmp_path):
+    p = str(tmp_path / "one.fq.gz")
+    open(p, "wb").write(gzip.compress(fastq))
+    got, n = ingest([p], chunk=32 << 20)
+    assert got == fastq and n == 1
+
+
+def test_empty_inputs(tmp_path):
+    p1, p2, p3 = str(tmp_path / "e.fq"), str(tmp_path / "e.fq.gz"), str(tmp_path / "blank.fq")
+    open(p1, "wb").close()
+    open(p2, "wb").write(gzip.compress(b""))
+    open(p3, "wb").write(b"\n\n")
+    assert ingest([p1, p2, p3]) == (b"", 0)
+
+
+def test_errors_are_loud(fastq, tmp_path):
+    gz = gzip.compress(fastq)
+    bad = {
+        "truncated.fq.gz": gz[:len(gz) // 2],
+        "no_trailer.fq.gz": gz[:-8],
+        "not_gzip.fq.gz": fastq,
+        "fasta.fq": b">r1\nACGT\n",
+        "junk.fq": b"hello\n",
+    }
+    corrupt = bytearray(gz)
+    corrupt[len(gz) // 3] ^= 0x55
+    for name, data in bad.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        with pytest.raises(_lib.StrainScanB200Error) as e:
+            ingest([p])
+        assert e.value.code in (_lib.SS_ERR_IO, _lib.SS_ERR_FORMAT), name
+    p = str(tmp_path / "corrupt.fq.gz")
+    open(p, "wb").write(bytes(corrupt))
+    try:                                       # a flipped byte either fails to decode or decodes to a wrong length
+        got, _ = ingest([p])
+        assert got != fastq
+    except _lib.StrainScanB200Error as e:
+        assert e.code in (_lib.SS_ERR_IO, _lib.SS_ERR_FORMAT)
+    with pytest.raises(_lib.StrainScanB200Error):
+        ingest([str(tmp_path / "missing.fq")])
+
+
+def test_random_deflate_streams_roundtrip(tmp_path):
+    """Non-FASTQ payloads exercise long codes, long matches and stored blocks: wrap each payload as the
+    sequence line of a single record so the chunker accepts it."""
+    rng = np.random.default_rng(11)
+    payloads = [
+        bytes(rng.integers(65, 91, 300_000, dtype=np.uint8)),                                # incompressible letters
+        b"ACGT" * 100_000,                                                                    # distance-4 matches, length 258
+        b"A" * 400_000,                                                                       # run-length
+        bytes(rng.choice(np.arange(65, 91, dtype=np.uint8), 400_000,
+                         p=np.array([2.0 ** -i for i in range(1, 26)] + [2.0 ** -25]))),      # skewed: 15-bit codes
+    ]
+    for i, pl in enumerate(payloads):
+        fq = b"@r\n" + pl + b"\n+\n" + pl + b"\n"
+        for lvl in (1, 6, 9):
+            p = str(tmp_path / ("p%d_%d.fq.gz" % (i, lvl)))
+            open(p, "wb").write(gzip.compress(fq, lvl))
+            got, _ = ingest([p], chunk=4 << 20, threads=1)
+            assert got == fq, (i, lvl)

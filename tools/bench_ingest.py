@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""End-to-end file ingest on the GPU box: FASTQ files (plain / gz / paired gz) in /dev/shm ->
+ss_reads_from_files (producer threads, own inflate, pinned chunks, H2D) -> ss_count, and the streaming
+ss_count_files; beside it the reference's own ingest (`zcat | jellyfish count`, identify.py:82-84).
+Prints one JSON object.  Usage: python tools/bench_ingest.py [--reads 2000000] [--no-reference]"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=2_000_000)
+    ap.add_argument("--leaves", type=int, default=823)
+    ap.add_argument("--no-reference", action="store_true")
+    a = ap.parse_args()
+    import numpy as np
+    import torch
+    from strainscan_b200 import Engine, synth
+
+    eng = Engine(0)
+    params = synth.default_params(n_leaves=a.leaves, seed=1)
+    sizes = synth.node_sizes(params, seed=1)
+    db_text, _ = eng.synth_db_host(params, sizes, want_nodes=False)
+    kset = eng.kmerset_from_text(db_text, params.k)
+    rec = eng.synth_read_record_bytes(params)
+    n_bytes = a.reads * rec
+    buf = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
+    eng.synth_reads_device(params, buf.data_ptr(), a.reads, 0)
+    host = buf.cpu().numpy()
+    del buf
+    tmp = tempfile.mkdtemp(prefix="ssb200_ing_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = {"reads": a.reads, "text_bytes": int(n_bytes), "host_cores": os.cpu_count(), "cases": {}}
+    try:
+        plain = os.path.join(tmp, "r.fq")
+        host.tofile(plain)
+        half = (a.reads // 2) * rec
+        r1, r2 = os.path.join(tmp, "r1.fq"), os.path.join(tmp, "r2.fq")
+        host[:half].tofile(r1)
+        host[half:].tofile(r2)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen("gzip -1 -c %s > %s.gz" % (p, p), shell=True) for p in (plain, r1, r2)]
+        for p in procs:
+            p.wait()
+        out["gzip_1_seconds"] = time.perf_counter() - t0
+        out["gz_bytes"] = os.path.getsize(plain + ".gz")
+        ref_counts = None
+        kpr = params.read_len - params.k + 1
+
+        def run(name, paths):
+            nonlocal ref_counts
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                reads = eng.reads_from_files(paths)
+                t1 = time.perf_counter()
+                got, st = eng.count(kset, reads)
+                t2 = time.perf_counter()
+                del reads
+                if best is None or t2 - t0 < best[0]:
+                    best = (t2 - t0, t1 - t0, t2 - t1)
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                got2, st2 = eng.count_files(kset, paths)
+                ts.append(time.perf_counter() - t0)
+            assert np.array_equal(got, got2) and st.n_reads == a.reads and st2.n_kmers == st.n_kmers
+            if ref_counts is None:
+                ref_counts = got
+            assert np.array_equal(got, ref_counts), "counts differ between input encodings"
+            out["cases"][name] = {
+                "cache_then_count_s": best[0], "ingest_s": best[1], "count_s": best[2], "stream_count_files_s": min(ts),
+                "text_gb_per_s": n_bytes / best[1] / 1e9, "e2e_kmers_per_s": a.reads * kpr / best[0],
+                "stream_kmers_per_s": a.reads * kpr / min(ts)}
+
+        run("plain_se", [plain])
+        run("gz_se", [plain + ".gz"])
+        run("gz_pe", [r1 + ".gz", r2 + ".gz"])
+        run("plain_pe", [r1, r2])
+
+        jf = os.path.join(ROOT, "oracle", "_ref", "jellyfish-linux")
+        if not a.no_reference and os.access(jf, os.X_OK):
+            fa = os.path.join(tmp, "kmer.fa")
+            db_text.tofile(fa)
+            t0 = time.perf_counter()
+            subprocess.check_call("zcat %s.gz %s.gz > /dev/null" % (r1, r2), shell=True)
+            out["zcat_only_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()     # identify.py:82 literal: zcat a b | jellyfish count /dev/fd/0 -t 8
+            subprocess.check_call("zcat %s.gz %s.gz | %s count /dev/fd/0 -m 31 -s 100M -t 8 --if %s -o %s/o.jf" % (
+                r1, r2, jf, fa, tmp), shell=True)
+            out["reference_zcat_jellyfish_t8_s"] = time.perf_counter() - t0
+            out["reference_kmers_per_s"] = a.reads * kpr / out["reference_zcat_jellyfish_t8_s"]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
