@@ -44,6 +44,8 @@ static double now_ms() {
 #define SS_CHUNK_DEFAULT (32ull << 20)   // streaming chunk of FASTQ text (host -> device); env SS_CHUNK_BYTES
 #define SS_SEG_DEFAULT (1ull << 30)      // read-cache segment when the total size is unknown (gzip); env SS_SEG_BYTES
 #define SS_NPEND 4                       // host chunks whose H2D copy may be in flight
+#define SS_NSLOT 4                       // device text slots of the streaming drivers (copy / inflate / scan overlap)
+#define SS_NGZ 8                         // BGZF batches in flight on the device
 
 struct ss_ctx {
     int device = 0;
@@ -55,12 +57,22 @@ struct ss_ctx {
     uint32_t *d_dense = nullptr;             // scratch dense vector for host-output counts
     uint64_t dense_cap = 0;
     // streaming (ss_count_host / ss_count_files)
-    uint8_t *d_chunk[2] = {nullptr, nullptr};
-    uint32_t *d_chunk_line[2] = {nullptr, nullptr};
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    uint8_t *h_pinned[2] = {nullptr, nullptr};   // staging for pageable sources
+    uint8_t *d_chunk[SS_NSLOT] = {};
+    uint32_t *d_chunk_line[SS_NSLOT] = {};
+    cudaEvent_t ev_copied[SS_NSLOT] = {}, ev_done[SS_NSLOT] = {};
+    uint8_t *h_pinned[SS_NSLOT] = {};            // staging for pageable sources
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     size_t chunk_bytes = SS_CHUNK_DEFAULT, seg_bytes = SS_SEG_DEFAULT;
+    // device inflate of BGZF batches (ss_gunzip.cu): compressed staging + member tables, double buffered
+    bool device_bgzf = true;
+    size_t bgzf_out_cap = 0;                     // text bytes one batch may inflate to
+    uint8_t *d_comp[SS_NGZ] = {};
+    ss_member *d_members[SS_NGZ] = {};
+    cudaStream_t gz_stream[SS_NGZ] = {};         // batches inflate concurrently: one batch alone cannot fill the GPU
+    cudaEvent_t ev_gz_copied[SS_NGZ] = {}, ev_gz_done[SS_NGZ] = {};
+    unsigned int *d_gz = nullptr;                // [slot] work counters, [SS_NGZ] smallest failing member (0xFFFFFFFF = none)
+    int gz_slot = 0;
+    bool gz_used[SS_NGZ] = {};
     ss_text_source *src = nullptr;               // file ingest: producer threads + pinned chunk pool (lazy)
     cudaEvent_t ev_pend[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -137,13 +149,22 @@ extern "C" int ss_init(int device, ss_ctx **out) {
     SS_CUDA(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
     SS_CUDA(cudaEventCreate(&c->ev_a)); SS_CUDA(cudaEventCreate(&c->ev_b));
     SS_CUDA(cudaEventCreate(&c->ev_c)); SS_CUDA(cudaEventCreate(&c->ev_d));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < SS_NSLOT; i++) {
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < SS_NPEND; i++) SS_CUDA(cudaEventCreateWithFlags(&c->ev_pend[i], cudaEventDisableTiming));
     if (const char *e = getenv("SS_CHUNK_BYTES")) { long long v = atoll(e); if (v >= (256 << 10) && v <= (1ll << 30)) c->chunk_bytes = (size_t)v; }
     if (const char *e = getenv("SS_SEG_BYTES")) { long long v = atoll(e); if (v >= (256 << 10)) c->seg_bytes = (size_t)v; }
+    c->bgzf_out_cap = 6 * c->chunk_bytes;
+    if (const char *e = getenv("SS_BGZF_OUT_CAP")) { long long v = atoll(e); if (v >= (1 << 20) && v <= (4ll << 30)) c->bgzf_out_cap = (size_t)v; }
+    if (const char *e = getenv("SS_BGZF_GPU")) c->device_bgzf = atoi(e) != 0;
+    for (int i = 0; i < SS_NGZ; i++) {
+        SS_CUDA(cudaEventCreateWithFlags(&c->ev_gz_done[i], cudaEventDisableTiming));
+        SS_CUDA(cudaEventCreateWithFlags(&c->ev_gz_copied[i], cudaEventDisableTiming));
+        SS_CUDA(cudaStreamCreateWithFlags(&c->gz_stream[i], cudaStreamNonBlocking));
+    }
+    SS_CUDA(cudaMalloc(&c->d_gz, (SS_NGZ + 1) * sizeof(unsigned int)));
     *out = c;
     return SS_OK;
 }
@@ -152,12 +173,18 @@ extern "C" int ss_shutdown(ss_ctx *c) {
     if (!c) return SS_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < SS_NSLOT; i++) {
         cudaFree(c->d_chunk[i]); cudaFree(c->d_chunk_line[i]);
         if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
         cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]);
     }
     delete c->src;
+    for (int i = 0; i < SS_NGZ; i++) {
+        cudaFree(c->d_comp[i]); cudaFree(c->d_members[i]);
+        cudaEventDestroy(c->ev_gz_done[i]); cudaEventDestroy(c->ev_gz_copied[i]);
+        cudaStreamDestroy(c->gz_stream[i]);
+    }
+    cudaFree(c->d_gz);
     for (int i = 0; i < SS_NPEND; i++) cudaEventDestroy(c->ev_pend[i]);
     cudaFree(c->d_dense); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d);
@@ -577,7 +604,7 @@ static int ensure_source(ss_ctx *c) {
     unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     int threads = (int)std::min(8u, std::max(2u, hw / 2));
     if (const char *e = getenv("SS_INGEST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) threads = v; }
-    int rc = c->src->init(c->chunk_bytes, threads + 3, threads);
+    int rc = c->src->init(c->chunk_bytes, threads + 3, threads, true, c->device_bgzf, c->bgzf_out_cap);
     if (rc) return fail(rc, c->src->error());
     return SS_OK;
 }
@@ -608,6 +635,54 @@ struct pending_ring {
     }
 };
 
+// Stage one BGZF batch (compressed members + member table + the two host-decoded text pieces) and
+// inflate it so that the batch's text starts at `dst` (device).  Copies go on the copy stream, the
+// kernel on one of SS_NGZ inflate streams; *done is the event the consumer of the text waits for.
+static int inflate_batch(ss_ctx *c, ss_chunk *ch, uint8_t *dst, cudaEvent_t *done) {
+    const int b = c->gz_slot;
+    if (!c->d_comp[b]) {
+        SS_CUDA(cudaMalloc(&c->d_comp[b], c->chunk_bytes + 64));
+        SS_CUDA(cudaMalloc(&c->d_members[b], (size_t)SS_BGZF_MAX_MEMBERS * sizeof(ss_member)));
+    }
+    if (c->gz_used[b]) SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_gz_done[b], 0));   // kernel done with the slot
+    SS_CUDA(cudaMemcpyAsync(c->d_comp[b], ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream));
+    SS_CUDA(cudaMemcpyAsync(c->d_members[b], ch->members, (size_t)ch->n_members * sizeof(ss_member), cudaMemcpyHostToDevice,
+                            c->copy_stream));
+    if (ch->pre_len) SS_CUDA(cudaMemcpyAsync(dst, ch->pre_text, ch->pre_len, cudaMemcpyHostToDevice, c->copy_stream));
+    if (ch->post_len)
+        SS_CUDA(cudaMemcpyAsync(dst + ch->pre_len + ch->inflated_len, ch->post_text, ch->post_len, cudaMemcpyHostToDevice,
+                                c->copy_stream));
+    SS_CUDA(cudaEventRecord(c->ev_gz_copied[b], c->copy_stream));
+    SS_CUDA(cudaStreamWaitEvent(c->gz_stream[b], c->ev_gz_copied[b], 0));
+    SS_CUDA(ss_launch_gunzip(c->d_comp[b], c->d_members[b], ch->n_members, dst, c->d_gz + b, c->d_gz + SS_NGZ, c->n_sm,
+                             c->gz_stream[b]));
+    SS_CUDA(cudaEventRecord(c->ev_gz_done[b], c->gz_stream[b]));
+    if (done) *done = c->ev_gz_done[b];
+    c->gz_used[b] = true;
+    c->gz_slot = (b + 1) % SS_NGZ;
+    return SS_OK;
+}
+
+static int gz_begin(ss_ctx *c) {
+    for (int i = 0; i < SS_NGZ; i++) c->gz_used[i] = false;
+    SS_CUDA(cudaMemsetAsync(c->d_gz + SS_NGZ, 0xFF, sizeof(unsigned int), c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+static void gz_sync(ss_ctx *c) { for (int i = 0; i < SS_NGZ; i++) cudaStreamSynchronize(c->gz_stream[i]); }
+
+// after the stream was synchronised: did every member inflate to its ISIZE?
+static int gz_check(ss_ctx *c, const char *what) {
+    unsigned int bad = 0xFFFFFFFFu;
+    gz_sync(c);
+    SS_CUDA(cudaMemcpy(&bad, c->d_gz + SS_NGZ, sizeof bad, cudaMemcpyDeviceToHost));
+    if (bad != 0xFFFFFFFFu)
+        return fail(SS_ERR_IO, std::string(what) + ": inflate failed on the device (invalid BGZF block, member " +
+                                   std::to_string(bad) + " of a batch)");
+    return SS_OK;
+}
+
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
@@ -625,26 +700,50 @@ extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_pa
     const uint64_t seg_default = src.gz_bytes() ? std::max<uint64_t>(c->seg_bytes, c->chunk_bytes) : known;
     pending_ring pend(c);
     cudaError_t ce = cudaSuccess;
-    while (ss_chunk *ch = src.next()) {
-        if (r->seg.empty() || r->seg.back().len + ch->len > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
+    rc = gz_begin(c);
+    bool any_gz = false;
+    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
+    double t_begin = now_ms(), t_wait = 0;
+    uint32_t n_chunks = 0;
+    while (!rc) {
+        double tw = now_ms();
+        ss_chunk *ch = src.next();
+        t_wait += now_ms() - tw;
+        if (!ch) break;
+        n_chunks++;
+        const uint64_t n = ch->text_len();
+        if (r->seg.empty() || r->seg.back().len + n + SSI_OUT_SLACK > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
             r->seg.emplace_back();
-            rc = alloc_segment(r->seg.back(), std::max<uint64_t>(seg_default, ch->len));
+            rc = alloc_segment(r->seg.back(), std::max<uint64_t>(seg_default, n + SSI_OUT_SLACK));
             if (rc) { r->seg.pop_back(); src.release(ch); break; }
         }
         ss_segment &g = r->seg.back();
-        ce = cudaMemcpyAsync(g.d_text + g.len, ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
-        if (ce == cudaSuccess) ce = pend.push(ch, c->copy_stream);
-        else src.release(ch);
+        if (ch->kind == SS_CHUNK_BGZF) {
+            rc = inflate_batch(c, ch, g.d_text + g.len, nullptr);     // the text is produced in place, in the cache segment
+            any_gz = true;
+            if (rc) { src.release(ch); break; }
+        } else {
+            ce = cudaMemcpyAsync(g.d_text + g.len, ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
+            if (ce != cudaSuccess) { src.release(ch); break; }
+        }
+        ce = pend.push(ch, c->copy_stream);
         if (ce != cudaSuccess) break;
-        g.len += ch->len;
-        r->len += ch->len;
+        g.len += n;
+        r->len += n;
     }
+    double t_loop = now_ms();
     pend.drain();
     int src_rc = src.finish();
+    cudaStreamSynchronize(c->copy_stream);
+    gz_sync(c);
+    cudaStreamSynchronize(c->stream);
+    if (dbg)
+        fprintf(stderr, "[ss ingest] %u chunks, %.1f MB text: loop %.1f ms (waiting for producers %.1f ms), drain+sync %.1f ms\n",
+                n_chunks, r->len / 1e6, t_loop - t_begin, t_wait, now_ms() - t_loop);
     if (ce != cudaSuccess) { ss_reads_free(r); return ss_cuda_fail(ce, "H2D reads", __FILE__, __LINE__); }
     if (rc) { ss_reads_free(r); return rc; }
     if (src_rc) { ss_reads_free(r); return fail(src_rc, src.error()); }
-    SS_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (any_gz) { rc = gz_check(c, "ss_reads_from_files"); if (rc) { ss_reads_free(r); return rc; } }
     for (auto &g : r->seg) {
         if (g.cap > ss_reads_device_capacity(g.len) + (64ull << 20)) {      // shrink a mostly empty segment
             ss_segment small;
@@ -667,22 +766,48 @@ extern "C" int ss_ingest_files_host(const char *const *paths, int n_paths, int s
                                     int n_threads, char *out, size_t out_cap, size_t *out_len, uint32_t *n_chunks) {
     if ((n_paths > 0 && !paths) || !out_len) return fail(SS_ERR_ARG, "ss_ingest_files_host: NULL argument");
     ss_text_source src;
-    int rc = src.init(chunk_bytes, std::max(1, n_threads) + 3, n_threads, false);
+    // BGZF inputs take the same producer path as on the GPU (member batches, host-decoded boundary
+    // members); the per-member inflate the device kernel would run is executed here with the same code
+    bool bgzf = true;
+    size_t bgzf_cap = 6 * chunk_bytes;
+    if (const char *e = getenv("SS_BGZF_GPU")) bgzf = atoi(e) != 0;
+    if (const char *e = getenv("SS_BGZF_OUT_CAP")) { long long v = atoll(e); if (v >= (1 << 20)) bgzf_cap = (size_t)v; }
+    int rc = src.init(chunk_bytes, std::max(1, n_threads) + 3, n_threads, false, bgzf, bgzf_cap);
     if (rc) return fail(rc, src.error());
     rc = src.start(paths, n_paths, shard, n_shards);
     if (rc) return fail(rc, src.error());
     size_t total = 0;
     uint32_t n = 0;
-    bool overflow = false;
+    bool overflow = false, bad_member = false;
+    ssi_tables *tabs = new ssi_tables;
     while (ss_chunk *ch = src.next()) {
-        if (out && total + ch->len <= out_cap) memcpy(out + total, ch->text, ch->len);
-        else if (out) overflow = true;
-        total += ch->len;
+        const size_t len = ch->text_len();
+        if (!out) {
+        } else if (total + len + SSI_OUT_SLACK > out_cap) {
+            overflow = true;
+        } else if (ch->kind == SS_CHUNK_BGZF) {
+            uint8_t *dst = (uint8_t *)out + total;
+            memcpy(dst, ch->pre_text, ch->pre_len);
+            for (uint32_t i = 0; i < ch->n_members; i++) {
+                const ss_member &m = ch->members[i];
+                ssi_stream st;
+                ssi_stream_init(st, ch->text + m.comp_off, ch->text + m.comp_off + m.comp_len);
+                uint8_t *w = dst + m.out_off;
+                int irc = ssi_inflate(st, *tabs, &w, dst + m.out_off + m.isize + SSI_OUT_SLACK);
+                if (irc != SSI_OK || st.out_total != m.isize) bad_member = true;
+            }
+            memcpy(dst + ch->pre_len + ch->inflated_len, ch->post_text, ch->post_len);
+        } else {
+            memcpy(out + total, ch->text, ch->len);
+        }
+        total += len;
         n++;
         src.release(ch);
     }
+    delete tabs;
     rc = src.finish();
     if (rc) return fail(rc, src.error());
+    if (bad_member) return fail(SS_ERR_IO, "ss_ingest_files_host: inflate failed (invalid BGZF block)");
     *out_len = total;
     if (n_chunks) *n_chunks = n;
     if (overflow) return fail(SS_ERR_ARG, "ss_ingest_files_host: output buffer too small");
@@ -785,9 +910,10 @@ extern "C" int ss_count(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint3
 
 static int ensure_chunks(ss_ctx *c) {
     if (c->d_chunk[0]) return SS_OK;
-    size_t cap = ss_reads_device_capacity(c->chunk_bytes);
-    uint32_t tiles = (uint32_t)(c->chunk_bytes / SS_TILE) + 2;
-    for (int i = 0; i < 2; i++) {
+    const size_t text_cap = std::max(c->chunk_bytes, c->device_bgzf ? c->bgzf_out_cap + SSI_OUT_SLACK : 0);
+    size_t cap = ss_reads_device_capacity(text_cap);
+    uint32_t tiles = (uint32_t)(text_cap / SS_TILE) + 2;
+    for (int i = 0; i < SS_NSLOT; i++) {
         SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
         SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 2) * sizeof(uint32_t)));
     }
@@ -801,16 +927,27 @@ static bool is_pinned(const void *p) {
 }
 
 // the double-buffered device side of the streaming drivers
-struct stream_state { int slot = 0; uint32_t probe_launches = 0, total_launches = 0; uint64_t bytes = 0; bool used[2] = {false, false}; };
+struct stream_state { int slot = 0; uint32_t probe_launches = 0, total_launches = 0; uint64_t bytes = 0; bool used[SS_NSLOT] = {}; };
 
-// copy one record-aligned chunk (n bytes at src, host) into device slot ss.slot and scan it
-static int stream_chunk(ss_ctx *c, const ss_kmerset *s, const char *src, size_t n, stream_state &ss) {
+// copy one record-aligned chunk (n bytes at src, host) into device slot ss.slot and scan it; a BGZF
+// batch (`batch` != NULL) is inflated into the slot by the device instead
+static int stream_chunk(ss_ctx *c, const ss_kmerset *s, const char *src, size_t n, stream_state &ss,
+                        ss_chunk *batch = nullptr) {
     int b = ss.slot;
     if (ss.used[b]) SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));   // kernels done with it
-    SS_CUDA(cudaMemcpyAsync(c->d_chunk[b], src, n, cudaMemcpyHostToDevice, c->copy_stream));
-    SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
-    SS_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-    SS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    if (batch) {
+        SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
+        cudaEvent_t inflated;
+        int rc = inflate_batch(c, batch, c->d_chunk[b], &inflated);
+        if (rc) return rc;
+        SS_CUDA(cudaStreamWaitEvent(c->stream, inflated, 0));
+        ss.total_launches++;
+    } else {
+        SS_CUDA(cudaMemcpyAsync(c->d_chunk[b], src, n, cudaMemcpyHostToDevice, c->copy_stream));
+        SS_CUDA(cudaMemsetAsync(c->d_chunk[b] + n, '\n', ss_reads_device_capacity(n) - n, c->copy_stream));
+        SS_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        SS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    }
     uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
     SS_CUDA(ss_launch_index(c->d_chunk[b], tiles, c->d_chunk_line[b], 0, c->n_sm, c->stream));
     SS_CUDA(ss_launch_probe(c->d_chunk[b], n, tiles, c->d_chunk_line[b], s->view(), c->d_stats, c->d_stats + 4,
@@ -818,7 +955,7 @@ static int stream_chunk(ss_ctx *c, const ss_kmerset *s, const char *src, size_t 
     SS_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
     ss.used[b] = true;
     ss.probe_launches++; ss.total_launches += 3; ss.bytes += n;
-    ss.slot ^= 1;
+    ss.slot = (b + 1) % SS_NSLOT;
     return SS_OK;
 }
 
@@ -923,8 +1060,14 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
     stream_state ss;
     pending_ring pend(c);
-    while (ss_chunk *ch = src.next()) {
-        rc = stream_chunk(c, s, (const char *)ch->text, ch->len, ss);
+    bool any_gz = false;
+    rc = gz_begin(c);
+    while (!rc) {
+        ss_chunk *ch = src.next();
+        if (!ch) break;
+        const bool gz = ch->kind == SS_CHUNK_BGZF;
+        any_gz |= gz;
+        rc = stream_chunk(c, s, (const char *)ch->text, ch->text_len(), ss, gz ? ch : nullptr);
         if (rc) { src.release(ch); break; }
         cudaError_t e = pend.push(ch, c->copy_stream);
         if (e != cudaSuccess) { rc = ss_cuda_fail(e, "ingest event", __FILE__, __LINE__); break; }
@@ -932,10 +1075,12 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
     pend.drain();
     int src_rc = src.finish();
     if (rc || src_rc) {
-        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->copy_stream); gz_sync(c); cudaStreamSynchronize(c->stream);
         return rc ? rc : fail(src_rc, src.error());
     }
-    return finish_streamed(c, s, ss, counts, st, t0, "ss_count_files");
+    rc = finish_streamed(c, s, ss, counts, st, t0, "ss_count_files");
+    if (any_gz) { int grc = gz_check(c, "ss_count_files"); if (grc) return grc; }   // a bad block explains a framing error
+    return rc;
 }
 
 extern "C" int ss_l2_finalize(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, int64_t *py_o) {

@@ -63,16 +63,24 @@ ss_text_source::~ss_text_source() {
     for (auto &b : bufs_) { if (pinned_) cudaFreeHost(b.base); else free(b.base); }
 }
 
-int ss_text_source::init(size_t chunk_bytes, int n_buffers, int n_threads, bool pinned) {
+// room behind the text area of every chunk buffer: the two host-decoded text pieces of a BGZF batch
+#define SS_PIECE_BYTES (3u * 65536u + 4096u)
+
+int ss_text_source::init(size_t chunk_bytes, int n_buffers, int n_threads, bool pinned, bool device_bgzf,
+                         size_t bgzf_out_cap) {
     if (!bufs_.empty()) return SS_OK;
     if (chunk_bytes < 4 * (size_t)SS_INGEST_BOUNDARY) { err_msg_ = "ingest: chunk size must be at least 256 KiB"; return SS_ERR_ARG; }
+    chunk_bytes = (chunk_bytes + 15) & ~(size_t)15;
     chunk_bytes_ = chunk_bytes;
     n_threads_ = std::max(1, n_threads);
     pinned_ = pinned;
+    device_bgzf_ = device_bgzf && chunk_bytes >= (1u << 20) && bgzf_out_cap >= (1u << 18);
+    bgzf_out_cap_ = bgzf_out_cap;
     bufs_.resize((size_t)std::max(3, n_buffers));
     for (auto &b : bufs_) {
         void *p = nullptr;
-        const size_t bytes = SS_INGEST_HIST + chunk_bytes + 4096;
+        const size_t bytes = SS_INGEST_HIST + chunk_bytes + 4096 + 2 * (size_t)SS_PIECE_BYTES +
+                             (size_t)SS_BGZF_MAX_MEMBERS * sizeof(ss_member);
         cudaError_t e = cudaSuccess;
         if (pinned) e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
         else p = malloc(bytes);
@@ -86,6 +94,7 @@ int ss_text_source::init(size_t chunk_bytes, int n_buffers, int n_threads, bool 
         b.text = b.base + SS_INGEST_HIST;
         b.cap = chunk_bytes;
         b.len = 0;
+        b.members = (ss_member *)(b.text + chunk_bytes + 4096 + 2 * (size_t)SS_PIECE_BYTES);
     }
     return SS_OK;
 }
@@ -115,6 +124,8 @@ int ss_text_source::plain_boundary(const file_map &f, size_t off, size_t *out) {
     }
 }
 
+static size_t bgzf_resync(const uint8_t *p, size_t size, size_t off);
+
 int ss_text_source::start(const char *const *paths, int n_paths, int shard, int n_shards) {
     if (bufs_.empty()) { err_msg_ = "ingest: init() was not called"; return SS_ERR_ARG; }
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { err_msg_ = "reads: bad shard / n_shards"; return SS_ERR_ARG; }
@@ -142,6 +153,9 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
             if (m == MAP_FAILED) { err_msg_ = std::string("cannot mmap ") + paths[i]; close(f.fd); finish(); return SS_ERR_IO; }
             madvise(m, f.size, MADV_SEQUENTIAL);
             f.map = (const uint8_t *)m;
+            ssi_gz_header h;
+            f.bgzf = device_bgzf_ && ssi_gz_parse_header(f.map, f.map + f.size, &h) == SSI_OK && h.bgzf_bsize >= h.header_len + 8 &&
+                     h.bgzf_bsize <= f.size;
         }
         files_.push_back(f);
     }
@@ -149,6 +163,24 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
     for (size_t fi = 0; fi < files_.size(); fi++) {
         const file_map &f = files_[fi];
         if (f.size == 0) continue;
+        if (f.bgzf) {
+            // members inflate independently: cut the file into parts at member starts (found by their
+            // 16-byte BGZF header signature and confirmed by walking the chain), one producer per part
+            size_t part_min = 4 * chunk_bytes_;
+            if (const char *e = getenv("SS_BGZF_PART_BYTES")) { long long v = atoll(e); if (v >= (256 << 10)) part_min = (size_t)v; }
+            int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads_, f.size / (part_min + 1) + 1));
+            size_t prev = 0;
+            for (int pi = 1; pi <= parts; pi++) {
+                size_t b = pi == parts ? f.size : bgzf_resync(f.map, f.size, (size_t)((unsigned __int128)f.size * pi / parts));
+                if (b > prev) {
+                    job j; j.file = (int)fi; j.lo = prev; j.hi = b; j.first_of_file = (prev == 0);
+                    jobs_.push_back(j);
+                }
+                prev = std::max(prev, b);
+            }
+            gz_bytes_ += f.size;
+            continue;
+        }
         if (f.gz) {
             job j; j.file = (int)fi; j.lo = 0; j.hi = f.size; j.first_of_file = true;
             jobs_.push_back(j);
@@ -211,12 +243,16 @@ ss_chunk *ss_text_source::acquire() {
     ss_chunk *c = free_.front();
     free_.pop_front();
     c->len = 0;
+    c->kind = SS_CHUNK_TEXT;
+    c->n_members = 0;
+    c->pre_text = c->post_text = nullptr;
+    c->pre_len = c->post_len = c->inflated_len = 0;
     return c;
 }
 
 void ss_text_source::emit(ss_chunk *c) {
     std::lock_guard<std::mutex> lk(mu_);
-    if (c->len == 0) { free_.push_back(c); cv_free_.notify_one(); return; }
+    if (c->text_len() == 0) { free_.push_back(c); cv_free_.notify_one(); return; }
     ready_.push_back(c);
     cv_ready_.notify_one();
 }
@@ -244,7 +280,9 @@ void ss_text_source::worker() {
             if (stop_ || next_job_ >= jobs_.size()) break;
             j = jobs_[next_job_++];
         }
-        if (files_[(size_t)j.file].gz) run_gz(j);
+        const file_map &f = files_[(size_t)j.file];
+        if (f.bgzf) run_bgzf(j);
+        else if (f.gz) run_gz(j);
         else run_plain(j);
     }
     std::lock_guard<std::mutex> lk(mu_);
@@ -362,4 +400,216 @@ void ss_text_source::run_gz(const job &j) {
         c = c2;
     }
     delete g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BGZF (blocked gzip: every member carries its own size in a "BC" extra field and inflates on its own).
+// The producer only walks the member chain and stages compressed bytes; the DEVICE inflates
+// (ss_gunzip.cu).  To hand out batches that begin and end on FASTQ record boundaries without a device
+// round trip, the member at every batch boundary is inflated here, on the host, and split at a record
+// start: its head closes this batch (post_text), its tail opens the next one (pre_text).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct bgzf_member { uint32_t hdr, bsize, isize; };
+
+int bgzf_parse(const uint8_t *p, size_t size, size_t at, bgzf_member *m) {
+    ssi_gz_header h;
+    if (ssi_gz_parse_header(p + at, p + size, &h) != SSI_OK || h.bgzf_bsize < h.header_len + 8 || at + h.bgzf_bsize > size) return -1;
+    m->hdr = h.header_len; m->bsize = h.bgzf_bsize;
+    const uint8_t *q = p + at + h.bgzf_bsize - 4;
+    m->isize = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    return m->isize <= 65536u ? 0 : -1;            // BGZF blocks hold at most 64 KiB of text
+}
+
+// inflate one member on the host, appending its text to `out`
+int bgzf_host_inflate(const uint8_t *p, size_t at, const bgzf_member &m, std::vector<uint8_t> &out) {
+    size_t o = out.size();
+    out.resize(o + m.isize + SSI_OUT_SLACK);
+    ssi_stream s;
+    ssi_tables t;
+    ssi_stream_init(s, p + at + m.hdr, p + at + m.bsize - 8);
+    uint8_t *w = out.data() + o;
+    int rc = ssi_inflate(s, t, &w, out.data() + out.size());
+    if (rc != SSI_OK || s.out_total != m.isize) return -1;
+    out.resize(o + m.isize);
+    return 0;
+}
+}   // namespace
+
+// first member start at or after `off`: the fixed bytes of a BGZF header (magic, deflate, FEXTRA, XLEN = 6,
+// "BC", SLEN = 2) confirmed by three chained members (or the file end)
+static size_t bgzf_resync(const uint8_t *p, size_t size, size_t off) {
+    for (size_t at = off; at + 18 <= size; at++) {
+        const uint8_t *q = (const uint8_t *)memchr(p + at, 0x1f, size - 18 - at + 1);
+        if (!q) return size;
+        at = (size_t)(q - p);
+        if (q[1] != 0x8b || q[2] != 8 || q[3] != 4 || q[12] != 'B' || q[13] != 'C') continue;
+        size_t w = at;
+        bool ok = true;
+        bgzf_member m;
+        for (int k = 0; k < 3 && w < size && ok; k++) {
+            ok = bgzf_parse(p, size, w, &m) == 0;
+            w += m.bsize;
+        }
+        if (ok) return at;
+    }
+    return size;
+}
+
+// Text of the member(s) at file offset `at` (a member start), extended by up to two more members until a
+// FASTQ record start shows up behind its first byte: *cut is that record start, *next the offset of the
+// first member not consumed.  The part that ends at `at` and the part that starts there both call this
+// and so agree on where one stops and the other begins.  Returns 0, or -1 on a broken chain;
+// *cut == text.size() when there is no record start before the file ends.
+static int bgzf_boundary(const uint8_t *p, size_t size, size_t at, std::vector<uint8_t> &text, size_t *cut, size_t *next) {
+    text.clear();
+    *cut = 0;
+    bgzf_member m;
+    for (int tries = 0; at < size; tries++) {
+        if (bgzf_parse(p, size, at, &m) || bgzf_host_inflate(p, at, m, text)) return -1;
+        at += m.bsize;
+        *cut = ss_find_record_start((const char *)text.data(), text.size(), 1);
+        if (*cut < text.size() || tries == 2) break;
+    }
+    *next = at;
+    if (*cut > text.size()) *cut = text.size();
+    return 0;
+}
+
+void ss_text_source::run_bgzf(const job &j) {
+    const file_map &f = files_[(size_t)j.file];
+    const uint8_t *p = f.map;                       // headers, trailers and boundary members are read through the map;
+    const size_t size = f.size;                     // the bulk of the compressed bytes goes pread -> pinned buffer
+    const std::string bad = "inflate failed on " + f.path + ": broken BGZF member chain";
+    const size_t out_cap = bgzf_out_cap_ - 2 * (size_t)SS_PIECE_BYTES;
+    std::vector<uint8_t> carry, btext;
+    bgzf_member m;
+    size_t pos = j.lo;
+    uint64_t batch_idx = 0;
+    if (j.lo == 0) {                                // head check on the first data member's text
+        size_t at = 0;
+        while (at < size) {
+            if (bgzf_parse(p, size, at, &m)) { fail(SS_ERR_IO, bad); return; }
+            if (m.isize) break;
+            at += m.bsize;
+        }
+        if (at < size) {
+            if (bgzf_host_inflate(p, at, m, btext)) { fail(SS_ERR_IO, bad); return; }
+            std::string msg;
+            int rc = check_head(btext.data(), ss_trim_tail((const char *)btext.data(), btext.size()), f.path, msg);
+            if (rc) { fail(rc, msg); return; }
+        }
+    } else {                                        // a later part of the file: it owns the text behind the first record start
+        size_t cut = 0;
+        if (bgzf_boundary(p, size, j.lo, btext, &cut, &pos)) { fail(SS_ERR_IO, bad); return; }
+        carry.assign(btext.begin() + (long)cut, btext.end());
+    }
+    bool done = false;
+    while (!done) {
+        ss_chunk *c = acquire();
+        if (!c) return;
+        c->kind = SS_CHUNK_BGZF;
+        uint8_t *pieces = c->text + c->cap + 4096;
+        memcpy(pieces, carry.data(), carry.size());
+        c->pre_text = pieces; c->pre_len = carry.size();
+        carry.clear();
+        // members for the device: a contiguous run of the file, up to (not including) the batch's boundary member
+        const size_t run_lo = pos;
+        size_t run_hi = pos, out_sum = 0;
+        uint32_t n = 0;
+        bool err = false, part_end = false;
+        while (true) {
+            if (pos >= j.hi || pos >= size) { part_end = true; break; }
+            if (bgzf_parse(p, size, pos, &m)) { err = true; break; }
+            if (m.isize == 0) { pos += m.bsize; if (n) run_hi = pos; continue; }     // empty member (EOF marker)
+            const bool fits = pos + m.bsize - run_lo + 16 <= c->cap && out_sum + m.isize <= out_cap && n < SS_BGZF_MAX_MEMBERS;
+            if (!fits) break;
+            // the last data member of the whole file is decoded on the host (its tail may need trimming)
+            if (j.hi >= size) {
+                size_t nx = pos + m.bsize;
+                bgzf_member e;
+                while (nx < size && bgzf_parse(p, size, nx, &e) == 0 && e.isize == 0) nx += e.bsize;
+                if (nx >= size) break;
+            }
+            ss_member &t = c->members[n++];
+            t.comp_off = (uint32_t)(pos - run_lo + m.hdr); t.comp_len = m.bsize - m.hdr - 8;
+            t.out_off = (uint32_t)(c->pre_len + out_sum); t.isize = m.isize;
+            out_sum += m.isize;
+            pos += m.bsize;
+            run_hi = pos;
+        }
+        if (err) { release(c); fail(SS_ERR_IO, bad); return; }
+        for (size_t have = 0, want = n ? run_hi - run_lo : 0; have < want;) {
+            ssize_t got = pread(f.fd, c->text + have, want - have, (off_t)(run_lo + have));
+            if (got <= 0) { release(c); fail(SS_ERR_IO, "short read on " + f.path); return; }
+            have += (size_t)got;
+        }
+        // the text that closes this batch
+        uint8_t *post = pieces + SS_PIECE_BYTES;
+        size_t post_len = 0;
+        if (part_end && j.hi < size) {              // the next part's first member(s): mine up to the agreed record start
+            size_t cut = 0, nx = 0;
+            if (bgzf_boundary(p, size, j.hi, btext, &cut, &nx)) { release(c); fail(SS_ERR_IO, bad); return; }
+            memcpy(post, btext.data(), cut);
+            post_len = cut;
+            done = true;
+        } else if (part_end || pos >= size) {       // nothing left at all
+            done = true;
+        } else {                                    // boundary member(s) inside my part, split at a late record start
+            btext.clear();
+            size_t cut = 0;
+            bool found = false, file_end = false;
+            for (int tries = 0; tries < 3 && !found; tries++) {
+                if (bgzf_parse(p, size, pos, &m) || bgzf_host_inflate(p, pos, m, btext)) { err = true; break; }
+                pos += m.bsize;
+                bgzf_member e;
+                while (pos < size && bgzf_parse(p, size, pos, &e) == 0 && e.isize == 0) pos += e.bsize;
+                if (pos >= size) { file_end = true; break; }
+                const size_t bn = btext.size();
+                cut = ss_find_record_start((const char *)btext.data(), bn, bn > 32768 ? bn - 32768 : 1);
+                if (cut >= bn) cut = ss_find_record_start((const char *)btext.data(), bn, 1);
+                found = cut < bn;
+                if (pos >= j.hi) break;             // do not run into the next part's members
+            }
+            if (err) { release(c); fail(SS_ERR_IO, bad); return; }
+            if (file_end) {                         // the file's last data member: trim blank tail lines, close the last line
+                size_t bn = ss_trim_tail((const char *)btext.data(), btext.size());
+                memcpy(post, btext.data(), bn);
+                if (bn) post[bn++] = '\n';
+                post_len = bn;
+                done = true;
+            } else if (found) {
+                memcpy(post, btext.data(), cut);
+                post_len = cut;
+                carry.assign(btext.begin() + (long)cut, btext.end());
+            } else if (pos >= j.hi) {               // no record start before my part ends: hand everything to the closing step
+                if (btext.size() > SS_PIECE_BYTES - 8) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within three BGZF blocks"); return; }
+                memcpy(post, btext.data(), btext.size());
+                post_len = btext.size();
+                size_t cut2 = 0, nx = 0;
+                std::vector<uint8_t> more;
+                if (j.hi < size) {
+                    if (bgzf_boundary(p, size, j.hi, more, &cut2, &nx)) { release(c); fail(SS_ERR_IO, bad); return; }
+                    if (post_len + cut2 > SS_PIECE_BYTES - 8) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within three BGZF blocks"); return; }
+                    memcpy(post + post_len, more.data(), cut2);
+                    post_len += cut2;
+                }
+                done = true;
+            } else {
+                release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within three BGZF blocks"); return;
+            }
+        }
+        c->post_text = post; c->post_len = post_len;
+        c->len = n ? run_hi - run_lo : 0; c->n_members = n; c->inflated_len = out_sum;
+        if (n == 0) {                                   // nothing for the device: deliver it as plain text
+            memmove(c->text, c->pre_text, c->pre_len);
+            memcpy(c->text + c->pre_len, c->post_text, c->post_len);
+            c->kind = SS_CHUNK_TEXT;
+            c->len = c->pre_len + c->post_len;
+            c->pre_len = c->post_len = 0;
+        }
+        if ((batch_idx + (uint64_t)j.file + (uint64_t)(j.lo >> 20)) % (uint64_t)n_shards_ == (uint64_t)shard_) emit(c);
+        else release(c);
+        batch_idx++;
+    }
 }

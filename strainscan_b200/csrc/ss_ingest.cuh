@@ -18,11 +18,32 @@
 #define SS_INGEST_HIST 32768u            // deflate history kept in front of every chunk's text area
 #define SS_INGEST_BOUNDARY (64u << 10)   // a FASTQ record boundary is searched in the last 64 KiB of a chunk
 
+// One independently inflatable gzip member (BGZF block) of a batch; the device kernel's work item.
+struct ss_member {
+    uint32_t comp_off;    // raw deflate stream inside the batch's compressed bytes
+    uint32_t comp_len;
+    uint32_t out_off;     // where its text goes, relative to the start of the batch's text
+    uint32_t isize;       // inflated size (ISIZE of the trailer)
+};
+#define SS_BGZF_MAX_MEMBERS 16384u
+
+// A chunk is either plain TEXT (whole FASTQ records in `text[0, len)`) or a BGZF batch, whose text is
+//   [pre_text][members inflated on the DEVICE][post_text]      (pre_len + inflated_len + post_len bytes)
+// with the compressed members in text[0, len), the two host-decoded text pieces behind them (the
+// boundary member of every batch is inflated by the producer so that batches begin and end on record
+// boundaries) and the member table in `members`.
+enum { SS_CHUNK_TEXT = 0, SS_CHUNK_BGZF = 1 };
 struct ss_chunk {
-    uint8_t *base = nullptr;   // pinned allocation: [SS_INGEST_HIST history][cap text bytes][slack]
-    uint8_t *text = nullptr;   // whole FASTQ records, starts at a record start, ends with '\n'
+    uint8_t *base = nullptr;   // pinned allocation: [SS_INGEST_HIST history][cap text bytes][slack][member table]
+    uint8_t *text = nullptr;   // TEXT: whole FASTQ records ending with '\n'; BGZF: compressed members
     size_t len = 0;
     size_t cap = 0;
+    int kind = SS_CHUNK_TEXT;
+    ss_member *members = nullptr;      // SS_BGZF_MAX_MEMBERS entries (pinned)
+    uint32_t n_members = 0;
+    const uint8_t *pre_text = nullptr, *post_text = nullptr;   // inside this buffer, behind the compressed bytes
+    size_t pre_len = 0, post_len = 0, inflated_len = 0;
+    size_t text_len() const { return kind == SS_CHUNK_TEXT ? len : pre_len + inflated_len + post_len; }
 };
 
 // FASTQ framing helpers shared with ss_api.cu
@@ -39,7 +60,10 @@ public:
     // Allocate `n_buffers` pinned chunk buffers of `chunk_bytes` text capacity (kept for the life of the
     // object).  Needs a current CUDA device.
     // `pinned` = false uses plain host memory (host-only tools and tests; no CUDA context needed).
-    int init(size_t chunk_bytes, int n_buffers, int n_threads, bool pinned = true);
+    // `device_bgzf`: deliver BGZF files as SS_CHUNK_BGZF batches for the device inflate kernel (at most
+    // `bgzf_out_cap` text bytes per batch); otherwise they are decoded on the host like any gzip stream.
+    int init(size_t chunk_bytes, int n_buffers, int n_threads, bool pinned = true, bool device_bgzf = false,
+             size_t bgzf_out_cap = 0);
     // Start producing shard `shard` of `n_shards` of the given files.  Plain files are split into
     // record-aligned byte ranges (one range per rank and producer); gzip streams are decoded whole by
     // every rank and their chunks are dealt round-robin.
@@ -51,15 +75,17 @@ public:
     size_t chunk_bytes() const { return chunk_bytes_; }
     uint64_t plain_bytes() const { return plain_bytes_; }   // bytes of plain text this shard will deliver
     uint64_t gz_bytes() const { return gz_bytes_; }         // compressed bytes of the gzip inputs
+    size_t bgzf_out_cap() const { return bgzf_out_cap_; }
     bool ready() const { return !bufs_.empty(); }
 
 private:
-    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false; };
+    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false, bgzf = false; };
     struct job { int file = 0; size_t lo = 0, hi = 0; bool first_of_file = false; };
 
     void worker();
     void run_plain(const job &j);
     void run_gz(const job &j);
+    void run_bgzf(const job &j);
     ss_chunk *acquire();
     void emit(ss_chunk *c);
     void fail(int code, const std::string &msg);
@@ -67,7 +93,8 @@ private:
 
     size_t chunk_bytes_ = 0;
     int n_threads_ = 1;
-    bool pinned_ = true;
+    bool pinned_ = true, device_bgzf_ = false;
+    size_t bgzf_out_cap_ = 0;
     std::vector<ss_chunk> bufs_;
     std::vector<file_map> files_;
     std::vector<job> jobs_;

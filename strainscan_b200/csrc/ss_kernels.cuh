@@ -32,3 +32,9 @@ cudaError_t ss_launch_strain_reduce(const unsigned long long *col_ptr, const uin
                                     unsigned long long *covered, unsigned long long *sum, cudaStream_t st);
 cudaError_t ss_launch_random_gather(const void *buf, uint64_t n_sectors, uint64_t n_probes, uint64_t seed,
                                     unsigned long long *sink, int n_sm, cudaStream_t st);
+
+struct ss_member;
+// device inflate of `n_members` independent gzip members: out[tab[i].out_off ...] = inflate(comp + tab[i].comp_off);
+// *err receives the smallest failing member index (initialise to 0xFFFFFFFF), *next is scratch
+cudaError_t ss_launch_gunzip(const uint8_t *comp, const ss_member *tab, uint32_t n_members, uint8_t *out,
+                             unsigned int *next, unsigned int *err, int n_sm, cudaStream_t st);

@@ -171,3 +171,95 @@ def test_random_deflate_streams_roundtrip(tmp_path):
             open(p, "wb").write(gzip.compress(fq, lvl))
             got, _ = ingest([p], chunk=4 << 20, threads=1)
             assert got == fq, (i, lvl)
+
+
+# ---- BGZF: the producer path that feeds the device inflate kernel (ss_gunzip.cu) ----------------------
+# ss_ingest_files_host runs the same batching (member chain walk, host-decoded boundary members, record
+# aligned batches) and executes the per-member inflate the kernel would run with the same source.
+BGZF_CHUNK = 1 << 20
+
+
+@pytest.mark.parametrize("block,level,empties", [(0xFF00, 6, 0), (10_000, 1, 0), (65536, 9, 0), (3000, 6, 3), (200, 6, 0)])
+def test_bgzf_batches_roundtrip(fastq, tmp_path, monkeypatch, block, level, empties):
+    import gzip as _gz
+    data = util.bgzf_compress(fastq, block=block, level=level, empty_every=empties)
+    assert _gz.decompress(data) == fastq                       # the writer itself is a valid multi-member gzip
+    p = str(tmp_path / "b.fq.gz")
+    open(p, "wb").write(data)
+    monkeypatch.setenv("SS_BGZF_OUT_CAP", str(1 << 20))        # ~600 KB of device text per batch: several batches
+    got, n_chunks = ingest([p], chunk=BGZF_CHUNK, threads=1)
+    assert got == fastq
+    assert n_chunks >= 3
+    monkeypatch.setenv("SS_BGZF_GPU", "0")                     # same file through the host gzip stream
+    assert ingest([p], chunk=BGZF_CHUNK, threads=1)[0] == fastq
+
+
+def test_bgzf_sharded_paired_and_tails(fastq, tmp_path, monkeypatch):
+    monkeypatch.setenv("SS_BGZF_OUT_CAP", str(1 << 20))
+    half = len(fastq) // 2
+    half = fastq.index(b"\n@", half) + 1
+    while not fastq[half:].split(b"\n", 3)[2].startswith(b"+"):
+        half = fastq.index(b"\n@", half) + 1
+    p1, p2 = str(tmp_path / "r1.fq.gz"), str(tmp_path / "r2.fq.gz")
+    open(p1, "wb").write(util.bgzf_compress(fastq[:half - 1], eof_marker=False))      # no final newline, no EOF marker
+    open(p2, "wb").write(util.bgzf_compress(fastq[half:] + b"\n \n"))                  # blank tail lines
+    assert records(ingest([p1, p2], chunk=BGZF_CHUNK)[0]) == records(fastq)
+    for n in (2, 3):
+        parts = [ingest([p1, p2], s, n, chunk=BGZF_CHUNK)[0] for s in range(n)]
+        assert records(b"".join(parts)) == records(fastq)
+        assert all(parts)
+
+
+def test_bgzf_small_and_broken(tmp_path, monkeypatch):
+    tiny = b"@r\nACGTACGT\n+\nIIIIIIII\n"
+    p = str(tmp_path / "tiny.fq.gz")
+    open(p, "wb").write(util.bgzf_compress(tiny))
+    assert ingest([p], chunk=BGZF_CHUNK) == (tiny, 1)
+    open(p, "wb").write(util.bgzf_compress(b""))
+    assert ingest([p], chunk=BGZF_CHUNK) == (b"", 0)
+    rng = np.random.default_rng(3)
+    fq = util.make_reads(rng, util.rand_genome(rng, 20_000), 3000, 150)
+    good = util.bgzf_compress(fq, block=20_000)
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x10                                 # inside some member's deflate data
+    open(p, "wb").write(bytes(bad))
+    try:
+        got, _ = ingest([p], chunk=BGZF_CHUNK)
+        assert got != fq
+    except _lib.StrainScanB200Error as e:
+        assert e.code in (_lib.SS_ERR_IO, _lib.SS_ERR_FORMAT)
+    open(p, "wb").write(good[:len(good) // 2])                 # chain cut inside a member
+    with pytest.raises(_lib.StrainScanB200Error):
+        ingest([p], chunk=BGZF_CHUNK)
+    open(p, "wb").write(util.bgzf_compress(b">r1\nACGT\n"))
+    with pytest.raises(_lib.StrainScanB200Error, match="FASTA"):
+        ingest([p], chunk=BGZF_CHUNK)
+
+
+@pytest.mark.parametrize("block", [0xFF00, 5000, 300])
+def test_bgzf_file_parts_agree_on_record_boundaries(tmp_path, monkeypatch, block):
+    """A BGZF file is cut into parts at member starts (one producer each); neighbouring parts split the
+    boundary member's text at the same record start, so every read is delivered exactly once."""
+    rng = np.random.default_rng(21)
+    fq = util.make_reads(rng, util.rand_genome(rng, 30_000), 16_000, 150, var_len=True)     # ~5 MB
+    monkeypatch.setenv("SS_BGZF_PART_BYTES", str(256 << 10))
+    monkeypatch.setenv("SS_BGZF_OUT_CAP", str(1 << 20))
+    p = str(tmp_path / "parts.fq.gz")
+    open(p, "wb").write(util.bgzf_compress(fq, block=block, level=1))
+    for threads in (1, 4, 7):
+        got, n_chunks = ingest([p], chunk=BGZF_CHUNK, threads=threads)
+        assert len(got) == len(fq) and records(got) == records(fq), (block, threads)
+    for n in (2, 3):
+        parts = [ingest([p], s, n, chunk=BGZF_CHUNK, threads=4)[0] for s in range(n)]
+        assert records(b"".join(parts)) == records(fq)
+    # one very long record spanning many members: no record start inside the boundary members
+    long_fq = b"@r0\n" + b"ACGT" * 100_000 + b"\n+\n" + b"I" * 400_000 + b"\n" + fq[:200_000]
+    long_fq = long_fq[:long_fq.rindex(b"\n@") + 1]
+    while not long_fq.endswith(b"\n") or len(long_fq.split(b"\n")) % 4 != 1:
+        long_fq = long_fq[:long_fq.rindex(b"\n@") + 1]
+    open(p, "wb").write(util.bgzf_compress(long_fq, block=0xFF00))
+    try:
+        got, _ = ingest([p], chunk=BGZF_CHUNK, threads=4)
+        assert records(got) == records(long_fq)
+    except _lib.StrainScanB200Error as e:          # a loud, documented limit (like the 64 KiB rule of the plain chunker)
+        assert e.code == _lib.SS_ERR_FORMAT and "record boundary" in str(e)

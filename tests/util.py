@@ -74,3 +74,27 @@ def make_reads(rng, genome, n, read_len=150, p_sub=0.01, p_n=0.002, var_len=Fals
             q = b"I" * L
         out.append(b"@read%d some comment" % i + nl + r + nl + b"+" + nl + q + nl)
     return b"".join(out)
+
+
+def bgzf_compress(data, block=0xFF00, level=6, eof_marker=True, empty_every=0):
+    """Blocked gzip (BGZF, SAM spec 4.1): every member holds <= 64 KiB of text and its own total size in a
+    'BC' extra subfield, so members inflate independently.  Written from the spec (bgzip is not in the image)."""
+    import struct
+    import zlib
+
+    def member(chunk):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(raw) + 8
+        assert bsize <= 65536
+        return (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+                + raw + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    out = []
+    for n, i in enumerate(range(0, len(data), block)):
+        out.append(member(data[i:i + block]))
+        if empty_every and n % empty_every == empty_every - 1:
+            out.append(member(b""))
+    if eof_marker:
+        out.append(member(b""))
+    return b"".join(out)

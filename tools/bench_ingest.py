@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reads", type=int, default=2_000_000)
     ap.add_argument("--leaves", type=int, default=823)
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--only-bgzf", action="store_true")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -47,11 +48,27 @@ def main():
         host[:half].tofile(r1)
         host[half:].tofile(r2)
         t0 = time.perf_counter()
-        procs = [subprocess.Popen("gzip -1 -c %s > %s.gz" % (p, p), shell=True) for p in (plain, r1, r2)]
+        procs = [] if a.only_bgzf else [subprocess.Popen("gzip -1 -c %s > %s.gz" % (p, p), shell=True) for p in (plain, r1, r2)]
         for p in procs:
             p.wait()
         out["gzip_1_seconds"] = time.perf_counter() - t0
-        out["gz_bytes"] = os.path.getsize(plain + ".gz")
+        out["gz_bytes"] = os.path.getsize(plain + ".gz") if not a.only_bgzf else None
+        # blocked gzip (BGZF) of the same text: written block-parallel, inflated on the device
+        from multiprocessing import Pool
+        from tests import util
+        t0 = time.perf_counter()
+        for src_path in (plain, r1, r2):
+            data = open(src_path, "rb").read()
+            step = 0xFF00 * 128
+            with Pool(min(16, os.cpu_count() or 1)) as pool:
+                parts = pool.starmap(util.bgzf_compress, [(data[i:i + step], 0xFF00, 1, False) for i in range(0, len(data), step)])
+            with open(src_path + ".bgz.gz", "wb") as f:
+                for part in parts:
+                    f.write(part)
+                f.write(util.bgzf_compress(b""))
+            del data, parts
+        out["bgzf_write_seconds"] = time.perf_counter() - t0
+        out["bgzf_bytes"] = os.path.getsize(plain + ".bgz.gz")
         ref_counts = None
         kpr = params.read_len - params.k + 1
 
@@ -82,9 +99,12 @@ def main():
                 "stream_kmers_per_s": a.reads * kpr / min(ts)}
 
         run("plain_se", [plain])
-        run("gz_se", [plain + ".gz"])
-        run("gz_pe", [r1 + ".gz", r2 + ".gz"])
-        run("plain_pe", [r1, r2])
+        if not a.only_bgzf:
+            run("gz_se", [plain + ".gz"])
+            run("gz_pe", [r1 + ".gz", r2 + ".gz"])
+            run("plain_pe", [r1, r2])
+        run("bgzf_se_device_inflate", [plain + ".bgz.gz"])
+        run("bgzf_pe_device_inflate", [r1 + ".bgz.gz", r2 + ".bgz.gz"])
 
         jf = os.path.join(ROOT, "oracle", "_ref", "jellyfish-linux")
         if not a.no_reference and os.access(jf, os.X_OK):
