@@ -409,7 +409,7 @@ def main():
         e2e = {"value": tot_kmers / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_bytes,
                "d2h_bytes_per_step": 4 * kset.n_records, "ms_per_step": e_ms,
                "reads_per_s": tot_reads / (e_ms * 1e-3), "wall_ms_per_step": float(te[1]) / args.steps,
-               "api": "ss_count_host (C ABI) from pinned host FASTQ text, 64 MiB chunks, copy/compute overlapped"}
+               "api": "ss_count_host (C ABI) from pinned host FASTQ text, 32 MiB chunks over 4 device slots, copy/compute overlapped; bytes are per rank"}
         del host_text
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------

@@ -30,7 +30,10 @@ def collect_reports(out_dir):
 
 
 def run_case(engine, db_dir, name, work):
+    """db_dir: one DB directory, or the {low_mem: dir} dict of synth_db.write_dbs()."""
     db = synth_db.SynthDB()
+    if isinstance(db_dir, dict):
+        db_dir = db_dir[bool(synth_db.CASES[name].get("low_mem", False))]
     args = synth_db.make_case_inputs(db, name, work)
     out = os.path.join(work, "out_%s_%s" % (engine, name))
     cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_pipeline.py"), "--engine", engine, "--"] + args + \
@@ -44,7 +47,7 @@ def run_case(engine, db_dir, name, work):
 def main():
     names = sys.argv[1:] or sorted(synth_db.CASES)
     with tempfile.TemporaryDirectory() as work:
-        db_dir = synth_db.SynthDB().write(os.path.join(work, "DB"))
+        db_dir = synth_db.write_dbs(work)
         for name in names:
             reports, log = run_case("reference", db_dir, name, work)
             dst = os.path.join(HERE, "pipeline", name)

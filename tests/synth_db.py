@@ -94,12 +94,18 @@ class SynthDB:
                     out[own].append(revcomp(km))
         return out
 
-    def write(self, db_dir):
+    def write(self, db_dir, low_mem=False):
+        """low_mem: the `-e 1` memory-efficient layout -- kmer.fa keeps only the lexicographically smaller
+        strand of every k-mer (Build_tree_mem.py:107-110) and <DB>/Memory_DB makes StrainScan.py:188-196 route
+        the search through identify_low_mem (reads are still counted without -C: only same-strand hits)."""
         rng = np.random.default_rng(self.seed + 1)
         tdb = os.path.join(db_dir, "Tree_database")
         os.makedirs(os.path.join(tdb, "kmers"), exist_ok=True)
         os.makedirs(os.path.join(db_dir, "Cluster_Result"), exist_ok=True)
         nk = self._node_kmers()
+        if low_mem:
+            nk = {v: [km for km in kms if km <= revcomp(km)] for v, kms in nk.items()}
+            open(os.path.join(db_dir, "Memory_DB"), "w").close()
         allk = [(v, km) for v in range(1, 8) for km in dict.fromkeys(nk[v])]
         order = rng.permutation(len(allk))
         node_ord = {v: [] for v in range(1, 8)}
@@ -180,9 +186,13 @@ class SynthDB:
         return [out[i] for i in order]
 
 
-def write_fastq(path, reads, start=0):
+def write_fastq(path, reads, start=0, bgzf=False):
     data = b"".join(b"@syn.%d\n%s\n+\n%s\n" % (start + i, r, b"I" * len(r)) for i, r in enumerate(reads))
-    if path.endswith(".gz"):
+    if bgzf:                                  # blocked gzip: `zcat` reads it as concatenated members, the GPU path
+        from tests import util                # inflates the members on the device
+        with open(path, "wb") as f:
+            f.write(util.bgzf_compress(data, block=20_000, level=6))
+    elif path.endswith(".gz"):
         with gzip.open(path, "wb", compresslevel=4) as f:
             f.write(data)
     else:
@@ -199,16 +209,30 @@ CASES = {
     "singleton_cluster": dict(mix=[((3, 1), 8)], flags=[], pe=False, gz=True),
     "low_depth_prob": dict(mix=[((2, 1), 0.6), ((4, 2), 0.4)], flags=["-l", "2", "-b", "1"], pe=False, gz=False),
     "extra_region": dict(mix=[((1, 2), 10), ((2, 2), 5)], flags=["-e", "1"], pe=False, gz=False),
+    "low_mem_db": dict(mix=[((1, 3), 14), ((2, 1), 9)], flags=[], pe=False, gz=False, low_mem=True),
+    "two_strains_pe_bgzf": dict(mix=[((4, 1), 9), ((4, 2), 7), ((1, 1), 5)], flags=[], pe=True, gz=True, bgzf=True),
 }
+
+
+# read-sampling seeds, fixed per case (the committed golden reports depend on them)
+CASE_SEEDS = {"extra_region": 1, "low_depth_prob": 2, "same_cluster_two_strains": 3, "singleton_cluster": 4,
+              "two_clusters_pe_gz": 5, "two_clusters_se": 6, "low_mem_db": 7, "two_strains_pe_bgzf": 8}
 
 
 def make_case_inputs(db, name, out_dir):
     case = CASES[name]
-    reads = db.reads(case["mix"], seed=sorted(CASES).index(name) + 1)
+    reads = db.reads(case["mix"], seed=CASE_SEEDS[name])
     ext = ".fq.gz" if case["gz"] else ".fq"
+    bgzf = case.get("bgzf", False)
     if case["pe"]:
         h = len(reads) // 2
-        a = write_fastq(os.path.join(out_dir, name + "_1" + ext), reads[:h])
-        b = write_fastq(os.path.join(out_dir, name + "_2" + ext), reads[h:], start=h)
+        a = write_fastq(os.path.join(out_dir, name + "_1" + ext), reads[:h], bgzf=bgzf)
+        b = write_fastq(os.path.join(out_dir, name + "_2" + ext), reads[h:], start=h, bgzf=bgzf)
         return ["-i", a, "-j", b]
-    return ["-i", write_fastq(os.path.join(out_dir, name + ext), reads)]
+    return ["-i", write_fastq(os.path.join(out_dir, name + ext), reads, bgzf=bgzf)]
+
+
+def write_dbs(base_dir):
+    """Both database layouts the cases use: {low_mem flag: DB directory}."""
+    db = SynthDB()
+    return {False: db.write(os.path.join(base_dir, "DB")), True: db.write(os.path.join(base_dir, "DB_mem"), low_mem=True)}

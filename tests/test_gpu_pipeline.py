@@ -5,7 +5,9 @@ C*/StrainVote.report and strain_prob.txt BYTE-IDENTICAL to the reference run wit
 jellyfish-linux (golden reports in tests/golden/pipeline/, made by tests/golden/make_pipeline_golden.py).
 
 Covers single-end / paired-end + gz, two clusters, two strains in one cluster (ElasticNet path),
-an all-singleton result, -l 2 -b 1 (low depth + probability report) and -e 1 (extraRegion_mode).
+an all-singleton result, -l 2 -b 1 (low depth + probability report), -e 1 (extraRegion_mode), a
+memory-efficient database (Memory_DB -> identify_low_mem, canonical-strand k-mer set) and paired
+blocked-gzip inputs (inflated on the device).
 Needs baseline/_ref (git-ignored, travels to the GPU box with gpurun); skipped when it is absent."""
 import os
 import sys
@@ -23,7 +25,7 @@ HAVE_REF = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "library"))
 
 @pytest.fixture(scope="module")
 def db_dir(tmp_path_factory):
-    return synth_db.SynthDB().write(str(tmp_path_factory.mktemp("db") / "DB"))
+    return synth_db.write_dbs(str(tmp_path_factory.mktemp("db")))
 
 
 def _golden(name):
