@@ -12,9 +12,9 @@
 #include "ss_ingest.cuh"
 #include "ss_kernels.cuh"
 
-#define SS_GUNZIP_WARPS 2
+#define SS_GUNZIP_WARPS 1        // one decoder per CTA: its tables sit at a fixed shared-memory address
 #ifndef SS_GUNZIP_MINCTAS
-#define SS_GUNZIP_MINCTAS 16      // 64 registers: 30 one-lane decoders per SM (shared memory allows 15 CTAs)
+#define SS_GUNZIP_MINCTAS 32      // 64 registers: 32 one-lane decoders per SM (the CTA limit; 7 KB of tables each)
 #endif
 
 __global__ void __launch_bounds__(SS_GUNZIP_WARPS * 32, SS_GUNZIP_MINCTAS)
@@ -42,7 +42,7 @@ cudaError_t ss_launch_gunzip(const uint8_t *comp, const ss_member *tab, uint32_t
     cudaError_t e = cudaMemsetAsync(next, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     uint32_t grid = (n_members + SS_GUNZIP_WARPS - 1) / SS_GUNZIP_WARPS;
-    uint32_t cap = (uint32_t)n_sm * 16u;
+    uint32_t cap = (uint32_t)n_sm * 32u;
     if (grid > cap) grid = cap;
     ss_gunzip_kernel<<<grid, SS_GUNZIP_WARPS * 32, 0, st>>>(comp, tab, n_members, out, next, err);
     return cudaGetLastError();

@@ -361,10 +361,11 @@ SS_HD int ssi_huff_fast(ssi_stream &s, const ssi_tables &t, uint8_t **out_io, co
     *out_io = out;
     return ret;
 #else
-    // DEVICE fast path (one lane of a warp walks the stream, ss_gunzip.cu): the bit buffer, the input cursor
-    // and one prefetched input word live in registers; input is read as aligned 32-bit words one word
-    // ahead of its use, so the only latency on the per-symbol dependency chain is the shared-memory
-    // table lookup.  Needs 16 readable bytes behind in_end (the staging buffers are padded).
+    // DEVICE fast path (one lane of a warp walks the stream, ss_gunzip.cu).  A lone lane issues one instruction
+    // every ~5 cycles, so the loop is written for instruction count: the bit buffer, a 32-bit word index into
+    // the (4-byte aligned) input and one prefetched input word live in registers; the refill and the
+    // sub-table step are real, rarely taken branches; the loop bounds are checked once per burst of
+    // symbols, not per symbol.  Needs 16 readable bytes behind in_end (the staging buffers are padded).
     ssi_bits &b = s.bits;
     if (b.overrun || b.in_end - b.in < 64 || out_end - *out_io < 2 * SSI_OUT_SLACK) return 0;
     // hand the whole bytes of the bit buffer back to the input, then take single bytes up to a word boundary
@@ -372,49 +373,65 @@ SS_HD int ssi_huff_fast(ssi_stream &s, const ssi_tables &t, uint8_t **out_io, co
     const uint8_t *in = b.in - (b.cnt >> 3);
     uint64_t buf = b.buf & ((1ull << cnt) - 1ull);
     while ((uintptr_t)in & 3u) { buf |= (uint64_t)(*in++) << cnt; cnt += 8u; }
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(in);
-    const uint32_t *const wp_safe = reinterpret_cast<const uint32_t *>(b.in_end - 32);
-    uint8_t *out = *out_io, *const out_safe = out_end - 2 * SSI_OUT_SLACK;
+    const uint32_t *const words = reinterpret_cast<const uint32_t *>(in);
+    const uint32_t n_words = (uint32_t)((b.in_end - in) >> 2);        // whole words before in_end
+    uint32_t wi = 0;                                                  // words[wi] is `nextw`, not yet in the bit buffer
+    uint8_t *out = *out_io;
     const uint32_t LM = (1u << SSI_LIT_BITS) - 1u, DM = (1u << SSI_DIST_BITS) - 1u;
-    uint32_t nextw = *wp;                                             // word at wp, not yet in the bit buffer
+    uint32_t nextw = words[0];
     int ret = 0;
-#define SSI_DEV_REFILL() do { if (cnt < 32u) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = *++wp; } } while (0)
-    while (wp <= wp_safe && out <= out_safe) {
-        SSI_DEV_REFILL();                                             // >= 32 bits: a length code with its extra bits
-        uint32_t e = t.lit[(uint32_t)buf & LM];
-        if (SSI_KIND(e) == SSI_SUB) { buf >>= SSI_LIT_BITS; cnt -= SSI_LIT_BITS; e = t.lit[SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u))]; }
-        buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
-        if (SSI_KIND(e) == SSI_LIT) { *out++ = (uint8_t)SSI_VAL(e); continue; }
-        if (SSI_KIND(e) != SSI_BASE) {
-            if (SSI_KIND(e) == SSI_EOB) { ret = 1; break; }
-            ret = SSI_ERR_DATA; break;
-        }
-        uint32_t len = SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u));
-        buf >>= SSI_EXTRA(e); cnt -= SSI_EXTRA(e);
-        SSI_DEV_REFILL();                                             // >= 32 bits: a distance code with its extra bits
-        uint32_t d = t.dist[(uint32_t)buf & DM];
-        if (SSI_KIND(d) == SSI_SUB) { buf >>= SSI_DIST_BITS; cnt -= SSI_DIST_BITS; d = t.dist[SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u))]; }
-        buf >>= SSI_LEN(d); cnt -= SSI_LEN(d);
-        if (SSI_KIND(d) != SSI_BASE) { ret = SSI_ERR_DATA; break; }
-        uint32_t dist = SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u));
-        buf >>= SSI_EXTRA(d); cnt -= SSI_EXTRA(d);
-        if (dist > s.out_total + (uint64_t)(out - call_start) || dist > 32768u) { ret = SSI_ERR_DATA; break; }
-        const uint8_t *src = out - dist;
-        if (dist >= len) {                                            // no overlap: the loads do not wait for the stores
-            uint32_t i = 0;
-            for (; i + 4 <= len; i += 4) {
-                uint8_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
-                out[i] = a0; out[i + 1] = a1; out[i + 2] = a2; out[i + 3] = a3;
+#define SSI_DEV_REFILL() do { if (__builtin_expect(cnt < 32u, 0)) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; } } while (0)
+    while (ret == 0) {
+        // symbols that can be decoded before a bound could be crossed: each takes <= 2 words of input and
+        // writes <= 258 bytes
+        uint32_t words_left = n_words > wi + 8u ? n_words - wi - 8u : 0u;
+        uint64_t room = (uint64_t)(out_end - out);
+        uint32_t burst = words_left >> 1;
+        if (room < 2 * SSI_OUT_SLACK) break;
+        uint64_t by_out = (room - 2 * SSI_OUT_SLACK) / 258u + 1u;
+        if (by_out < burst) burst = (uint32_t)by_out;
+        if (burst == 0) break;
+        if (burst > 4096u) burst = 4096u;
+        for (; burst; burst--) {
+            SSI_DEV_REFILL();                                         // >= 32 bits: a length code with its extra bits
+            uint32_t e = t.lit[(uint32_t)buf & LM];
+            if (__builtin_expect(SSI_KIND(e) == SSI_SUB, 0)) {
+                buf >>= SSI_LIT_BITS; cnt -= SSI_LIT_BITS;
+                e = t.lit[SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u))];
             }
-            for (; i < len; i++) out[i] = src[i];
-        } else {
-            for (uint32_t i = 0; i < len; i++) out[i] = src[i];
+            buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
+            if (SSI_KIND(e) == SSI_LIT) { *out++ = (uint8_t)SSI_VAL(e); continue; }
+            if (SSI_KIND(e) != SSI_BASE) { ret = SSI_KIND(e) == SSI_EOB ? 1 : SSI_ERR_DATA; break; }
+            uint32_t len = SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u));
+            buf >>= SSI_EXTRA(e); cnt -= SSI_EXTRA(e);
+            SSI_DEV_REFILL();                                         // >= 32 bits: a distance code with its extra bits
+            uint32_t d = t.dist[(uint32_t)buf & DM];
+            if (__builtin_expect(SSI_KIND(d) == SSI_SUB, 0)) {
+                buf >>= SSI_DIST_BITS; cnt -= SSI_DIST_BITS;
+                d = t.dist[SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u))];
+            }
+            buf >>= SSI_LEN(d); cnt -= SSI_LEN(d);
+            if (SSI_KIND(d) != SSI_BASE) { ret = SSI_ERR_DATA; break; }
+            uint32_t dist = SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u));
+            buf >>= SSI_EXTRA(d); cnt -= SSI_EXTRA(d);
+            if (dist > s.out_total + (uint64_t)(out - call_start) || dist > 32768u) { ret = SSI_ERR_DATA; break; }
+            const uint8_t *src = out - dist;
+            if (dist >= len) {                                        // no overlap: the loads do not wait for the stores
+                uint32_t i = 0;
+                for (; i + 4 <= len; i += 4) {
+                    uint8_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
+                    out[i] = a0; out[i + 1] = a1; out[i + 2] = a2; out[i + 3] = a3;
+                }
+                for (; i < len; i++) out[i] = src[i];
+            } else {
+                for (uint32_t i = 0; i < len; i++) out[i] = src[i];
+            }
+            out += len;
         }
-        out += len;
     }
 #undef SSI_DEV_REFILL
     // hand the state back: the prefetched word was not consumed
-    b.in = reinterpret_cast<const uint8_t *>(wp); b.buf = buf; b.cnt = cnt;
+    b.in = reinterpret_cast<const uint8_t *>(words + wi); b.buf = buf; b.cnt = cnt;
     *out_io = out;
     return ret;
 #endif
