@@ -289,7 +289,7 @@ def main():
     params = synth.default_params(n_leaves=args.leaves, seed=args.seed)
     sizes = synth.node_sizes(params, seed=args.seed)
     t0 = time.perf_counter()
-    db_text, _ = eng.synth_db_host(params, sizes, want_nodes=False)
+    db_text, node_of = eng.synth_db_host(params, sizes, want_nodes=(rank == 0))
     kset = eng.kmerset_from_text(db_text, params.k)
     t_db = time.perf_counter() - t0
     rec = eng.synth_read_record_bytes(params)
@@ -341,6 +341,20 @@ def main():
     total_counts = int(counts.to(torch.int64)[torch.from_numpy(kset.valid).to(dev)].sum())
     assert total_counts == tot_hits, "sum of valid-record counts %d != hits %d" % (total_counts, tot_hits)
     assert tot_reads == args.reads * world
+
+    # ---- per-node hit vectors of the whole search tree (K4 = match_node for every node, identify.py:115-127;
+    # what identify_low_depth.identify_ranks asks for), outside the timed region, with its own full-size check
+    node_reduce = None
+    if rank == 0:
+        order = np.argsort(node_of, kind="stable").astype(np.uint32)
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(node_of, minlength=sizes.size))]).astype(np.uint64)
+        t0 = time.perf_counter()
+        length, covered, total = eng.node_reduce(kset, counts.data_ptr(), ptr, order)
+        t_nr = (time.perf_counter() - t0) * 1e3
+        assert int(length.sum()) == int(kset.valid.sum()) and int(total.sum()) == tot_hits
+        node_reduce = {"nodes": int(sizes.size), "list_entries": int(order.size), "ms_incl_csr_upload": t_nr,
+                       "nodes_with_hits": int((covered > 0).sum())}
+        del order, node_of
 
     # ---- roofline of the dominant kernel (K3 probe), this rank ---------------------------------
     p2 = st.n_second_probe / max(st.n_kmers, 1)
@@ -434,7 +448,7 @@ def main():
             "reads_per_s": tot_reads / (ms_per_step * 1e-3),
             "wall_ms_per_step": float(t[1]) / args.steps,
             "kernel_ms": {"probe": probe_avg_ms, "gather": sum(gather_ms) / len(gather_ms)},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+            "node_reduce": node_reduce, "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": launches, "clocks": sampler.summary(),
             "device": info["name"], "n_sm": info["n_sm"],
         }
