@@ -183,6 +183,34 @@ def match_node_low_depth(match_results, db_dir, node_id, valid_kmers=None):
     return _profile(match_results, d)
 
 
+def adjust_profile_gather(match_results, db_dir, node_id, delete_positions, valid_kmers=None):
+    """Gather part of adjust_profile (identify.py:167-191): the node's k-mer list minus the overlap
+    positions (`overlapping_info[leaf][node]`: indices INTO the node's list as written in kmers/<node>,
+    identify.py:176-178).  Returns (len(valid_kmer), k_profile) when at least 1000 list entries remain
+    (identify.py:181), else None -- the caller then takes the reference's Poisson branch (identify.py:196-228),
+    which stays host code."""
+    with open(os.path.join(db_dir, "kmers", str(node_id)), "r") as f:
+        lines = f.readlines()
+    d = np.array(lines[0].split(), dtype=np.int64)                  # list order matters: positions index it
+    delete = np.unique(d[np.asarray(list(delete_positions), dtype=np.int64)]) if len(delete_positions) else np.zeros(0, np.int64)
+    ds = np.unique(d)
+    if ds.size - delete.size < 1000:
+        return None
+    return _profile(match_results, np.setdiff1d(ds, delete, assume_unique=True))
+
+
+def node_coverage_all(match_results, db_dir, node_ids, min_valid=1000):
+    """Coverage part of identify_ranks (identify_low_depth.py:113-132) for every node at once:
+    {node_id: len(k_profile) / length, or -1 when the node has fewer than `min_valid` valid k-mers or an
+    empty list}.  Same numbers as calling match_node_low_depth per node; the per-node vectors are gathers
+    of the GPU-produced dense count vector."""
+    out = {}
+    for nid in node_ids:
+        length, prof = match_node_low_depth(match_results, db_dir, nid) if min_valid else match_node(match_results, db_dir, nid)
+        out[nid] = -1 if length == 0 else len(prof) / length
+    return out
+
+
 def load_node_csr(db_dir, node_ids):
     """kmers/<node> files -> CSR (ptr uint64[n+1], ordinals uint32[nnz]), lists de-duplicated."""
     ptr = np.zeros(len(node_ids) + 1, dtype=np.uint64)

@@ -80,6 +80,32 @@ def test_match_node_equals_reference(l1_case, tmp_path):
     assert ptr[-1] == ordinals.size and ptr[5] == ptr[4]
 
 
+def test_adjust_profile_gather_and_node_coverage(l1_case, tmp_path):
+    """identify.py:167-191 (gather part) and identify_low_depth.py:113-132 (coverage of every node)."""
+    d, cv, ref = l1_case
+    ref_valid = set(ref.keys())
+    rng = np.random.default_rng(9)
+    os.makedirs(tmp_path / "kmers")
+    lists = {0: rng.integers(0, len(d.cnt), 5000), 1: rng.integers(0, len(d.cnt), 1200), 2: rng.integers(0, len(d.cnt), 30)}
+    for node, ords in lists.items():
+        with open(tmp_path / "kmers" / str(node), "w") as f:
+            f.write("".join("%d " % x for x in ords))
+    open(tmp_path / "kmers" / "3", "w").close()
+    for node, n_del in ((0, 0), (0, 700), (0, 4500), (1, 100), (1, 400)):
+        pos = rng.choice(len(lists[node]), n_del, replace=False).tolist()
+        got = identify_shim.adjust_profile_gather(cv, str(tmp_path), node, pos, cv.valid_kmers())
+        want = adapters.adjust_profile_gather(ref, lists[node], pos, ref_valid)
+        if want is None:
+            assert got is None
+        else:
+            assert got[0] == want[0] and sorted(got[1]) == want[1]
+    cov = identify_shim.node_coverage_all(cv, str(tmp_path), [0, 1, 2, 3])
+    for node in (0, 1, 2):
+        length, prof = adapters.match_node(ref, lists[node], ref_valid, min_valid=1000)
+        assert cov[node] == (-1 if length == 0 else len(prof) / length)
+    assert cov[3] == -1 and cov[2] == -1
+
+
 def test_del_outlier_equals_reference():
     rng = np.random.default_rng(0)
     for _ in range(20):
