@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--only", type=int, default=-1, help="run only case number N (for ncu captures)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -25,7 +26,10 @@ def main():
     eng = Engine(0)
     out = {"reads": a.reads, "cases": []}
     rand = None
-    for n_rec, off in ((200_000, 0.0), (2_000_000, 0.0), (9_900_000, 0.0), (9_900_000, 0.7), (2_000_000, 0.7)):
+    cases = ((200_000, 0.0), (2_000_000, 0.0), (9_900_000, 0.0), (9_900_000, 0.7), (2_000_000, 0.7))
+    for ci, (n_rec, off) in enumerate(cases):
+        if a.only >= 0 and ci != a.only:
+            continue
         # one cluster genome of 5 Mb; the set holds n_rec of its ~1e7 strand-specific 31-mers; a fraction
         # `off` of the reads comes from elsewhere (the other clusters of the sample)
         p = synth.default_params(n_leaves=1, genome_len=5_000_000, seed=3, sources=[(0, 0, 1.0)], p_offtarget=off)
