@@ -602,7 +602,7 @@ static int ensure_source(ss_ctx *c) {
     if (c->src && c->src->ready()) return SS_OK;
     if (!c->src) c->src = new ss_text_source();
     unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-    int threads = (int)std::min(8u, std::max(2u, hw / 2));
+    int threads = (int)std::min(12u, std::max(2u, hw > 4 ? hw - 4 : 2u));   // measured: 8 -> 21-30, 12 -> 35 GB/s of plain text
     if (const char *e = getenv("SS_INGEST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) threads = v; }
     int rc = c->src->init(c->chunk_bytes, threads + 3, threads, true, c->device_bgzf, c->bgzf_out_cap);
     if (rc) return fail(rc, c->src->error());
