@@ -305,8 +305,9 @@ static int check_head(const uint8_t *text, size_t len, const std::string &path, 
 
 // Cut a filled chunk at its last record start inside the boundary window; the tail is carried over.
 // Returns the cut (== fill when `last`, after trimming blank tail lines and closing the last line).
-static size_t cut_chunk(ss_chunk *c, size_t fill, bool last) {
+static size_t cut_chunk(ss_chunk *c, size_t fill, bool last, bool file_end = true) {
     char *t = (char *)c->text;
+    if (last && !file_end) return fill;      // an inner part of a plain file ends right before a record start
     if (last) {
         size_t n = ss_trim_tail(t, fill);
         if (n) t[n++] = '\n';       // slack behind cap
@@ -343,7 +344,7 @@ void ss_text_source::run_plain(const job &j) {
             first = false;
         }
         const bool last = pos >= j.hi;
-        size_t cut = cut_chunk(c, fill, last);
+        size_t cut = cut_chunk(c, fill, last, j.hi >= f.size);
         if (!last) {
             if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within 64 KiB"); return; }
             carry.assign(c->text + cut, c->text + fill);

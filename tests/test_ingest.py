@@ -263,3 +263,34 @@ def test_bgzf_file_parts_agree_on_record_boundaries(tmp_path, monkeypatch, block
         assert records(got) == records(long_fq)
     except _lib.StrainScanB200Error as e:          # a loud, documented limit (like the 64 KiB rule of the plain chunker)
         assert e.code == _lib.SS_ERR_FORMAT and "record boundary" in str(e)
+
+
+def test_randomized_inputs_chunks_threads_shards(tmp_path, monkeypatch):
+    """Seeded sweep over file encodings (plain / gzip / BGZF), record lengths, CRLF, file tails, chunk
+    sizes, producer counts, BGZF part and batch sizes and shard counts: the delivered records must be the
+    file's records, every byte accounted for (tail blank lines trimmed, last line closed)."""
+    rng = np.random.default_rng(2026)
+    G = util.rand_genome(rng, 40_000)
+    for it in range(36):
+        fq = util.make_reads(rng, G, int(rng.integers(1, 5000)), int(rng.integers(20, 300)), var_len=rng.random() < 0.7,
+                             crlf=rng.random() < 0.2)
+        tail = [b"", b"\n", b"\n\n", b" \n", b"\r\n\r\n"][int(rng.integers(0, 5))]
+        data = (fq[:-1] if rng.random() < 0.3 else fq) + tail
+        kind = ("plain", "gz", "bgzf")[it % 3]
+        p = str(tmp_path / ("f%d.%s" % (it, "fq" if kind == "plain" else "fq.gz")))
+        if kind == "plain":
+            blob = data
+        elif kind == "gz":
+            blob = gzip.compress(data, int(rng.integers(1, 10)))
+        else:
+            blob = util.bgzf_compress(data, block=int(rng.integers(100, 65000)), level=int(rng.integers(1, 10)),
+                                      eof_marker=rng.random() < 0.5, empty_every=int(rng.integers(0, 4)))
+        open(p, "wb").write(blob)
+        monkeypatch.setenv("SS_BGZF_OUT_CAP", str(int(rng.integers(1 << 20, 4 << 20))))
+        monkeypatch.setenv("SS_BGZF_PART_BYTES", str(int(rng.integers(256 << 10, 2 << 20))))
+        chunk = (256 << 10, 1 << 20, 3 << 20)[int(rng.integers(0, 3))]
+        n_sh = int(rng.integers(1, 5))
+        got = b"".join(ingest([p], s, n_sh, chunk=chunk, threads=int(rng.integers(1, 9)))[0] for s in range(n_sh))
+        exp = data.rstrip(b"\r\n \t") + b"\n"
+        assert len(got) == len(exp), (it, kind)
+        assert records(got) == records(exp), (it, kind)
