@@ -376,60 +376,85 @@ SS_HD int ssi_huff_fast(ssi_stream &s, const ssi_tables &t, uint8_t **out_io, co
     const uint32_t *const words = reinterpret_cast<const uint32_t *>(in);
     const uint32_t n_words = (uint32_t)((b.in_end - in) >> 2);        // whole words before in_end
     uint32_t wi = 0;                                                  // words[wi] is `nextw`, not yet in the bit buffer
-    uint8_t *out = *out_io;
-    const uint32_t LM = (1u << SSI_LIT_BITS) - 1u, DM = (1u << SSI_DIST_BITS) - 1u;
+    uint8_t *const out0 = *out_io;
+    uint32_t o = 0;                                                   // bytes written by this call: out0[o] is next
+    const uint64_t total0 = s.out_total + (uint64_t)(out0 - call_start);   // member bytes produced before out0
+    const uint32_t room0 = (uint32_t)((uint64_t)(out_end - out0) > 0x7FFFFFFFull ? 0x7FFFFFFFull : (uint64_t)(out_end - out0));
+    // the decode tables live in shared memory (ss_gunzip.cu): 32-bit shared addresses and ld.shared keep the
+    // per-symbol address arithmetic at one instruction
+    const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(t.lit), dist_sa = (uint32_t)__cvta_generic_to_shared(t.dist);
+    const uint32_t LM4 = ((1u << SSI_LIT_BITS) - 1u) << 2, DM4 = ((1u << SSI_DIST_BITS) - 1u) << 2;
     uint32_t nextw = words[0];
     int ret = 0;
-#define SSI_DEV_REFILL() do { if (__builtin_expect(cnt < 32u, 0)) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; } } while (0)
+#define SSI_LDS(v, addr) asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr))
+#define SSI_DEV_REFILL() do { if (cnt < 32u) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; } } while (0)
+    // Loop shape: ptxas predicates every small conditional block, and a lone lane pays for each predicated-off
+    // instruction.  So the common case -- a run of literals decoded from the main table while >= 32 bits remain --
+    // is its own inner loop, and everything rarer (refill, sub-table, match, end of block, burst bookkeeping)
+    // is reached only through that loop's EXITS, which are real branches.
+    uint32_t burst = 0;
     while (ret == 0) {
-        // symbols that can be decoded before a bound could be crossed: each takes <= 2 words of input and
-        // writes <= 258 bytes
-        uint32_t words_left = n_words > wi + 8u ? n_words - wi - 8u : 0u;
-        uint64_t room = (uint64_t)(out_end - out);
-        uint32_t burst = words_left >> 1;
-        if (room < 2 * SSI_OUT_SLACK) break;
-        uint64_t by_out = (room - 2 * SSI_OUT_SLACK) / 258u + 1u;
-        if (by_out < burst) burst = (uint32_t)by_out;
-        if (burst == 0) break;
-        if (burst > 4096u) burst = 4096u;
-        for (; burst; burst--) {
-            SSI_DEV_REFILL();                                         // >= 32 bits: a length code with its extra bits
-            uint32_t e = t.lit[(uint32_t)buf & LM];
-            if (__builtin_expect(SSI_KIND(e) == SSI_SUB, 0)) {
-                buf >>= SSI_LIT_BITS; cnt -= SSI_LIT_BITS;
-                e = t.lit[SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u))];
-            }
-            buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
-            if (SSI_KIND(e) == SSI_LIT) { *out++ = (uint8_t)SSI_VAL(e); continue; }
-            if (SSI_KIND(e) != SSI_BASE) { ret = SSI_KIND(e) == SSI_EOB ? 1 : SSI_ERR_DATA; break; }
-            uint32_t len = SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u));
-            buf >>= SSI_EXTRA(e); cnt -= SSI_EXTRA(e);
-            SSI_DEV_REFILL();                                         // >= 32 bits: a distance code with its extra bits
-            uint32_t d = t.dist[(uint32_t)buf & DM];
-            if (__builtin_expect(SSI_KIND(d) == SSI_SUB, 0)) {
-                buf >>= SSI_DIST_BITS; cnt -= SSI_DIST_BITS;
-                d = t.dist[SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u))];
-            }
-            buf >>= SSI_LEN(d); cnt -= SSI_LEN(d);
-            if (SSI_KIND(d) != SSI_BASE) { ret = SSI_ERR_DATA; break; }
-            uint32_t dist = SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u));
-            buf >>= SSI_EXTRA(d); cnt -= SSI_EXTRA(d);
-            if (dist > s.out_total + (uint64_t)(out - call_start) || dist > 32768u) { ret = SSI_ERR_DATA; break; }
-            const uint8_t *src = out - dist;
-            if (dist >= len) {                                        // no overlap: the loads do not wait for the stores
-                uint32_t i = 0;
-                for (; i + 4 <= len; i += 4) {
-                    uint8_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
-                    out[i] = a0; out[i + 1] = a1; out[i + 2] = a2; out[i + 3] = a3;
-                }
-                for (; i < len; i++) out[i] = src[i];
-            } else {
-                for (uint32_t i = 0; i < len; i++) out[i] = src[i];
-            }
-            out += len;
+        if (burst == 0) {
+            // symbols that can be decoded before a bound could be crossed: each takes <= 2 words of input and
+            // writes <= 258 bytes
+            uint32_t words_left = n_words > wi + 8u ? n_words - wi - 8u : 0u;
+            burst = words_left >> 1;
+            if (room0 - o < 2 * SSI_OUT_SLACK) break;
+            uint32_t by_out = (room0 - o - 2 * SSI_OUT_SLACK) / 258u + 1u;
+            if (by_out < burst) burst = by_out;
+            if (burst == 0) break;
+            if (burst > 4096u) burst = 4096u;
         }
+        SSI_DEV_REFILL();                                             // >= 32 bits: a length code with its extra bits
+        uint32_t e;
+        bool more = true;
+        do {                                                          // literal run
+            SSI_LDS(e, lit_sa + (((uint32_t)buf << 2) & LM4));
+            if (SSI_KIND(e) != SSI_LIT) break;
+            buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
+            out0[o++] = (uint8_t)SSI_VAL(e);
+            more = --burst != 0 && cnt >= 32u;
+        } while (more);
+        if (!more) continue;                                          // refill / new burst, then on with the run
+        burst--;
+        if (SSI_KIND(e) == SSI_SUB) {
+            buf >>= SSI_LIT_BITS; cnt -= SSI_LIT_BITS;
+            SSI_LDS(e, lit_sa + ((SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u))) << 2));
+        }
+        buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
+        if (SSI_KIND(e) == SSI_LIT) { out0[o++] = (uint8_t)SSI_VAL(e); continue; }
+        if (SSI_KIND(e) != SSI_BASE) { ret = SSI_KIND(e) == SSI_EOB ? 1 : SSI_ERR_DATA; break; }
+        uint32_t len = SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u));
+        buf >>= SSI_EXTRA(e); cnt -= SSI_EXTRA(e);
+        SSI_DEV_REFILL();                                             // >= 32 bits: a distance code with its extra bits
+        uint32_t d;
+        SSI_LDS(d, dist_sa + (((uint32_t)buf << 2) & DM4));
+        if (SSI_KIND(d) == SSI_SUB) {
+            buf >>= SSI_DIST_BITS; cnt -= SSI_DIST_BITS;
+            SSI_LDS(d, dist_sa + ((SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u))) << 2));
+        }
+        buf >>= SSI_LEN(d); cnt -= SSI_LEN(d);
+        if (SSI_KIND(d) != SSI_BASE) { ret = SSI_ERR_DATA; break; }
+        uint32_t dist = SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u));
+        buf >>= SSI_EXTRA(d); cnt -= SSI_EXTRA(d);
+        if (dist > total0 + o || dist > 32768u) { ret = SSI_ERR_DATA; break; }
+        uint8_t *dst = out0 + o;
+        const uint8_t *src = dst - dist;
+        if (dist >= len) {                                            // no overlap: the loads do not wait for the stores
+            uint32_t i = 0;
+            for (; i + 4 <= len; i += 4) {
+                uint8_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
+                dst[i] = a0; dst[i + 1] = a1; dst[i + 2] = a2; dst[i + 3] = a3;
+            }
+            for (; i < len; i++) dst[i] = src[i];
+        } else {
+            for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+        }
+        o += len;
     }
 #undef SSI_DEV_REFILL
+#undef SSI_LDS
+    uint8_t *out = out0 + o;
     // hand the state back: the prefetched word was not consumed
     b.in = reinterpret_cast<const uint8_t *>(words + wi); b.buf = buf; b.cnt = cnt;
     *out_io = out;
