@@ -272,6 +272,8 @@ def main():
 
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the match+count path has no CPU fallback")
+    from strainscan_b200 import dist as ssd
+    local_cpus = ssd.bind_to_gpu_cpus(local_rank) if world > 1 else None     # NUMA-local pinned staging per rank
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -444,7 +446,8 @@ def main():
                            n_bytes / 1e9, kset.table_bytes / 1e9),
                        "hit_rate": h, "second_sector_rate": p2,
                        "table_probe_rate": st.n_table_probes / max(st.n_kmers, 1), "db_build_s": t_db, "seed": args.seed,
-                       "collective": "NCCL all-reduce(sum) of the dense int32 count vector" if world > 1 else "none (1 GPU)"},
+                       "collective": "NCCL all-reduce(sum) of the dense int32 count vector" if world > 1 else "none (1 GPU)",
+                       "rank0_cpu_affinity": ("%d GPU-local cores" % len(local_cpus)) if local_cpus else "unchanged"},
             "reads_per_s": tot_reads / (ms_per_step * 1e-3),
             "wall_ms_per_step": float(t[1]) / args.steps,
             "kernel_ms": {"probe": probe_avg_ms, "gather": sum(gather_ms) / len(gather_ms)},

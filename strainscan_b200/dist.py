@@ -20,6 +20,29 @@ def world():
     return 0, 1
 
 
+def bind_to_gpu_cpus(device_index):
+    """Pin this process (one per GPU) to the CPU cores NVML reports as local to its GPU, so that the pinned
+    staging buffers it allocates afterwards are first-touched on that NUMA node and host->device copies of
+    several ranks do not all cross one socket's memory controllers.  Returns the core list, or None when
+    NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_range(buf, shard, n_shards):
     """Record-aligned byte range of FASTQ text owned by `shard` (host-only C ABI helper)."""
     lib = _lib.load()
