@@ -197,6 +197,7 @@ SS_HD const uint8_t *ssi_in_pos(const ssi_bits &b) {
 enum {
     SSI_OK = 0,            // stream / member finished
     SSI_MORE_OUTPUT = 1,   // out of output room: call again with a fresh window (history kept by the caller)
+    SSI_STOP = 2,          // stopped at a requested block boundary (ssi_stream::stops / limit_bit)
     SSI_ERR_DATA = -1,     // invalid deflate data
     SSI_ERR_TRUNC = -2,    // input ended inside the stream
     SSI_ERR_HEADER = -3,   // not a gzip member
@@ -210,11 +211,24 @@ struct ssi_stream {
     int phase, last_block;
     uint32_t stored_left;
     uint64_t out_total;     // bytes produced since the start of this deflate stream (= member)
+    // optional stop points (parallel gzip decoding on the host, ss_pgz.cuh): standing at a block boundary whose
+    // bit position (relative to `base`) is one of `stops`, or at the first boundary >= `limit_bit`, the
+    // decoder returns SSI_STOP instead of reading the next block header
+    const uint8_t *base;
+    const uint64_t *stops;
+    uint32_t n_stops;
+    uint64_t limit_bit;
 };
 
 SS_HD void ssi_stream_init(ssi_stream &s, const uint8_t *in, const uint8_t *in_end) {
     s.bits.in = in; s.bits.in_end = in_end; s.bits.buf = 0; s.bits.cnt = 0; s.bits.overrun = 0;
     s.phase = SSI_PH_BLOCK; s.last_block = 0; s.stored_left = 0; s.out_total = 0;
+    s.base = nullptr; s.stops = nullptr; s.n_stops = 0; s.limit_bit = 0;
+}
+
+// bit position of the next unread bit, relative to s.base (exact while no phantom bits were loaded)
+SS_HD uint64_t ssi_bitpos(const ssi_stream &s) {
+    return (uint64_t)(s.bits.in - s.base) * 8u - s.bits.cnt + (uint64_t)s.bits.overrun * 8u;
 }
 
 SS_HD int ssi_fixed_tables(ssi_tables &t) {
@@ -473,6 +487,12 @@ SS_HD int ssi_inflate(ssi_stream &s, ssi_tables &t, uint8_t **out_pos, uint8_t *
     while (true) {
         if (s.phase == SSI_PH_BLOCK) {
             if (s.last_block) { s.phase = SSI_PH_DONE; break; }
+            if (s.base) {
+                const uint64_t at = ssi_bitpos(s);
+                bool stop = s.limit_bit && at >= s.limit_bit;
+                for (uint32_t i = 0; i < s.n_stops && !stop; i++) stop = s.stops[i] == at;
+                if (stop) { rc = SSI_STOP; break; }
+            }
             ssi_refill(b);
             s.last_block = (int)ssi_take(b, 1);
             uint32_t type = ssi_take(b, 2);

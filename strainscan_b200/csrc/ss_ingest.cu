@@ -13,6 +13,7 @@
 
 #include "../../include/strainscan_b200.h"
 #include "ss_inflate.cuh"
+#include "ss_pgz.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // FASTQ framing helpers
@@ -133,6 +134,7 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
     err_code_ = 0; err_msg_.clear(); stop_ = false;
     shard_ = shard; n_shards_ = n_shards;
     plain_bytes_ = gz_bytes_ = 0;
+    n_gz_jobs_ = 0;
     files_.clear(); jobs_.clear(); next_job_ = 0;
     free_.clear(); ready_.clear();
     for (auto &b : bufs_) free_.push_back(&b);
@@ -185,6 +187,7 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
             job j; j.file = (int)fi; j.lo = 0; j.hi = f.size; j.first_of_file = true;
             jobs_.push_back(j);
             gz_bytes_ += f.size;
+            n_gz_jobs_++;
             continue;
         }
         // parts per rank: enough to keep the producers busy, at least ~4 chunks each
@@ -282,7 +285,15 @@ void ss_text_source::worker() {
         }
         const file_map &f = files_[(size_t)j.file];
         if (f.bgzf) run_bgzf(j);
-        else if (f.gz) run_gz(j);
+        else if (f.gz) {
+            // an ordinary gzip stream: decoded by several threads per round when cores are to spare (ss_pgz.cuh)
+            int t = std::max(1, n_threads_ / std::max(1, n_gz_jobs_));
+            size_t span = 2u << 20;
+            if (const char *e = getenv("SS_PGZ_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) t = v; }
+            if (const char *e = getenv("SS_PGZ_SPAN")) { long long v = atoll(e); if (v >= (64 << 10)) span = (size_t)v; }
+            if (t >= 2 && f.size >= 4 * span) run_gz_parallel(j, t, span);
+            else run_gz(j);
+        }
         else run_plain(j);
     }
     std::lock_guard<std::mutex> lk(mu_);
@@ -401,6 +412,101 @@ void ss_text_source::run_gz(const job &j) {
         c = c2;
     }
     delete g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream -> chunks, and the parallel gzip producer
+// ---------------------------------------------------------------------------------------------
+bool ss_text_source::stream_writer::append(const uint8_t *p, size_t n) {
+    const file_map &f = src->files_[(size_t)j->file];
+    while (n) {
+        if (!c) {
+            c = src->acquire();
+            if (!c) return false;
+        }
+        size_t take = std::min(c->cap - fill, n);
+        memcpy(c->text + fill, p, take);
+        fill += take; p += take; n -= take;
+        if (fill < c->cap) break;
+        if (first) {
+            std::string m;
+            int hrc = check_head(c->text, ss_trim_tail((const char *)c->text, fill), f.path, m);
+            if (hrc) { abandon(); src->fail(hrc, m); return false; }
+            first = false;
+        }
+        size_t cut = cut_chunk(c, fill, false);
+        if (cut == 0) { abandon(); src->fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within 64 KiB"); return false; }
+        ss_chunk *c2 = src->acquire();
+        if (!c2) { abandon(); return false; }
+        size_t tail = fill - cut;
+        memcpy(c2->text, c->text + cut, tail);
+        if ((chunk_idx + (uint64_t)j->file) % (uint64_t)src->n_shards_ == (uint64_t)src->shard_) { c->len = cut; src->emit(c); }
+        else src->release(c);
+        chunk_idx++;
+        c = c2;
+        fill = tail;
+    }
+    return true;
+}
+
+bool ss_text_source::stream_writer::finish() {
+    if (!c) return true;
+    const file_map &f = src->files_[(size_t)j->file];
+    if (first) {
+        std::string m;
+        int hrc = check_head(c->text, ss_trim_tail((const char *)c->text, fill), f.path, m);
+        if (hrc) { abandon(); src->fail(hrc, m); return false; }
+    }
+    size_t cut = cut_chunk(c, fill, true);
+    if ((chunk_idx + (uint64_t)j->file) % (uint64_t)src->n_shards_ == (uint64_t)src->shard_) { c->len = cut; src->emit(c); }
+    else src->release(c);
+    c = nullptr;
+    return true;
+}
+
+void ss_text_source::stream_writer::abandon() {
+    if (c) src->release(c);
+    c = nullptr;
+}
+
+void ss_text_source::run_gz_parallel(const job &j, int threads, size_t span) {
+    const file_map &f = files_[(size_t)j.file];
+    stream_writer w;
+    w.src = this; w.j = &j;
+    size_t p = 0;
+    uint64_t n_members = 0;
+    auto why = [](int rc) {
+        return rc == SSI_ERR_TRUNC ? "unexpected end of file" : rc == SSI_ERR_HEADER ? "not in gzip format"
+               : rc == SSI_ERR_SIZE ? "length error" : "invalid compressed data";
+    };
+    while (p < f.size) {
+        ssi_gz_header h;
+        int rc = ssi_gz_parse_header(f.map + p, f.map + f.size, &h);
+        if (rc == SSI_ERR_HEADER && n_members) break;               // trailing garbage, as zcat
+        if (rc) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why(rc)); return; }
+        pgz_member m;
+        m.base = f.map; m.size = f.size; m.bit = (uint64_t)(p + h.header_len) * 8u;
+        bool ok = true;
+        while (true) {
+            rc = pgz_round(m, threads, span, [&](const uint8_t *q, size_t n) { if (ok) ok = w.append(q, n); });
+            if (!ok) return;                                        // stopped, or append() reported the failure
+            if (rc < 0) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why(rc)); return; }
+            if (rc == 1) break;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (stop_) { w.abandon(); return; }
+            }
+        }
+        size_t q = (size_t)((m.bit + 7u) >> 3);
+        if (f.size - q < 8) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": unexpected end of file"); return; }
+        const uint8_t *tr = f.map + q;
+        uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+        if (isize != (uint32_t)m.member_out) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": length error"); return; }
+        p = q + 8;
+        n_members++;
+    }
+    if (n_members == 0) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": not in gzip format"); return; }
+    w.finish();
 }
 
 // ---------------------------------------------------------------------------------------------

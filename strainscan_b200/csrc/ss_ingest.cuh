@@ -85,7 +85,20 @@ private:
     void worker();
     void run_plain(const job &j);
     void run_gz(const job &j);
+    void run_gz_parallel(const job &j, int threads, size_t span);
     void run_bgzf(const job &j);
+    // in-order byte stream of one file -> record-aligned chunks (used by the parallel gzip decoder)
+    struct stream_writer {
+        ss_text_source *src = nullptr;
+        const job *j = nullptr;
+        ss_chunk *c = nullptr;
+        size_t fill = 0;
+        uint64_t chunk_idx = 0;
+        bool first = true;
+        bool append(const uint8_t *p, size_t n);   // false: stopped or failed (fail() was called)
+        bool finish();
+        void abandon();
+    };
     ss_chunk *acquire();
     void emit(ss_chunk *c);
     void fail(int code, const std::string &msg);
@@ -101,6 +114,7 @@ private:
     size_t next_job_ = 0;
     int active_ = 0;
     int shard_ = 0, n_shards_ = 1;
+    int n_gz_jobs_ = 0;
     uint64_t plain_bytes_ = 0, gz_bytes_ = 0;
 
     std::mutex mu_;

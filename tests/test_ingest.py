@@ -294,3 +294,51 @@ def test_randomized_inputs_chunks_threads_shards(tmp_path, monkeypatch):
         exp = data.rstrip(b"\r\n \t") + b"\n"
         assert len(got) == len(exp), (it, kind)
         assert records(got) == records(exp), (it, kind)
+
+
+# ---- parallel decoding of ordinary (single-stream) gzip: ss_pgz.cuh ----------------------------------------
+@pytest.mark.parametrize("threads,span", [(2, 64 << 10), (5, 100_000), (8, 256 << 10)])
+def test_parallel_gzip_equals_zlib(tmp_path, monkeypatch, threads, span):
+    """Pieces of one deflate stream decoded concurrently (block starts found by search, unknown 32 KiB windows
+    carried as 16-bit marker symbols, pieces stitched only where the previous one ended exactly on the found
+    start): the bytes must equal zlib's, for every stream shape."""
+    rng = np.random.default_rng(31)
+    fq = util.make_reads(rng, util.rand_genome(rng, 60_000), 16_000, 150, var_len=True)     # ~5 MB
+    monkeypatch.setenv("SS_PGZ_THREADS", str(threads))
+    monkeypatch.setenv("SS_PGZ_SPAN", str(span))
+    for name, data in _variants(fq).items():
+        p = str(tmp_path / ("%s.fq.gz" % name))
+        open(p, "wb").write(data)
+        got, _ = ingest([p], threads=1, chunk=1 << 20)
+        assert got == fq, name
+    # sharded: chunks of the (deterministic) stream are dealt round-robin
+    p = str(tmp_path / "level6.fq.gz")
+    parts = [ingest([p], s, 3, chunk=512 << 10)[0] for s in range(3)]
+    assert records(b"".join(parts)) == records(fq)
+
+
+def test_parallel_gzip_errors(tmp_path, monkeypatch):
+    rng = np.random.default_rng(32)
+    fq = util.make_reads(rng, util.rand_genome(rng, 60_000), 12_000, 150)
+    gz = gzip.compress(fq, 6)
+    monkeypatch.setenv("SS_PGZ_THREADS", "4")
+    monkeypatch.setenv("SS_PGZ_SPAN", str(64 << 10))
+    p = str(tmp_path / "x.fq.gz")
+    for bad in (gz[:len(gz) // 2], gz[:-8], gz[:-3]):
+        open(p, "wb").write(bad)
+        with pytest.raises(_lib.StrainScanB200Error, match="inflate failed"):
+            ingest([p])
+    flipped = bytearray(gz)
+    for i in range(7):
+        flipped[len(gz) * (i + 1) // 9] ^= 0xA5
+    open(p, "wb").write(bytes(flipped))
+    try:
+        got, _ = ingest([p])
+        assert got != fq
+    except _lib.StrainScanB200Error as e:
+        assert e.code in (_lib.SS_ERR_IO, _lib.SS_ERR_FORMAT)
+    # sequential and parallel modes agree
+    open(p, "wb").write(gz)
+    a = ingest([p], threads=1)[0]
+    monkeypatch.setenv("SS_PGZ_THREADS", "1")
+    assert ingest([p], threads=1)[0] == a == fq
