@@ -9,6 +9,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "../../include/strainscan_b200.h"
@@ -487,16 +488,21 @@ void ss_text_source::run_gz_parallel(const job &j, int threads, size_t span) {
         pgz_member m;
         m.base = f.map; m.size = f.size; m.bit = (uint64_t)(p + h.header_len) * 8u;
         bool ok = true;
-        while (true) {
-            rc = pgz_round(m, threads, span, [&](const uint8_t *q, size_t n) { if (ok) ok = w.append(q, n); });
-            if (!ok) return;                                        // stopped, or append() reported the failure
-            if (rc < 0) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why(rc)); return; }
-            if (rc == 1) break;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (stop_) { w.abandon(); return; }
+        struct report {                                             // SS_DEBUG_TIMING: where a member's time went
+            pgz_member &m; int threads;
+            ~report() {
+                if (getenv("SS_DEBUG_TIMING") && m.rounds > 1)
+                    fprintf(stderr, "[ss pgz] %d threads, %llu rounds, %llu/%llu pieces used, %.1f MB out (%.1f MB through markers): "
+                            "find %.3f s, decode %.3f s, stitch+emit %.3f s\n", threads, (unsigned long long)m.rounds,
+                            (unsigned long long)m.pieces_used, (unsigned long long)m.pieces_found, m.member_out / 1e6,
+                            m.marker_syms / 1e6, m.t_find, m.t_decode, m.t_stitch);
             }
-        }
+        } rep{m, threads};
+        rc = pgz_member_decode(m, threads, span, [&](const uint8_t *q, size_t n) { if (ok) ok = w.append(q, n); },
+                               [&]() { std::lock_guard<std::mutex> lk(mu_); return ok && !stop_; });
+        if (!ok) return;                                            // stopped, or append() reported the failure
+        if (rc == 0) { w.abandon(); return; }                       // asked to stop
+        if (rc < 0) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why(rc)); return; }
         size_t q = (size_t)((m.bit + 7u) >> 3);
         if (f.size - q < 8) { w.abandon(); fail(SS_ERR_IO, "inflate failed on " + f.path + ": unexpected end of file"); return; }
         const uint8_t *tr = f.map + q;

@@ -251,6 +251,9 @@ struct pgz_piece {
     pgz_symbuf sym;                // unknown-window part
     std::vector<uint8_t> text;     // 8-bit part; text[0, hist) is history, not output
     size_t hist = 0, text_len = 0; // text_len: bytes in `text` including the history prefix
+    std::vector<uint8_t> resolved; // the unknown-window part as bytes (filled while stitching)
+    // buffers keep their memory from round to round (no page faults after the first rounds)
+    void reset() { start_bit = ~0ull; end_bit = 0; valid = false; status = SSI_ERR_DATA; sym.clear(); hist = text_len = 0; }
 };
 
 // 8-bit decoding into a growing vector until a stop, the limit or the member end
@@ -272,7 +275,8 @@ inline void pgz_decode_known(const uint8_t *base, size_t size, pgz_piece &pc, co
     pgz_seek(s, base, size, pc.start_bit);
     s.stops = stops.data(); s.n_stops = (uint32_t)stops.size(); s.limit_bit = limit_bit;
     s.out_total = member_out;
-    pc.text.assign(window.begin(), window.end());
+    if (pc.text.size() < window.size() + (4u << 20)) pc.text.resize(window.size() + (8u << 20));
+    memcpy(pc.text.data(), window.data(), window.size());
     pc.hist = pc.text_len = window.size();
     pc.status = pgz_run_8bit(s, *t, pc);
     pc.end_bit = ssi_bitpos(s);
@@ -303,7 +307,7 @@ inline void pgz_decode_unknown(const uint8_t *base, size_t size, pgz_piece &pc, 
         }
     }
     if (clean) {                                                     // no unknown symbol can be copied any more
-        pc.text.resize(PGZ_WINDOW + (8u << 20));
+        if (pc.text.size() < PGZ_WINDOW + (4u << 20)) pc.text.resize(PGZ_WINDOW + (8u << 20));
         const uint16_t *w = pc.sym.p + pc.sym.size() - PGZ_WINDOW;
         for (uint32_t i = 0; i < PGZ_WINDOW; i++) pc.text[i] = (uint8_t)w[i];
         pc.hist = pc.text_len = PGZ_WINDOW;
@@ -317,6 +321,16 @@ inline void pgz_decode_unknown(const uint8_t *base, size_t size, pgz_piece &pc, 
 }
 
 // ---- the member decoder -------------------------------------------------------------------------------
+// the pieces of one round: decoded by pgz_round_decode, handed out by pgz_round_emit (two of these let the
+// next round decode while the previous one is resolved and copied out)
+struct pgz_roundbuf {
+    std::vector<pgz_piece> pieces;                     // reused from round to round
+    std::vector<int> order;                            // accepted pieces, in stream order
+    std::vector<std::vector<uint8_t>> win_before;      // the window in front of each accepted piece
+    int T = 0;
+    int rc = SSI_ERR_DATA;                             // 0 more of the member follows, 1 member end, < 0 error
+};
+
 struct pgz_member {
     const uint8_t *base = nullptr;
     size_t size = 0;
@@ -327,19 +341,38 @@ struct pgz_member {
     double t_find = 0, t_decode = 0, t_stitch = 0;    // seconds, summed over rounds
 };
 
-// Decode one round with T threads of `span` compressed bytes each; `emit(ptr, n)` receives the text in order.
-// Returns 0 (more of the member follows), 1 (the member's final block was decoded; m.bit stands behind it)
-// or an SSI_ERR_* code.
-template <typename Emit>
-int pgz_round(pgz_member &m, int T, size_t span, Emit &&emit) {
+inline double pgz_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// unknown-window symbols -> bytes, given the window in front of the piece
+inline bool pgz_resolve(const uint16_t *sym, size_t n, const std::vector<uint8_t> &win, uint8_t *out) {
+    const size_t wn = win.size();
+    bool ok = true;
+    for (size_t i = 0; i < n; i++) {
+        uint16_t v = sym[i];
+        if (v < 256) out[i] = (uint8_t)v;
+        else {
+            size_t off = (size_t)v - 256u;                       // 0 = 32 KiB before the piece, 32767 = the byte before it
+            if (off + wn < PGZ_WINDOW) { ok = false; out[i] = 0; }   // reaches before the start of the member
+            else out[i] = win[off + wn - PGZ_WINDOW];
+        }
+    }
+    return ok;                                                   // (copies of unknown symbols carry the same offsets)
+}
+
+// Decode one round with T threads of `span` compressed bytes each into `rb`, and advance the member state
+// (bit position, window, bytes produced) past it.  rb.rc: 0 more follows, 1 the member's final block was
+// decoded (m.bit stands behind it), < 0 an SSI_ERR_* code.
+inline int pgz_round_decode(pgz_member &m, pgz_roundbuf &rb, int T, size_t span) {
     const uint64_t size_bits = (uint64_t)m.size * 8u;
     const uint64_t first_byte = m.bit >> 3;
     T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)T, (m.size - first_byte) / span + 1));
-    std::vector<pgz_piece> pieces((size_t)T);
+    if (rb.pieces.size() < (size_t)T) { std::vector<pgz_piece> np((size_t)T); rb.pieces.swap(np); }
+    std::vector<pgz_piece> &pieces = rb.pieces;
+    for (auto &pc : pieces) pc.reset();
+    rb.T = T; rb.order.clear(); rb.rc = SSI_ERR_DATA;
     pieces[0].start_bit = m.bit; pieces[0].valid = true;
     const uint64_t limit_bit = std::min<uint64_t>(size_bits, (first_byte + (uint64_t)T * span) * 8u);
-    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t0 = now();
+    double t0 = pgz_now();
     // phase A: find the block starts of pieces 1..T-1
     if (T > 1) {
         std::vector<std::thread> th;
@@ -357,7 +390,7 @@ int pgz_round(pgz_member &m, int T, size_t span, Emit &&emit) {
     std::vector<uint64_t> stops;
     for (int j = 1; j < T; j++) if (pieces[(size_t)j].valid) stops.push_back(pieces[(size_t)j].start_bit);
     m.pieces_found += stops.size();
-    double t1 = now();
+    double t1 = pgz_now();
     m.t_find += t1 - t0;
     // phase B: decode
     {
@@ -374,15 +407,13 @@ int pgz_round(pgz_member &m, int T, size_t span, Emit &&emit) {
         for (auto &x : th) x.join();
     }
     m.rounds++;
-    double t2 = now();
+    double t2 = pgz_now();
     m.t_decode += t2 - t1;
-    struct stitch_timer { pgz_member &m; double t; decltype(now) &f; ~stitch_timer() { m.t_stitch += f() - t; } } st_{m, t2, now};
     // stitch: a piece is used only if the one before it ended exactly on its start
-    std::vector<int> order;
     for (int cur = 0;;) {
         pgz_piece &pc = pieces[(size_t)cur];
-        if (pc.status < 0) return pc.status;
-        order.push_back(cur);
+        if (pc.status < 0) return rb.rc = pc.status;
+        rb.order.push_back(cur);
         if (pc.status == SSI_OK) break;                              // member end
         int next = -1;
         for (int j = cur + 1; j < T; j++)
@@ -391,71 +422,85 @@ int pgz_round(pgz_member &m, int T, size_t span, Emit &&emit) {
         cur = next;
     }
     // the window in front of every accepted piece: sequential, but only the last 32 KiB of each piece matter
-    auto resolve = [](const uint16_t *sym, size_t n, const std::vector<uint8_t> &win, uint8_t *out) -> bool {
-        const size_t wn = win.size();
-        bool ok = true;
-        for (size_t i = 0; i < n; i++) {
-            uint16_t v = sym[i];
-            if (v < 256) out[i] = (uint8_t)v;
-            else {
-                size_t off = (size_t)v - 256u;                       // 0 = 32 KiB before the piece, 32767 = the byte before it
-                if (off + wn < PGZ_WINDOW) { ok = false; out[i] = 0; }   // reaches before the start of the member
-                else out[i] = win[off + wn - PGZ_WINDOW];
-            }
+    rb.win_before.resize(rb.order.size());
+    std::vector<uint8_t> w = m.window, tail, nw;
+    for (size_t k = 0; k < rb.order.size(); k++) {
+        pgz_piece &pc = pieces[(size_t)rb.order[k]];
+        rb.win_before[k] = w;
+        const size_t n8 = pc.text_len - pc.hist, n16 = rb.order[k] ? pc.sym.size() : 0;
+        nw.clear();
+        if (n8 < PGZ_WINDOW) {                                       // new window = last 32 KiB of (w | resolved sym | 8-bit text)
+            size_t need = PGZ_WINDOW - n8, take16 = std::min(need, n16);
+            tail.resize(take16);
+            if (!pgz_resolve(pc.sym.p + n16 - take16, take16, w, tail.data())) return rb.rc = SSI_ERR_DATA;
+            size_t from_w = std::min(w.size(), need - take16);
+            nw.insert(nw.end(), w.end() - (long)from_w, w.end());
+            nw.insert(nw.end(), tail.begin(), tail.end());
         }
-        return ok;                                                   // (copies of unknown symbols carry the same offsets)
-    };
-    std::vector<std::vector<uint8_t>> win_before(order.size());
-    {
-        std::vector<uint8_t> w = m.window, tail;
-        for (size_t k = 0; k < order.size(); k++) {
-            pgz_piece &pc = pieces[(size_t)order[k]];
-            win_before[k] = w;
-            const size_t n8 = pc.text_len - pc.hist, n16 = order[k] ? pc.sym.size() : 0;
-            // new window = last 32 KiB of (w | resolved sym | 8-bit text)
-            std::vector<uint8_t> nw;
-            if (n8 < PGZ_WINDOW) {
-                size_t need = PGZ_WINDOW - n8, take16 = std::min(need, n16);
-                tail.resize(take16);
-                if (!resolve(pc.sym.p + n16 - take16, take16, w, tail.data())) return SSI_ERR_DATA;
-                size_t from_w = std::min(w.size(), need - take16);
-                nw.insert(nw.end(), w.end() - (long)from_w, w.end());
-                nw.insert(nw.end(), tail.begin(), tail.end());
-            }
-            size_t t8 = std::min<size_t>(n8, PGZ_WINDOW);
-            nw.insert(nw.end(), pc.text.data() + pc.text_len - t8, pc.text.data() + pc.text_len);
-            w.swap(nw);
-        }
-        m.window.swap(w);
+        size_t t8 = std::min<size_t>(n8, PGZ_WINDOW);
+        nw.insert(nw.end(), pc.text.data() + pc.text_len - t8, pc.text.data() + pc.text_len);
+        w.swap(nw);
+        m.member_out += n16 + n8;
+        if (k > 0) { m.marker_syms += n16; m.pieces_used++; }
+        m.bit = pc.end_bit;
     }
-    // resolve the unknown-window parts in parallel, then hand the text out in order
-    std::vector<std::vector<uint8_t>> resolved(order.size());
-    std::vector<int> bad(order.size(), 0);
+    m.window.swap(w);
+    m.t_stitch += pgz_now() - t2;
+    return rb.rc = pieces[(size_t)rb.order.back()].status == SSI_OK ? 1 : 0;
+}
+
+// Resolve the unknown-window parts of a decoded round (in parallel) and hand its text out in order through
+// `emit(ptr, n)`.  Touches only `rb`.  Returns rb.rc, or SSI_ERR_DATA for a reference before the member start.
+template <typename Emit>
+int pgz_round_emit(pgz_roundbuf &rb, Emit &&emit) {
+    if (rb.rc < 0) return rb.rc;
+    std::vector<int> bad(rb.order.size(), 0);
     {
         std::vector<std::thread> th;
-        for (size_t k = 1; k < order.size(); k++) {
-            pgz_piece &pc = pieces[(size_t)order[k]];
-            if (pc.sym.size() == 0) continue;
+        for (size_t k = 1; k < rb.order.size(); k++) {
+            if (rb.pieces[(size_t)rb.order[k]].sym.size() == 0) continue;
             th.emplace_back([&, k]() {
-                pgz_piece &q = pieces[(size_t)order[k]];
-                resolved[k].resize(q.sym.size());
-                bad[k] = resolve(q.sym.p, q.sym.size(), win_before[k], resolved[k].data()) ? 0 : 1;
+                pgz_piece &q = rb.pieces[(size_t)rb.order[k]];
+                if (q.resolved.size() < q.sym.size()) q.resolved.resize(q.sym.size() + (q.sym.size() >> 2));
+                bad[k] = pgz_resolve(q.sym.p, q.sym.size(), rb.win_before[k], q.resolved.data()) ? 0 : 1;
             });
         }
         for (auto &x : th) x.join();
     }
-    for (size_t k = 0; k < order.size(); k++) {
-        pgz_piece &pc = pieces[(size_t)order[k]];
+    for (size_t k = 0; k < rb.order.size(); k++) {
+        pgz_piece &pc = rb.pieces[(size_t)rb.order[k]];
         if (bad[k]) return SSI_ERR_DATA;
-        if (k > 0) {
-            emit(resolved[k].data(), resolved[k].size());
-            m.member_out += resolved[k].size();
-            m.marker_syms += resolved[k].size();
-            m.pieces_used++;
-        }
+        if (k > 0 && pc.sym.size()) emit(pc.resolved.data(), pc.sym.size());
         const size_t n8 = pc.text_len - pc.hist;
-        if (n8) { emit(pc.text.data() + pc.hist, n8); m.member_out += n8; }
-        m.bit = pc.end_bit;
+        if (n8) emit(pc.text.data() + pc.hist, n8);
     }
-    return pieces[(size_t)order.back()].status == SSI_OK ? 1 : 0;
+    return rb.rc;
+}
+
+// Whole member, two round buffers: round r+1 is decoded while round r is resolved and handed out.
+// Returns 1 at the member end (m.bit stands behind the final block) or an SSI_ERR_* code; `keep_going()`
+// is polled between rounds (false -> returns 0).
+template <typename Emit, typename Keep>
+int pgz_member_decode(pgz_member &m, int T, size_t span, Emit &&emit, Keep &&keep_going) {
+    pgz_roundbuf *rb = new pgz_roundbuf[2];
+    int cur = 0, rc = pgz_round_decode(m, rb[0], T, span);
+    while (true) {
+        if (rc < 0) break;
+        const bool more = rc == 0;
+        std::thread next;
+        int rc_next = 0;
+        if (more) next = std::thread([&]() { rc_next = pgz_round_decode(m, rb[cur ^ 1], T, span); });
+        double t0 = pgz_now();
+        int erc = pgz_round_emit(rb[cur], emit);
+        double dt = pgz_now() - t0;
+        if (more) next.join();
+        m.t_stitch += dt;
+        if (erc < 0) { rc = erc; break; }
+        if (!more) { rc = 1; break; }
+        if (!keep_going()) { rc = 0; break; }
+        rc = rc_next;
+        cur ^= 1;
+    }
+    delete[] rb;
+    return rc;
 }
