@@ -418,16 +418,18 @@ void ss_text_source::run_gz(const job &j) {
 // ---------------------------------------------------------------------------------------------
 // stream -> chunks, and the parallel gzip producer
 // ---------------------------------------------------------------------------------------------
-bool ss_text_source::stream_writer::append(const uint8_t *p, size_t n) {
+bool ss_text_source::stream_writer::append(size_t n, const std::function<void(uint8_t *, size_t, size_t)> &fill_fn) {
     const file_map &f = src->files_[(size_t)j->file];
+    size_t done = 0;
     while (n) {
         if (!c) {
             c = src->acquire();
             if (!c) return false;
         }
         size_t take = std::min(c->cap - fill, n);
-        memcpy(c->text + fill, p, take);
-        fill += take; p += take; n -= take;
+        pgz_parallel_fill(c->text + fill, take, fill_threads,
+                          [&](uint8_t *dst, size_t off, size_t len) { fill_fn(dst, done + off, len); });
+        fill += take; done += take; n -= take;
         if (fill < c->cap) break;
         if (first) {
             std::string m;
@@ -473,7 +475,7 @@ void ss_text_source::stream_writer::abandon() {
 void ss_text_source::run_gz_parallel(const job &j, int threads, size_t span) {
     const file_map &f = files_[(size_t)j.file];
     stream_writer w;
-    w.src = this; w.j = &j;
+    w.src = this; w.j = &j; w.fill_threads = std::max(1, threads / 2);
     size_t p = 0;
     uint64_t n_members = 0;
     auto why = [](int rc) {
@@ -498,7 +500,8 @@ void ss_text_source::run_gz_parallel(const job &j, int threads, size_t span) {
                             m.marker_syms / 1e6, m.t_find, m.t_decode, m.t_stitch);
             }
         } rep{m, threads};
-        rc = pgz_member_decode(m, threads, span, [&](const uint8_t *q, size_t n) { if (ok) ok = w.append(q, n); },
+        rc = pgz_member_decode(m, threads, span,
+                               [&](size_t n, const std::function<void(uint8_t *, size_t, size_t)> &fill) { if (ok) ok = w.append(n, fill); },
                                [&]() { std::lock_guard<std::mutex> lk(mu_); return ok && !stop_; });
         if (!ok) return;                                            // stopped, or append() reported the failure
         if (rc == 0) { w.abandon(); return; }                       // asked to stop

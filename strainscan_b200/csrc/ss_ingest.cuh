@@ -10,6 +10,7 @@
 
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -95,7 +96,10 @@ private:
         size_t fill = 0;
         uint64_t chunk_idx = 0;
         bool first = true;
-        bool append(const uint8_t *p, size_t n);   // false: stopped or failed (fail() was called)
+        int fill_threads = 1;
+        // n bytes produced by fill(dst, off, len) (callable on disjoint slices from several threads);
+        // false: stopped or failed (fail() was called)
+        bool append(size_t n, const std::function<void(uint8_t *, size_t, size_t)> &fill);
         bool finish();
         void abandon();
     };

@@ -22,7 +22,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -449,32 +451,46 @@ inline int pgz_round_decode(pgz_member &m, pgz_roundbuf &rb, int T, size_t span)
     return rb.rc = pieces[(size_t)rb.order.back()].status == SSI_OK ? 1 : 0;
 }
 
-// Resolve the unknown-window parts of a decoded round (in parallel) and hand its text out in order through
-// `emit(ptr, n)`.  Touches only `rb`.  Returns rb.rc, or SSI_ERR_DATA for a reference before the member start.
+// Hand the text of a decoded round out in order.  `emit(n, fill)` receives each part as a length and a
+// function fill(dst, off, len) that writes bytes [off, off + len) of the part to dst -- a memcpy for the
+// 8-bit parts, the symbol resolution for the unknown-window parts -- so that the receiver can produce the
+// bytes directly where they are needed, several slices at a time.  Touches only `rb`.
+// Returns rb.rc, or SSI_ERR_DATA for a reference before the member start.
 template <typename Emit>
 int pgz_round_emit(pgz_roundbuf &rb, Emit &&emit) {
     if (rb.rc < 0) return rb.rc;
-    std::vector<int> bad(rb.order.size(), 0);
-    {
-        std::vector<std::thread> th;
-        for (size_t k = 1; k < rb.order.size(); k++) {
-            if (rb.pieces[(size_t)rb.order[k]].sym.size() == 0) continue;
-            th.emplace_back([&, k]() {
-                pgz_piece &q = rb.pieces[(size_t)rb.order[k]];
-                if (q.resolved.size() < q.sym.size()) q.resolved.resize(q.sym.size() + (q.sym.size() >> 2));
-                bad[k] = pgz_resolve(q.sym.p, q.sym.size(), rb.win_before[k], q.resolved.data()) ? 0 : 1;
-            });
-        }
-        for (auto &x : th) x.join();
-    }
+    std::atomic<int> bad{0};
     for (size_t k = 0; k < rb.order.size(); k++) {
         pgz_piece &pc = rb.pieces[(size_t)rb.order[k]];
-        if (bad[k]) return SSI_ERR_DATA;
-        if (k > 0 && pc.sym.size()) emit(pc.resolved.data(), pc.sym.size());
+        if (k > 0 && pc.sym.size()) {
+            const uint16_t *sym = pc.sym.p;
+            const std::vector<uint8_t> &win = rb.win_before[k];
+            emit(pc.sym.size(), [&, sym](uint8_t *dst, size_t off, size_t len) { if (!pgz_resolve(sym + off, len, win, dst)) bad = 1; });
+        }
         const size_t n8 = pc.text_len - pc.hist;
-        if (n8) emit(pc.text.data() + pc.hist, n8);
+        if (n8) {
+            const uint8_t *src = pc.text.data() + pc.hist;
+            emit(n8, [src](uint8_t *dst, size_t off, size_t len) { memcpy(dst, src + off, len); });
+        }
+        if (bad) return SSI_ERR_DATA;
     }
     return rb.rc;
+}
+
+// run fill(dst, off, len) over [0, n) in slices on up to `threads` threads
+template <typename Fill>
+void pgz_parallel_fill(uint8_t *dst, size_t n, int threads, Fill &&fill) {
+    const size_t min_slice = 1u << 20;
+    int t = (int)std::min<size_t>((size_t)std::max(1, threads), n / min_slice);
+    if (t <= 1) { fill(dst, 0, n); return; }
+    std::vector<std::thread> th;
+    size_t per = (n + (size_t)t - 1) / (size_t)t;
+    for (int i = 1; i < t; i++) {
+        size_t lo = per * (size_t)i, hi = std::min(n, lo + per);
+        if (lo < hi) th.emplace_back([&, lo, hi]() { fill(dst + lo, lo, hi - lo); });
+    }
+    fill(dst, 0, std::min(n, per));
+    for (auto &x : th) x.join();
 }
 
 // Whole member, two round buffers: round r+1 is decoded while round r is resolved and handed out.
