@@ -37,7 +37,7 @@ extern "C" {
 #define SS_ERR_NO_DEVICE    1   /* no CUDA device of compute capability 10.x */
 #define SS_ERR_CUDA         2   /* a CUDA runtime call or kernel failed */
 #define SS_ERR_IO           3   /* file open/read/inflate failure */
-#define SS_ERR_FORMAT       4   /* input is not 4-line FASTQ (wrapped FASTQ / FASTA reads are rejected) */
+#define SS_ERR_FORMAT       4   /* input is not FASTQ / FASTA, or its record framing breaks */
 #define SS_ERR_ARG          5   /* bad argument (NULL, k out of 1..32, ...) */
 #define SS_ERR_NOMEM        6
 #define SS_ERR_UNSUPPORTED  7

@@ -19,6 +19,7 @@
 #include "ss_kernels.cuh"
 #include "ss_synth.cuh"
 #include "ss_inflate.cuh"
+#include "ss_fastx.h"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -222,35 +223,9 @@ static int ensure_dense(ss_ctx *c, uint64_t n) {
 // ---------------------------------------------------------------------------------------------
 // whole file into memory (k-mer FASTA databases; gzip'ed ones are inflated by ss_inflate.cuh)
 static int read_file(const char *path, std::vector<char> &out) {
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail(SS_ERR_IO, std::string("cannot open ") + path);
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> raw((size_t)sz);
-    size_t rd = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
-    fclose(f);
-    if (rd != (size_t)sz) return fail(SS_ERR_IO, std::string("short read on ") + path);
-    const char *dot = strrchr(path, '.');
-    bool gz = (dot && strcmp(dot + 1, "gz") == 0) || (sz >= 2 && (unsigned char)raw[0] == 0x1f && (unsigned char)raw[1] == 0x8b);
-    if (!gz) { out.insert(out.end(), raw.begin(), raw.end()); return SS_OK; }
-    ssi_gz_stream *g = new ssi_gz_stream;
-    ssi_gz_init(*g, (const uint8_t *)raw.data(), raw.size());
-    const size_t win = 8u << 20;
-    std::vector<uint8_t> buf(SS_INGEST_HIST + win);
-    uint8_t *text = buf.data() + SS_INGEST_HIST;
-    int rc;
-    do {
-        uint8_t *pos = text;
-        rc = ssi_gz_read(*g, &pos, text + win);
-        size_t got = (size_t)(pos - text);
-        out.insert(out.end(), (char *)text, (char *)pos);
-        if (got >= SS_INGEST_HIST) memcpy(text - SS_INGEST_HIST, pos - SS_INGEST_HIST, SS_INGEST_HIST);
-        else if (got) { memmove(text - SS_INGEST_HIST, text - SS_INGEST_HIST + got, SS_INGEST_HIST - got); memcpy(text - got, text, got); }
-    } while (rc == SSI_MORE_OUTPUT);
-    delete g;
-    if (rc != SSI_OK) return fail(SS_ERR_IO, std::string("inflate failed on ") + path);
-    return SS_OK;
+    std::string err;
+    int rc = ss_read_whole_file(path, out, err);
+    return rc ? fail(rc, err) : SS_OK;
 }
 
 static size_t trim_tail(const char *buf, size_t len) { return ss_trim_tail(buf, len); }
@@ -258,10 +233,19 @@ static size_t find_record_start(const char *buf, size_t len, size_t from) { retu
 
 static int check_fastq_head(const char *buf, size_t len, const char *what) {
     if (len == 0) return SS_OK;
-    if (buf[0] == '>')
-        return fail(SS_ERR_FORMAT, std::string(what) + ": FASTA read input is not supported by the GPU path "
-                                                        "(convert to 4-line FASTQ)");
     if (buf[0] != '@') return fail(SS_ERR_FORMAT, std::string(what) + ": not a FASTQ file (first byte is not '@')");
+    return SS_OK;
+}
+
+// in-memory read text of any dialect Jellyfish accepts -> 4-line FASTQ (`store` keeps a rewritten copy alive)
+static int normalize_host_text(const char *&buf, size_t &len, std::vector<char> &store, const char *what) {
+    int kind = ss_fastx_kind(buf, len, true);
+    if (kind < 0) return fail(SS_ERR_FORMAT, std::string(what) + ": not a FASTQ / FASTA file (first byte is neither '@' nor '>')");
+    if (kind == 0) return SS_OK;
+    store.clear();
+    if (ss_fastx_normalize(buf, len, store))
+        return fail(SS_ERR_FORMAT, std::string(what) + ": malformed FASTA / multi-line FASTQ (record framing breaks)");
+    buf = store.data(); len = store.size();
     return SS_OK;
 }
 
@@ -550,12 +534,17 @@ static int gather_host_text(const char *const *bufs, const size_t *lens, int n, 
     size_t total = 0;
     for (int i = 0; i < n; i++) total += lens[i] + 1;
     all.reserve(total);
+    std::vector<char> store;
     for (int i = 0; i < n; i++) {
-        size_t l = trim_tail(bufs[i], lens[i]);
-        int rc = check_fastq_head(bufs[i], l, "reads");
+        const char *b = bufs[i];
+        size_t bl = lens[i];
+        int rc = normalize_host_text(b, bl, store, "reads");
+        if (rc) return rc;
+        size_t l = trim_tail(b, bl);
+        rc = check_fastq_head(b, l, "reads");
         if (rc) return rc;
         if (l == 0) continue;
-        all.insert(all.end(), bufs[i], bufs[i] + l);
+        all.insert(all.end(), b, b + l);
         all.push_back('\n');
     }
     return SS_OK;
@@ -837,8 +826,8 @@ static int check_format_result(ss_ctx *c, const char *what) {
     if (c->h_stats[4] != ~0ull) {
         char buf[256];
         snprintf(buf, sizeof buf,
-                 "%s: input is not 4-line FASTQ (line framing breaks at text byte %llu of a chunk); wrapped FASTQ / "
-                 "FASTA reads are not supported",
+                 "%s: FASTQ record framing breaks at text byte %llu of a chunk (a file must be 4-line FASTQ throughout, "
+                 "or FASTA / multi-line FASTQ from its first record on)",
                  what, c->h_stats[4]);
         return fail(SS_ERR_FORMAT, buf);
     }
@@ -1021,11 +1010,16 @@ static int count_streamed(ss_ctx *c, const ss_kmerset *s, const char *const *buf
     if (rc) return rc;
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
     stream_state ss;
+    std::vector<std::vector<char>> stores((size_t)n);
     for (int i = 0; i < n; i++) {
-        size_t l = trim_tail(bufs[i], lens[i]);
-        rc = check_fastq_head(bufs[i], l, "reads");
+        const char *b = bufs[i];
+        size_t bl = lens[i];
+        rc = normalize_host_text(b, bl, stores[(size_t)i], "reads");   // FASTA / wrapped FASTQ: rewritten copy
         if (rc) return rc;
-        rc = stream_text(c, s, bufs[i], l, ss);   // every buffer starts a record: line index restarts at 0
+        size_t l = trim_tail(b, bl);
+        rc = check_fastq_head(b, l, "reads");
+        if (rc) return rc;
+        rc = stream_text(c, s, b, l, ss);   // every buffer starts a record: line index restarts at 0
         if (rc) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); return rc; }
     }
     return finish_streamed(c, s, ss, counts, st, t0, "ss_count_host");

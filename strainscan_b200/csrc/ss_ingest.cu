@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "../../include/strainscan_b200.h"
+#include "ss_fastx.h"
 #include "ss_inflate.cuh"
 #include "ss_pgz.cuh"
 
@@ -55,6 +56,37 @@ size_t ss_find_record_start(const char *buf, size_t len, size_t from) {
 static bool ends_with_gz(const char *path) {   // identify.py:81: re.split('\.', path)[-1] == 'gz'
     const char *dot = strrchr(path, '.');
     return dot && strcmp(dot + 1, "gz") == 0;
+}
+
+int ss_read_whole_file(const char *path, std::vector<char> &out, std::string &err) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return SS_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> raw((size_t)sz + 16, 0);
+    size_t rd = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    if (rd != (size_t)sz) { err = std::string("short read on ") + path; return SS_ERR_IO; }
+    bool gz = ends_with_gz(path) || (sz >= 2 && (unsigned char)raw[0] == 0x1f && (unsigned char)raw[1] == 0x8b);
+    if (!gz) { out.insert(out.end(), raw.begin(), raw.begin() + sz); return SS_OK; }
+    ssi_gz_stream *g = new ssi_gz_stream;
+    ssi_gz_init(*g, (const uint8_t *)raw.data(), (size_t)sz);
+    const size_t win = 8u << 20;
+    std::vector<uint8_t> buf(SS_INGEST_HIST + win);
+    uint8_t *text = buf.data() + SS_INGEST_HIST;
+    int rc;
+    do {
+        uint8_t *pos = text;
+        rc = ssi_gz_read(*g, &pos, text + win);
+        size_t got = (size_t)(pos - text);
+        out.insert(out.end(), (char *)text, (char *)pos);
+        if (got >= SS_INGEST_HIST) memcpy(text - SS_INGEST_HIST, pos - SS_INGEST_HIST, SS_INGEST_HIST);
+        else if (got) { memmove(text - SS_INGEST_HIST, text - SS_INGEST_HIST + got, SS_INGEST_HIST - got); memcpy(text - got, text, got); }
+    } while (rc == SSI_MORE_OUTPUT);
+    delete g;
+    if (rc != SSI_OK) { err = std::string("inflate failed on ") + path; return SS_ERR_IO; }
+    return SS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -160,12 +192,46 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
             f.bgzf = device_bgzf_ && ssi_gz_parse_header(f.map, f.map + f.size, &h) == SSI_OK && h.bgzf_bsize >= h.header_len + 8 &&
                      h.bgzf_bsize <= f.size;
         }
+        if (f.size) {   // dialect from the head of the text: FASTA and wrapped FASTQ are rewritten on the host (ss_fastx.h)
+            std::vector<uint8_t> head(SS_INGEST_HIST + (64u << 10));
+            size_t hn = 0;
+            bool whole = false;
+            if (f.gz) {
+                ssi_gz_stream *g = new ssi_gz_stream;
+                ssi_gz_init(*g, f.map, f.size);
+                uint8_t *pos = head.data() + SS_INGEST_HIST;
+                int rc = ssi_gz_read(*g, &pos, head.data() + head.size());
+                delete g;
+                hn = (size_t)(pos - (head.data() + SS_INGEST_HIST));
+                whole = rc == SSI_OK;
+                if (rc < 0) hn = 0;                              // the producer reports the inflate error
+            } else {
+                ssize_t got2 = pread(f.fd, head.data() + SS_INGEST_HIST, 64u << 10, 0);
+                hn = got2 > 0 ? (size_t)got2 : 0;
+                whole = hn == f.size;
+            }
+            int kind = hn ? ss_fastx_kind((const char *)head.data() + SS_INGEST_HIST, hn, whole) : 0;
+            if (kind < 0) {
+                err_msg_ = f.path + ": not a FASTQ / FASTA file (first byte is neither '@' nor '>')";
+                if (f.map) munmap((void *)f.map, f.size);
+                close(f.fd);
+                finish();
+                return SS_ERR_FORMAT;
+            }
+            if (kind == 1) { f.normalize = true; f.bgzf = false; }
+        }
         files_.push_back(f);
     }
     // jobs: one per gzip stream (serial by nature); plain files in record-aligned parts
     for (size_t fi = 0; fi < files_.size(); fi++) {
         const file_map &f = files_[fi];
         if (f.size == 0) continue;
+        if (f.normalize) {
+            job j; j.file = (int)fi; j.lo = 0; j.hi = f.size; j.first_of_file = true;
+            jobs_.push_back(j);
+            gz_bytes_ += f.size;                                 // size after rewriting is unknown: grow by segments
+            continue;
+        }
         if (f.bgzf) {
             // members inflate independently: cut the file into parts at member starts (found by their
             // 16-byte BGZF header signature and confirmed by walking the chain), one producer per part
@@ -285,7 +351,8 @@ void ss_text_source::worker() {
             j = jobs_[next_job_++];
         }
         const file_map &f = files_[(size_t)j.file];
-        if (f.bgzf) run_bgzf(j);
+        if (f.normalize) run_normalize(j);
+        else if (f.bgzf) run_bgzf(j);
         else if (f.gz) {
             // an ordinary gzip stream: decoded by several threads per round when cores are to spare (ss_pgz.cuh)
             int t = std::max(1, n_threads_ / std::max(1, n_gz_jobs_));
@@ -470,6 +537,26 @@ bool ss_text_source::stream_writer::finish() {
 void ss_text_source::stream_writer::abandon() {
     if (c) src->release(c);
     c = nullptr;
+}
+
+// FASTA / wrapped FASTQ: read (and inflate) the whole file, rewrite it as 4-line FASTQ, chunk it
+void ss_text_source::run_normalize(const job &j) {
+    const file_map &f = files_[(size_t)j.file];
+    std::vector<char> raw, norm;
+    std::string err;
+    int rc = ss_read_whole_file(f.path.c_str(), raw, err);
+    if (rc) { fail(rc, err); return; }
+    if (ss_fastx_normalize(raw.data(), raw.size(), norm)) {
+        fail(SS_ERR_FORMAT, f.path + ": malformed FASTA / multi-line FASTQ (record framing breaks)");
+        return;
+    }
+    std::vector<char>().swap(raw);
+    stream_writer w;
+    w.src = this; w.j = &j; w.fill_threads = 2;
+    w.first = false;                                            // the rewritten text opens with '@' by construction
+    const char *src = norm.data();
+    if (!w.append(norm.size(), [src](uint8_t *dst, size_t off, size_t len) { memcpy(dst, src + off, len); })) return;
+    w.finish();
 }
 
 void ss_text_source::run_gz_parallel(const job &j, int threads, size_t span) {

@@ -48,6 +48,8 @@ struct ss_chunk {
 };
 
 // FASTQ framing helpers shared with ss_api.cu
+// whole file into memory; gzip'ed files (by suffix or magic) are inflated.  Returns SS_OK or an SS_ERR_* code.
+int ss_read_whole_file(const char *path, std::vector<char> &out, std::string &err);
 size_t ss_trim_tail(const char *buf, size_t len);
 size_t ss_find_record_start(const char *buf, size_t len, size_t from);
 
@@ -80,7 +82,7 @@ public:
     bool ready() const { return !bufs_.empty(); }
 
 private:
-    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false, bgzf = false; };
+    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false, bgzf = false, normalize = false; };
     struct job { int file = 0; size_t lo = 0, hi = 0; bool first_of_file = false; };
 
     void worker();
@@ -88,6 +90,7 @@ private:
     void run_gz(const job &j);
     void run_gz_parallel(const job &j, int threads, size_t span);
     void run_bgzf(const job &j);
+    void run_normalize(const job &j);
     // in-order byte stream of one file -> record-aligned chunks (used by the parallel gzip decoder)
     struct stream_writer {
         ss_text_source *src = nullptr;

@@ -25,7 +25,9 @@ def _gold_dense(case):
 
 
 def _supported(case):
-    return case["name"] not in ("wrapped_fastq", "fasta_reads")
+    """Every dialect the reference engine accepts is supported: FASTA and multi-line FASTQ reads are rewritten
+    as 4-line FASTQ on the host (csrc/ss_fastx.h) before the scan."""
+    return True
 
 
 def _check_against_dump(case, got, flags):
@@ -93,14 +95,20 @@ def test_golden_files_plain_and_gz(eng, golden_cases, tmp_path):
 
 def test_unsupported_inputs_fail_loudly(eng, golden_cases):
     from strainscan_b200 import StrainScanB200Error
-    for case in golden_cases:
-        if _supported(case):
-            continue
-        ks = eng.kmerset_from_text(case["fasta"], case["k"])
+    case = [c for c in golden_cases if c["name"] == "strand"][0]
+    ks = eng.kmerset_from_text(case["fasta"], case["k"])
+    bad_inputs = [
+        b"hello world\n",                                           # not a sequence file
+        b"@r1\nACGT\n+\nIIII\n@r2\nACGT\nACGT\n+\nIIIIIIII\n",       # 4-line head, wrapped record later: framing breaks
+        b"@r1\nACGT\nACGT\n+\nIIII\n",                              # wrapped, quality shorter than the sequence
+    ]
+    for text in bad_inputs:
         with pytest.raises(StrainScanB200Error) as ei:
-            reads = eng.reads_from_host([r.encode() for r in case["reads"]])
-            eng.count(ks, reads)
-        assert ei.value.code == 4   # SS_ERR_FORMAT
+            eng.count(ks, eng.reads_from_host([text]))
+        assert ei.value.code == 4, text   # SS_ERR_FORMAT
+        with pytest.raises(StrainScanB200Error) as ei:
+            eng.count_host(ks, [text])
+        assert ei.value.code == 4, text
     with pytest.raises(StrainScanB200Error):
         eng.kmerset_from_text(">1\nACGT\n", 33)
     with pytest.raises(StrainScanB200Error):

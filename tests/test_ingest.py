@@ -131,8 +131,8 @@ def test_errors_are_loud(fastq, tmp_path):
         "truncated.fq.gz": gz[:len(gz) // 2],
         "no_trailer.fq.gz": gz[:-8],
         "not_gzip.fq.gz": fastq,
-        "fasta.fq": b">r1\nACGT\n",
         "junk.fq": b"hello\n",
+        "bad_wrapped.fq": b"@r1\nACGT\nACGT\n+\nIIII\n",
     }
     corrupt = bytearray(gz)
     corrupt[len(gz) // 3] ^= 0x55
@@ -231,9 +231,8 @@ def test_bgzf_small_and_broken(tmp_path, monkeypatch):
     open(p, "wb").write(good[:len(good) // 2])                 # chain cut inside a member
     with pytest.raises(_lib.StrainScanB200Error):
         ingest([p], chunk=BGZF_CHUNK)
-    open(p, "wb").write(util.bgzf_compress(b">r1\nACGT\n"))
-    with pytest.raises(_lib.StrainScanB200Error, match="FASTA"):
-        ingest([p], chunk=BGZF_CHUNK)
+    open(p, "wb").write(util.bgzf_compress(b">r1\nACGT\n"))            # FASTA inside BGZF: rewritten on the host
+    assert ingest([p], chunk=BGZF_CHUNK)[0] == b"@r1\nACGT\n+\nIIII\n"
 
 
 @pytest.mark.parametrize("block", [0xFF00, 5000, 300])
@@ -342,3 +341,27 @@ def test_parallel_gzip_errors(tmp_path, monkeypatch):
     a = ingest([p], threads=1)[0]
     monkeypatch.setenv("SS_PGZ_THREADS", "1")
     assert ingest([p], threads=1)[0] == a == fq
+
+
+def test_fasta_and_wrapped_fastq_are_rewritten(tmp_path):
+    """Dialects Jellyfish accepts beyond 4-line FASTQ (csrc/ss_fastx.h): the sequence characters arrive in the
+    same order on one line per record, whatever the file encoding."""
+    rng = np.random.default_rng(41)
+    seqs = [util.rand_genome(rng, int(n)) for n in rng.integers(1, 400, 300)]
+    fasta = b"".join(b">s%d some text\n" % i + b"\n".join(s[j:j + 60] for j in range(0, len(s), 60)) + b"\n" for i, s in enumerate(seqs))
+    wrapped = b"".join(b"@s%d\n" % i + b"\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + b"\n+\n" +
+                       b"\n".join((b"@" * len(s))[j:j + 50] for j in range(0, len(s), 50)) + b"\n" for i, s in enumerate(seqs))
+    want_fa = b"".join(b"@s%d some text\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(seqs))
+    want_fq = b"".join(b"@s%d\n%s\n+\n%s\n" % (i, s, b"@" * len(s)) for i, s in enumerate(seqs))
+    for name, blob, want in (("a.fa", fasta, want_fa), ("a.fa.gz", gzip.compress(fasta), want_fa),
+                             ("w.fq", b"\n\n" + wrapped, want_fq), ("w.fq.gz", util.bgzf_compress(wrapped), want_fq),
+                             ("crlf.fa", fasta.replace(b"\n", b"\r\n"), None)):
+        p = str(tmp_path / name)
+        open(p, "wb").write(blob)
+        got, _ = ingest([p], chunk=BGZF_CHUNK)
+        if want is not None:
+            assert got == want, name
+        else:                                   # CR characters stay inside the joined sequence (they break windows there too)
+            assert got.count(b"\n") == 4 * len(seqs) and got.startswith(b"@s0 some text\r\n")
+        parts = [ingest([p], s, 2, chunk=256 << 10)[0] for s in range(2)]
+        assert sorted(b"".join(parts).split(b"\n")) == sorted(got.split(b"\n"))
