@@ -380,6 +380,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "ss_probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_kmer": bytes_per_kmer, "kmers_per_launch": st.n_kmers, "launch_ms": probe_avg_ms,
+                "note": "achieved = algorithmic bytes (SURVEY 8d: 32 B table sector + 1 B text per k-mer, + second sectors and "
+                        "counter updates) / launch time; an L2-resident filter answers ~97 % of the probes, so the DRAM traffic "
+                        "(`traffic`, ncu) is ~4x smaller than the algorithmic bytes; what binds the kernel is the L1 tag stage "
+                        "and the L2 random-sector rate (~4.0 ms per launch each, DESIGN.md section 3)",
                 "random_sector_gather_gbps": rand_gbps,
                 "frac_of_random_gather": (st.n_kmers * 32.0 * (1 + p2) / (probe_avg_ms * 1e-3) / 1e9 / rand_gbps)
                 if rand_gbps else None}
