@@ -89,6 +89,13 @@ int ss_device_info(const ss_ctx *ctx, char *name, size_t name_cap, int *n_sm, ui
  * Vote_...:359-371) and kmer_index_dict (identify.py:90-95). */
 int ss_kmerset_from_fasta(ss_ctx *ctx, const char *path, int k, ss_kmerset **set);
 int ss_kmerset_from_text(ss_ctx *ctx, const char *text, size_t len, int k, ss_kmerset **set);
+/* Same as ss_kmerset_from_fasta with a binary cache of the parsed records (packed 2-bit k-mers, validity flags,
+ * header ids: 9 bytes per record instead of ~36 of text) at `cache_path`: used when it matches the FASTA's size,
+ * mtime and k, (re)written otherwise (best effort).  The FASTA stays the source of truth.  *cache_hit (may be NULL)
+ * tells which way it went.  Removes the text parse the adapters pay per call (identify.py:90-95 re-reads kmer.fa
+ * every time). */
+int ss_kmerset_from_fasta_cached(ss_ctx *ctx, const char *path, int k, const char *cache_path, int *cache_hit,
+                                 ss_kmerset **set);
 int ss_kmerset_free(ss_kmerset *set);
 uint64_t ss_kmerset_records(const ss_kmerset *set);   /* int(len(lines)/2) */
 uint64_t ss_kmerset_distinct(const ss_kmerset *set);  /* distinct valid k-mers (= dump lines) */

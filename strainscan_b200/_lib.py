@@ -59,6 +59,7 @@ SIGNATURES = {
     "ss_device_info": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "ss_kmerset_from_fasta": (C.c_int, [_P, C.c_char_p, C.c_int, _PP]),
     "ss_kmerset_from_text": (C.c_int, [_P, C.c_char_p, C.c_size_t, C.c_int, _PP]),
+    "ss_kmerset_from_fasta_cached": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), _PP]),
     "ss_kmerset_free": (C.c_int, [_P]),
     "ss_kmerset_records": (C.c_uint64, [_P]),
     "ss_kmerset_distinct": (C.c_uint64, [_P]),

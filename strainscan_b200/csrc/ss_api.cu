@@ -4,6 +4,9 @@
 // Replaces the process/file protocol around library/jellyfish-linux at
 //   library/identify.py:73-103, library/identify_low_mem.py:67-90, library/identify_low_depth.py:46-74,
 //   library/Vote_Strain_L2_Lasso_new_sp.py:354-403.
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -310,12 +313,17 @@ static void parse_fasta_range(const char *text, size_t len, size_t lo, size_t hi
     }
 }
 
-static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset **out) {
-    if (!c || !out) return fail(SS_ERR_ARG, "kmerset: NULL argument");
-    *out = nullptr;
-    if (k < 1 || k > 32) return fail(SS_ERR_UNSUPPORTED, "kmerset: k must be in 1..32 (one 64-bit word per k-mer)");
-    SS_CUDA(cudaSetDevice(c->device));
+// the parsed form of a k-mer FASTA: what the table build consumes and what the binary cache stores
+struct parsed_set {
+    uint64_t n = 0;
+    std::vector<uint64_t> keys;          // packed k-mer of every record (0 when not ok)
+    std::vector<uint8_t> ok, raw_upper;  // record is k ACGT chars after case folding / already uppercase
+    std::vector<uint64_t> header_ids;    // integer after '>' (0 if none)
+};
 
+static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out);
+
+static int parse_set(const char *text, size_t len, int k, parsed_set &ps) {
     // line structure (Python readlines(): a last line without '\n' still counts)
     unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     if (len < (1u << 20)) T = 1;
@@ -344,21 +352,40 @@ static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset 
     if (len > 0 && text[len - 1] != '\n') n_lines++;
     uint64_t n = n_lines / 2;
     if (n >= 0xFFFFFFF0ull) return fail(SS_ERR_UNSUPPORTED, "kmerset: more than 2^32 records");
-
-    std::vector<uint64_t> keys(n);
-    std::vector<uint8_t> ok(n, 0), raw_upper(n, 0);
-    ss_kmerset *s = new ss_kmerset();
-    s->ctx = c; s->k = k; s->n_records = n;
-    s->header_ids.assign(n, 0);
+    ps.n = n;
+    ps.keys.assign(n, 0); ps.ok.assign(n, 0); ps.raw_upper.assign(n, 0); ps.header_ids.assign(n, 0);
     {
         std::vector<std::thread> th;
         for (unsigned t = 0; t < T; t++)
             th.emplace_back([&, t]() {
-                parse_fasta_range(text, len, cut[t], cut[t + 1], line_at[t], k, n, keys.data(), ok.data(),
-                                  raw_upper.data(), s->header_ids.data());
+                parse_fasta_range(text, len, cut[t], cut[t + 1], line_at[t], k, n, ps.keys.data(), ps.ok.data(),
+                                  ps.raw_upper.data(), ps.header_ids.data());
             });
         for (auto &x : th) x.join();
     }
+    return SS_OK;
+}
+
+static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset **out, parsed_set *keep = nullptr) {
+    if (!c || !out) return fail(SS_ERR_ARG, "kmerset: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(SS_ERR_UNSUPPORTED, "kmerset: k must be in 1..32 (one 64-bit word per k-mer)");
+    parsed_set local;
+    parsed_set &ps = keep ? *keep : local;
+    int rc = parse_set(text, len, k, ps);
+    if (rc) return rc;
+    return build_from_parsed(c, k, ps, out);
+}
+
+static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out) {
+    *out = nullptr;
+    SS_CUDA(cudaSetDevice(c->device));
+    const uint64_t n = ps.n;
+    std::vector<uint64_t> &keys = ps.keys;
+    std::vector<uint8_t> &ok = ps.ok, &raw_upper = ps.raw_upper;
+    ss_kmerset *s = new ss_kmerset();
+    s->ctx = c; s->k = k; s->n_records = n;
+    s->header_ids = ps.header_ids;
     uint64_t n_ok = 0;
     for (uint64_t i = 0; i < n; i++) {
         n_ok += ok[i];
@@ -460,6 +487,89 @@ extern "C" int ss_kmerset_from_fasta(ss_ctx *c, const char *path, int k, ss_kmer
     int rc = read_file(path, buf);
     if (rc) return rc;
     return build_set(c, buf.data(), buf.size(), k, out);
+}
+
+// ---- binary database cache: the parsed form of a k-mer FASTA next to / instead of re-parsing the
+// text.  The FASTA stays the source of truth: the cache records its size and mtime and is ignored when they differ.
+struct cache_header {
+    char magic[8];              // "SSB200K1"
+    uint32_t k, ids_mode;       // ids_mode: 0 all zero, 1 identity (1..n), 2 constant, 3 explicit array
+    uint64_t n, ids_const, src_size, src_mtime_ns;
+};
+
+static bool stat_file(const char *path, uint64_t *size, uint64_t *mtime_ns) {
+    struct stat st;
+    if (stat(path, &st) != 0) return false;
+    *size = (uint64_t)st.st_size;
+    *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    return true;
+}
+
+static bool cache_write(const char *cache_path, int k, const parsed_set &ps, uint64_t src_size, uint64_t src_mtime_ns) {
+    std::string tmp = std::string(cache_path) + ".tmp" + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    cache_header h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "SSB200K1", 8);
+    h.k = (uint32_t)k; h.n = ps.n; h.src_size = src_size; h.src_mtime_ns = src_mtime_ns;
+    bool zero = true, ident = true, cst = true;
+    for (uint64_t i = 0; i < ps.n; i++) {
+        uint64_t v = ps.header_ids[i];
+        zero &= v == 0; ident &= v == i + 1; cst &= v == ps.header_ids[0];
+    }
+    h.ids_mode = zero ? 0 : ident ? 1 : cst ? 2 : 3;
+    h.ids_const = (cst && ps.n) ? ps.header_ids[0] : 0;
+    std::vector<uint8_t> fl(ps.n);
+    for (uint64_t i = 0; i < ps.n; i++) fl[i] = (uint8_t)((ps.ok[i] ? 1 : 0) | (ps.raw_upper[i] ? 2 : 0));
+    bool good = fwrite(&h, sizeof h, 1, f) == 1 && (ps.n == 0 || (fwrite(ps.keys.data(), 8, ps.n, f) == ps.n && fwrite(fl.data(), 1, ps.n, f) == ps.n));
+    if (good && h.ids_mode == 3) good = fwrite(ps.header_ids.data(), 8, ps.n, f) == ps.n;
+    good = (fclose(f) == 0) && good;
+    if (!good || rename(tmp.c_str(), cache_path) != 0) { remove(tmp.c_str()); return false; }
+    return true;
+}
+
+static bool cache_read(const char *cache_path, int k, uint64_t src_size, uint64_t src_mtime_ns, bool check_src, parsed_set &ps) {
+    FILE *f = fopen(cache_path, "rb");
+    if (!f) return false;
+    cache_header h;
+    bool good = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "SSB200K1", 8) == 0 && h.k == (uint32_t)k && h.ids_mode <= 3 &&
+                h.n < 0xFFFFFFF0ull && (!check_src || (h.src_size == src_size && h.src_mtime_ns == src_mtime_ns));
+    if (good) {
+        ps.n = h.n;
+        ps.keys.resize(h.n); ps.ok.resize(h.n); ps.raw_upper.resize(h.n); ps.header_ids.resize(h.n);
+        std::vector<uint8_t> fl(h.n);
+        good = h.n == 0 || (fread(ps.keys.data(), 8, h.n, f) == h.n && fread(fl.data(), 1, h.n, f) == h.n);
+        for (uint64_t i = 0; good && i < h.n; i++) { ps.ok[i] = fl[i] & 1; ps.raw_upper[i] = (fl[i] >> 1) & 1; }
+        if (good && h.ids_mode == 3) good = fread(ps.header_ids.data(), 8, h.n, f) == h.n;
+        else if (good) for (uint64_t i = 0; i < h.n; i++) ps.header_ids[i] = h.ids_mode == 1 ? i + 1 : h.ids_mode == 2 ? h.ids_const : 0;
+        if (good) { char extra; good = fread(&extra, 1, 1, f) == 0; }          // nothing behind the arrays
+        if (good && k < 32) for (uint64_t i = 0; good && i < h.n; i += 4097) good = (ps.keys[i] >> (2 * k)) == 0;   // spot check
+    }
+    fclose(f);
+    return good;
+}
+
+extern "C" int ss_kmerset_from_fasta_cached(ss_ctx *c, const char *path, int k, const char *cache_path, int *cache_hit,
+                                            ss_kmerset **out) {
+    if (!c || !path || !cache_path || !out) return fail(SS_ERR_ARG, "ss_kmerset_from_fasta_cached: NULL argument");
+    *out = nullptr;
+    if (cache_hit) *cache_hit = 0;
+    if (k < 1 || k > 32) return fail(SS_ERR_UNSUPPORTED, "kmerset: k must be in 1..32 (one 64-bit word per k-mer)");
+    uint64_t sz = 0, mt = 0;
+    if (!stat_file(path, &sz, &mt)) return fail(SS_ERR_IO, std::string("cannot open ") + path);
+    parsed_set ps;
+    if (cache_read(cache_path, k, sz, mt, true, ps)) {
+        if (cache_hit) *cache_hit = 1;
+        return build_from_parsed(c, k, ps, out);
+    }
+    std::vector<char> buf;
+    int rc = read_file(path, buf);
+    if (rc) return rc;
+    rc = build_set(c, buf.data(), buf.size(), k, out, &ps);
+    if (rc) return rc;
+    cache_write(cache_path, k, ps, sz, mt);          // best effort: a read-only cache directory is not an error
+    return SS_OK;
 }
 
 extern "C" int ss_kmerset_free(ss_kmerset *s) {

@@ -62,6 +62,13 @@ class Engine:
         check(self.lib.ss_kmerset_from_fasta(self.h, path.encode(), int(k), C.byref(h)))
         return KmerSet(self, h)
 
+    def kmerset_from_fasta_cached(self, path, k, cache_path):
+        """Binary cache of the parsed records next to the text FASTA; returns (KmerSet, cache_hit)."""
+        h = C.c_void_p()
+        hit = C.c_int(0)
+        check(self.lib.ss_kmerset_from_fasta_cached(self.h, path.encode(), int(k), cache_path.encode(), C.byref(hit), C.byref(h)))
+        return KmerSet(self, h), bool(hit.value)
+
     def kmerset_from_text(self, text, k):
         if isinstance(text, str):
             text = text.encode()

@@ -38,10 +38,29 @@ def default_engine():
     return _ENGINE
 
 
+def _db_cache_path(fasta_path, k):
+    """Where the binary form of a k-mer FASTA is kept: SS_DB_CACHE=1 -> next to the FASTA (<fasta>.k<k>.ssb200),
+    SS_DB_CACHE=<dir> -> in that directory (for read-only databases), unset -> no cache."""
+    where = os.environ.get("SS_DB_CACHE", "")
+    if not where or where == "0":
+        return None
+    full = os.path.abspath(fasta_path)
+    if where == "1":
+        return "%s.k%d.ssb200" % (full, int(k))
+    import hashlib
+    tag = hashlib.sha1(full.encode()).hexdigest()[:16]
+    os.makedirs(where, exist_ok=True)
+    return os.path.join(where, "%s_%s.k%d.ssb200" % (os.path.basename(full), tag, int(k)))
+
+
 def cached_kmerset(engine, fasta_path, k):
     key = (engine.device, os.path.abspath(fasta_path), int(k), os.path.getmtime(fasta_path))
     if key not in _SETS:
-        _SETS[key] = engine.kmerset_from_fasta(fasta_path, k)
+        cache = _db_cache_path(fasta_path, k)
+        if cache:
+            _SETS[key] = engine.kmerset_from_fasta_cached(fasta_path, k, cache)[0]
+        else:
+            _SETS[key] = engine.kmerset_from_fasta(fasta_path, k)
     return _SETS[key]
 
 

@@ -396,3 +396,38 @@ def test_bgzf_device_inflate(tmp_path, monkeypatch):
         assert np.array_equal(e.count_files(ks, [str(p1), str(p2)])[0], got)
     finally:
         e.close()
+
+
+def test_binary_database_cache(eng, golden_cases, tmp_path):
+    """the parsed form of a k-mer FASTA cached in binary next to the text.  A set built from the cache
+    must be indistinguishable from one parsed from the text (flags, header ids, counts); a stale or foreign cache
+    is ignored and rewritten; the FASTA stays the source of truth."""
+    rng = np.random.default_rng(8)
+    G = util.rand_genome(rng, 100_000)
+    cases = [(util.make_db(rng, G, 31, 12_000, lower_frac=0.03, junk=40), 31),
+             (util.make_db(rng, G, 21, 5_000, header=None), 21)]            # header ids 1..n (all_kmer.fasta form)
+    cases += [(c["fasta"].encode(), c["k"]) for c in golden_cases if c["name"] in ("if_oddities", "polyT_k32", "l2_k21")]
+    fq = util.make_reads(rng, G, 4000, 150)
+    for i, (fa, k) in enumerate(cases):
+        p, cp = tmp_path / ("db%d.fa" % i), str(tmp_path / ("db%d.cache" % i))
+        p.write_bytes(fa)
+        ks0 = eng.kmerset_from_fasta(str(p), k)
+        ks1, hit1 = eng.kmerset_from_fasta_cached(str(p), k, cp)
+        ks2, hit2 = eng.kmerset_from_fasta_cached(str(p), k, cp)
+        assert (hit1, hit2) == (False, True) and os.path.getsize(cp) < len(fa)
+        reads = eng.reads_from_host([fq])
+        want = eng.count(ks0, reads)[0]
+        for ks in (ks1, ks2):
+            assert np.array_equal(ks.flags, ks0.flags) and np.array_equal(ks.header_ids, ks0.header_ids)
+            assert ks.n_distinct == ks0.n_distinct and ks.n_records == ks0.n_records
+            assert np.array_equal(eng.count(ks, reads)[0], want)
+        # another k, a changed FASTA, a truncated cache: not used
+        assert eng.kmerset_from_fasta_cached(str(p), k - 2, cp)[1] is False
+        assert eng.kmerset_from_fasta_cached(str(p), k, cp)[1] is False          # the k-2 call rewrote it
+        p.write_bytes(fa + b">1\n" + G[:k] + b"\n")
+        ks3, hit3 = eng.kmerset_from_fasta_cached(str(p), k, cp)
+        assert hit3 is False and ks3.n_records == ks0.n_records + 1
+        blob = open(cp, "rb").read()
+        open(cp, "wb").write(blob[:len(blob) // 2])
+        assert eng.kmerset_from_fasta_cached(str(p), k, cp)[1] is False
+        assert eng.kmerset_from_fasta_cached(str(p), k, cp)[1] is True
