@@ -431,3 +431,21 @@ def test_binary_database_cache(eng, golden_cases, tmp_path):
         open(cp, "wb").write(blob[:len(blob) // 2])
         assert eng.kmerset_from_fasta_cached(str(p), k, cp)[1] is False
         assert eng.kmerset_from_fasta_cached(str(p), k, cp)[1] is True
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 25, 30])
+def test_small_and_odd_k(eng, k):
+    """Every k the one-word key supports, against the oracle: short k stresses the window masks (nearly every
+    position is a valid window, lines shorter than a 32-byte run) and table collisions (4^k < records)."""
+    rng = np.random.default_rng(500 + k)
+    G = util.rand_genome(rng, 30_000)
+    fa = util.make_db(rng, G, k, min(3000, len(G) - k - 1), both_strands=True, junk=12)
+    fq = util.make_reads(rng, G, 1500, 80, var_len=True, p_n=0.02, lower_frac=0.1)
+    fq += b"@tiny\nA\n+\nI\n@nn\nNNNN\n+\nIIII\n"
+    ks = eng.kmerset_from_text(fa, k)
+    d = adapters.count_dense(fa, k, [fq])
+    got, st = eng.count(ks, eng.reads_from_host([fq]))
+    assert np.array_equal(got.astype(np.uint64), d.cnt)
+    assert st.n_kmers == adapters.count_windows([fq], k)
+    got2, _ = eng.count_host(ks, [fq])
+    assert np.array_equal(got2, got)
