@@ -12,6 +12,18 @@
                      the jellyfish block of vote_strain_L2() (Vote_Strain_L2_Lasso_new_sp.py:348-403)
                      replaced by strainscan_b200.l2_shim.count_cluster.  Tree descent, Pre_Scan,
                      ElasticNet and the report writers are untouched.
+--plasmid-db DIR   : plasmid_mode (-p 1 / -p 2) builds a database at run time by shelling out to
+                     `python StrainScan_build.py -i <refs> -o <out>/DB_plasmid -n 500` (StrainScan.py:235),
+                     whose tool chain (dashing, R, sibeliaz) is absent from this image.  With this option
+                     that ONE os.system call is answered by copying the pre-made database DIR to the
+                     -o directory of the command, for either engine alike; everything after it (the tree
+                     search and the intra-cluster search against DB_plasmid, StrainScan.py:238-266) is the
+                     reference's own code.
+--engine b200-full : as b200, plus the SURVEY 8f mirrors in place of the reference's per-node and per-strain
+                     reductions: match_node of identify / identify_low_mem / identify_low_depth (a5, a7) ->
+                     identify_shim.match_node[_low_depth] (array gathers of the dense GPU vector), and
+                     cal_cov_all / get_candidate_arr / get_remainc of identify_strains_L2_Enet_Pscan_new_sp
+                     (a11, a12) -> l2_shim (ss_strain_reduce on the GPU).  Decisions stay the reference's.
 Both engines seed numpy / random identically (identify.py:214 draws unseeded Poisson samples).
 Reports (final_report.txt, C*/StrainVote.report, strain_prob.txt) must come out byte-identical.
 """
@@ -54,15 +66,60 @@ def install_b200():
     exec(compile(src, path, "exec"), mod.__dict__)
 
 
+def install_b200_reducers():
+    """The optional mirrors under the reference's own names and signatures."""
+    import numpy as np
+    from strainscan_b200 import identify_shim, l2_shim
+    from library import identify, identify_low_depth, identify_low_mem
+    identify.match_node = identify_shim.match_node
+    identify_low_mem.match_node = identify_shim.match_node
+    identify_low_depth.match_node = identify_shim.match_node_low_depth
+    import identify_strains_L2_Enet_Pscan_new_sp as ids          # the module Vote_... imports (library/ on sys.path)
+
+    def cal_cov_all(ix, iy):                                      # ix: rows x strains (identify_strains...:44-49)
+        return l2_shim.cal_cov_all(ix, iy)
+
+    def get_candidate_arr(ix, iy):                                # ix: strains x rows (identify_strains...:121-134)
+        cand, check = l2_shim.get_candidate_arr(ix.T, iy)
+        return cand, np.result_type(ix.dtype, np.asarray(iy).dtype).type(check)   # np.sum()'s scalar type is printed
+
+    def get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc):             # identify_strains...:94-108
+        return l2_shim.get_remainc(dominat, used_kmer, pXt_tem.T, py, strain_remainc)
+
+    ids.cal_cov_all, ids.get_candidate_arr, ids.get_remainc = cal_cov_all, get_candidate_arr, get_remainc
+
+
+def install_plasmid_db(src_dir):
+    """Answer `python StrainScan_build.py ... -o X ...` (StrainScan.py:235) with a copy of src_dir at X."""
+    import shlex
+    import shutil
+    real_system = os.system
+
+    def system(cmd):
+        tok = shlex.split(cmd) if isinstance(cmd, str) else []
+        if len(tok) > 2 and tok[0] == "python" and tok[1] == "StrainScan_build.py" and "-o" in tok:
+            dst = tok[tok.index("-o") + 1]
+            shutil.rmtree(dst, ignore_errors=True)
+            shutil.copytree(src_dir, dst)
+            print("[run_pipeline] StrainScan_build.py stand-in: %s -> %s" % (src_dir, dst))
+            return 0
+        return real_system(cmd)
+
+    os.system = system
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--engine", choices=["reference", "b200"], required=True)
+    ap.add_argument("--engine", choices=["reference", "b200", "b200-full"], required=True)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--plasmid-db", default=None)
     ap.add_argument("rest", nargs=argparse.REMAINDER)
     a = ap.parse_args()
     rest = a.rest[1:] if a.rest and a.rest[0] == "--" else a.rest
     if not os.path.isdir(REF):
         sys.exit("baseline/_ref missing: run `python baseline/setup_ref.py` where the reference is mounted")
+    if a.plasmid_db:
+        a.plasmid_db = os.path.abspath(a.plasmid_db)
     # absolute paths before we chdir into the sandbox (the reference uses cwd-relative imports/temp files)
     for i, tok in enumerate(rest):
         if i > 0 and rest[i - 1] in ("-i", "-j", "-d", "-o", "-r") and not os.path.isabs(tok):
@@ -74,8 +131,12 @@ def main():
     import numpy as np
     np.random.seed(a.seed)
     random.seed(a.seed)
-    if a.engine == "b200":
+    if a.engine in ("b200", "b200-full"):
         install_b200()
+    if a.engine == "b200-full":
+        install_b200_reducers()
+    if a.plasmid_db:
+        install_plasmid_db(a.plasmid_db)
     spec = importlib.util.spec_from_file_location("StrainScan", os.path.join(REF, "StrainScan.py"))
     ss = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ss)

@@ -36,7 +36,13 @@ def run_case(engine, db_dir, name, work):
         db_dir = db_dir[bool(synth_db.CASES[name].get("low_mem", False))]
     args = synth_db.make_case_inputs(db, name, work)
     out = os.path.join(work, "out_%s_%s" % (engine, name))
-    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_pipeline.py"), "--engine", engine, "--"] + args + \
+    opts = []
+    if "pmix" in synth_db.CASES[name]:
+        pdir = os.path.join(work, "DB_plasmid_src")
+        if not os.path.isdir(pdir):
+            synth_db.write_plasmid_db(work)
+        opts = ["--plasmid-db", pdir]
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_pipeline.py"), "--engine", engine] + opts + ["--"] + args + \
           ["-d", db_dir, "-o", out] + synth_db.CASES[name]["flags"]
     log = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if log.returncode != 0:

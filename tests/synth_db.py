@@ -27,7 +27,7 @@ def _rand_seq(rng, n):
 class SynthDB:
     """4 clusters with 3/2/1/2 strains; 7-node search tree: leaves 1..4, internal 5=(1,2) 6=(3,4), root 7."""
 
-    def __init__(self, seed=20260117, seg_len=5000, n_seg=12, snp_rate=0.004):
+    def __init__(self, seed=20260117, seg_len=5000, n_seg=12, snp_rate=0.004, prefix="GCF"):
         rng = np.random.default_rng(seed)
         self.seed = seed
         self.n_strains = {1: 3, 2: 2, 3: 1, 4: 2}
@@ -64,7 +64,7 @@ class SynthDB:
                                 continue
                             g[p] = b"ACGT"[(b"ACGT".index(g[p]) + 1 + int(rng.integers(0, 3))) % 4]
                             pos.append(p)
-                self.strain_name[(c, s)] = "GCF_C%d_S%d" % (c, s)
+                self.strain_name[(c, s)] = "%s_C%d_S%d" % (prefix, c, s)
                 self.strain_genome[(c, s)] = bytes(g)
                 self.snps[(c, s)] = pos
         self.rng = rng
@@ -211,25 +211,59 @@ CASES = {
     "extra_region": dict(mix=[((1, 2), 10), ((2, 2), 5)], flags=["-e", "1"], pe=False, gz=False),
     "low_mem_db": dict(mix=[((1, 3), 14), ((2, 1), 9)], flags=[], pe=False, gz=False, low_mem=True),
     "two_strains_pe_bgzf": dict(mix=[((4, 1), 9), ((4, 2), 7), ((1, 1), 5)], flags=[], pe=True, gz=True, bgzf=True),
+    # plasmid_mode (StrainScan.py:225-266): the run-time database DB_plasmid is the pre-made PLASMID_DB below
+    # (baseline/run_pipeline.py --plasmid-db stands in for the StrainScan_build.py call); `pmix` = reads drawn
+    # from ITS strains, added to the sample.  -p 2: reference genomes given by -r; -p 1: short contigs of the
+    # strains of the identified multi-strain clusters (load_db_cls, StrainScan.py:47-94), default_cov = 0.
+    "plasmid_mode_2": dict(mix=[((1, 2), 10)], pmix=[((2, 1), 12), ((4, 2), 7)], flags=["-p", "2"], pe=False, gz=False),
+    "plasmid_mode_1": dict(mix=[((1, 1), 9), ((2, 2), 6)], pmix=[((1, 3), 10), ((1, 1), 5)], flags=["-p", "1"], pe=True,
+                           gz=True),
 }
 
 
 # read-sampling seeds, fixed per case (the committed golden reports depend on them)
 CASE_SEEDS = {"extra_region": 1, "low_depth_prob": 2, "same_cluster_two_strains": 3, "singleton_cluster": 4,
-              "two_clusters_pe_gz": 5, "two_clusters_se": 6, "low_mem_db": 7, "two_strains_pe_bgzf": 8}
+              "two_clusters_pe_gz": 5, "two_clusters_se": 6, "low_mem_db": 7, "two_strains_pe_bgzf": 8,
+              "plasmid_mode_2": 9, "plasmid_mode_1": 10}
+
+
+def plasmid_db():
+    """The database the plasmid_mode cases search: same layout, other sequences (shorter replicons)."""
+    return SynthDB(seed=20260331, seg_len=1500, n_seg=12, snp_rate=0.006, prefix="PLS")
 
 
 def make_case_inputs(db, name, out_dir):
     case = CASES[name]
     reads = db.reads(case["mix"], seed=CASE_SEEDS[name])
+    extra = []
+    if "pmix" in case:
+        pdb = plasmid_db()
+        more = pdb.reads(case["pmix"], seed=CASE_SEEDS[name])
+        rng = np.random.default_rng(CASE_SEEDS[name])
+        reads = reads + more
+        reads = [reads[i] for i in rng.permutation(len(reads))]
+        rdir = os.path.join(out_dir, name + "_refs")      # -r: one FASTA per strain (two contigs each)
+        os.makedirs(rdir, exist_ok=True)
+        src = db if case["flags"][1] == "1" else pdb
+        for (c, s_), nm in src.strain_name.items():
+            g = src.strain_genome[(c, s_)]
+            with open(os.path.join(rdir, nm + ".fna"), "wb") as f:
+                h = len(g) // 2
+                f.write(b">" + nm.encode() + b"_ctg1\n" + g[:h] + b"\n>" + nm.encode() + b"_ctg2\n" + g[h:] + b"\n")
+        extra = ["-r", rdir]
     ext = ".fq.gz" if case["gz"] else ".fq"
     bgzf = case.get("bgzf", False)
     if case["pe"]:
         h = len(reads) // 2
         a = write_fastq(os.path.join(out_dir, name + "_1" + ext), reads[:h], bgzf=bgzf)
         b = write_fastq(os.path.join(out_dir, name + "_2" + ext), reads[h:], start=h, bgzf=bgzf)
-        return ["-i", a, "-j", b]
-    return ["-i", write_fastq(os.path.join(out_dir, name + ext), reads, bgzf=bgzf)]
+        return ["-i", a, "-j", b] + extra
+    return ["-i", write_fastq(os.path.join(out_dir, name + ext), reads, bgzf=bgzf)] + extra
+
+
+def write_plasmid_db(base_dir):
+    """The pre-made DB_plasmid of the plasmid_mode cases (run_pipeline.py --plasmid-db)."""
+    return plasmid_db().write(os.path.join(base_dir, "DB_plasmid_src"))
 
 
 def write_dbs(base_dir):

@@ -6,8 +6,11 @@ jellyfish-linux (golden reports in tests/golden/pipeline/, made by tests/golden/
 
 Covers single-end / paired-end + gz, two clusters, two strains in one cluster (ElasticNet path),
 an all-singleton result, -l 2 -b 1 (low depth + probability report), -e 1 (extraRegion_mode), a
-memory-efficient database (Memory_DB -> identify_low_mem, canonical-strand k-mer set) and paired
-blocked-gzip inputs (inflated on the device).
+memory-efficient database (Memory_DB -> identify_low_mem, canonical-strand k-mer set), paired
+blocked-gzip inputs (inflated on the device) and plasmid_mode -p 1 / -p 2 (the run-time StrainScan_build.py
+call is answered with a pre-made DB_plasmid, baseline/run_pipeline.py --plasmid-db).
+A second test repeats every case with the per-node and per-strain reductions (match_node, cal_cov_all,
+get_candidate_arr, get_remainc) replaced by the GPU-backed mirrors as well (--engine b200-full).
 Needs baseline/_ref (git-ignored, travels to the GPU box with gpurun); skipped when it is absent."""
 import os
 import sys
@@ -73,3 +76,16 @@ def test_reports_identical_to_reference(name, db_dir, tmp_path):
         for rel in ref:
             assert got[rel] == ref[rel], "%s/%s not byte-identical\n--- reference (live)\n%s\n--- b200\n%s" % (
                 name, rel, ref[rel].decode(), got[rel].decode())
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not present (python baseline/setup_ref.py)")
+@pytest.mark.parametrize("name", sorted(synth_db.CASES))
+def test_reports_identical_with_gpu_reducers(name, db_dir, tmp_path):
+    """SURVEY 8a rows a5-a7, a11, a12 inside the pipeline: the reference's decisions consume the mirrors'
+    numbers and must write the same reports."""
+    gold = _golden(name)
+    got, log = mpg.run_case("b200-full", db_dir, name, str(tmp_path))
+    assert sorted(got) == sorted(gold), log[-2000:]
+    for rel in gold:
+        assert _same_up_to_float_ulps(got[rel], gold[rel]), "%s/%s differs\n--- reference\n%s\n--- b200-full\n%s" % (
+            name, rel, gold[rel].decode(), got[rel].decode())
