@@ -66,6 +66,9 @@ typedef struct ss_stats {
     uint32_t total_launches;  /* all kernel launches inside this call */
     uint64_t n_table_probes;  /* k-mers that passed the L2-resident prefilter and probed the HBM table
                                  (0 when the set is small enough to need no filter) */
+    uint32_t binned_rounds;   /* rounds of the binned mode (large table + many table probes: survivors are
+                                 grouped by table range first, then probed range after range out of L2) */
+    uint32_t bins;            /* table ranges used by those rounds (0 = direct probing throughout) */
 } ss_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */

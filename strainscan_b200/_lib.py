@@ -28,7 +28,7 @@ class Stats(C.Structure):
                 ("ms_index", C.c_double), ("ms_probe", C.c_double), ("ms_gather", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_total", C.c_double),
                 ("probe_launches", C.c_uint32), ("total_launches", C.c_uint32),
-                ("n_table_probes", C.c_uint64)]
+                ("n_table_probes", C.c_uint64), ("binned_rounds", C.c_uint32), ("bins", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -77,6 +77,12 @@ struct ss_ctx {
     unsigned int *d_gz = nullptr;                // [slot] work counters, [SS_NGZ] smallest failing member (0xFFFFFFFF = none)
     int gz_slot = 0;
     bool gz_used[SS_NGZ] = {};
+    // binned probing (ss_count on resident reads against a large table with many table probes)
+    unsigned long long *d_bin_keys = nullptr;    // pool of bin_pool_chunks chunks of SS_BIN_CHUNK keys
+    uint32_t *d_bin_fill = nullptr;              // keys per chunk
+    uint32_t *d_bin_n = nullptr;                 // [SS_BIN_PMAX] chunks per bin, [SS_BIN_PMAX] overflow flag
+    unsigned long long *h_bin = nullptr;         // pinned: [0..5] the round's scan statistics, then the uint32 d_bin_n mirror
+    uint64_t bin_pool_chunks = 0, bin_pool_want = 0;
     ss_text_source *src = nullptr;               // file ingest: producer threads + pinned chunk pool (lazy)
     cudaEvent_t ev_pend[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -95,6 +101,10 @@ struct ss_kmerset {
     std::vector<uint8_t> flags;
     std::vector<uint64_t> header_ids;
     int has_ones = 0;
+    // what the last resident pass of this set learned from its sample (direct or binned probing, ss_count_device):
+    // a repeated pass over the same read cache (-b 1's second call, a re-run) does not sample again
+    mutable uint64_t seen_reads_id = 0;
+    mutable double seen_rate = 0.0, seen_per_tile = 0.0, seen_kmers_per_tile = 0.0;
     ss_table_view view() const {
         ss_table_view v;
         v.buckets = d_buckets; v.slot_cnt = d_slot_cnt; v.n_buckets = n_buckets;
@@ -115,10 +125,12 @@ struct ss_segment {
     uint32_t *d_tile_line = nullptr;
     bool owns_text = false;
 };
+static uint64_t g_reads_id = 0;
 struct ss_reads {
     ss_ctx *ctx = nullptr;
     std::vector<ss_segment> seg;
     uint64_t len = 0;
+    uint64_t id = ++g_reads_id;     // identity of this cache (never reused)
 };
 
 static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
@@ -149,7 +161,7 @@ extern "C" int ss_init(int device, ss_ctx **out) {
     SS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     SS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    SS_CUDA(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    SS_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));   // [8..13]: one binned round's scan statistics
     SS_CUDA(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
     SS_CUDA(cudaEventCreate(&c->ev_a)); SS_CUDA(cudaEventCreate(&c->ev_b));
     SS_CUDA(cudaEventCreate(&c->ev_c)); SS_CUDA(cudaEventCreate(&c->ev_d));
@@ -191,6 +203,7 @@ extern "C" int ss_shutdown(ss_ctx *c) {
     cudaFree(c->d_gz);
     for (int i = 0; i < SS_NPEND; i++) cudaEventDestroy(c->ev_pend[i]);
     cudaFree(c->d_dense); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
+    cudaFree(c->d_bin_keys); cudaFree(c->d_bin_fill); cudaFree(c->d_bin_n); cudaFreeHost(c->h_bin);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d);
     cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -958,6 +971,81 @@ static void fill_stats(ss_ctx *c, ss_stats *st) {
     st->n_table_probes = c->h_stats[5];   // 0 when the set has no filter: every k-mer probes the table
 }
 
+// ---- binned probing ---------------------------------------------------------------------------
+// A probe of a table that does not fit in L2 costs one random 128-byte DRAM line, which
+// bounds a pass at ~4e10 table probes/s.  The first pass over the sample barely notices (its filter sends
+// 2-3 % of the k-mers to the table), but a cluster's own k-mer set is hit by most k-mers of that cluster's
+// reads.  For those passes the k-mers that pass the filter are first grouped by table range (bins, written
+// as warp-owned 1 KiB chunks) and then probed bin after bin with the range resident in L2.
+// Knobs (environment): SS_BIN=0 never, 1 decide from a sample (default), 2 always when a filter exists;
+// SS_BIN_MIN_RATE (0.08) table probes per k-mer in the sample; SS_BIN_MIN_TABLE_MB (160); SS_BIN_SLICE_MB (3/4 of
+// the L2) table + counter bytes per bin; SS_BIN_POOL_MB (4096) key pool; SS_BIN_FILTER (1).
+static double env_double(const char *name, double dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atof(e) : dflt;
+}
+
+static int ensure_bin_pool(ss_ctx *c) {
+    uint64_t want = (uint64_t)(env_double("SS_BIN_POOL_MB", 4096.0) * 1048576.0);
+    if (c->d_bin_keys && c->bin_pool_want == want) return SS_OK;
+    cudaFree(c->d_bin_keys); cudaFree(c->d_bin_fill); cudaFree(c->d_bin_n); cudaFreeHost(c->h_bin);
+    c->d_bin_keys = nullptr; c->d_bin_fill = nullptr; c->d_bin_n = nullptr; c->h_bin = nullptr;
+    c->bin_pool_want = want;
+    size_t free_b = 0, total_b = 0;
+    SS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (want > free_b / 3) want = free_b / 3;
+    uint64_t chunks = want / (SS_BIN_CHUNK * 8ull);
+    if (chunks > 0x1800000ull) chunks = 0x1800000ull;            // key indices are 32-bit (chunk * 128 + i)
+    if (chunks < SS_BIN_PMAX) return fail(SS_ERR_NOMEM, "binned probing: no room for the key pool");
+    SS_CUDA(cudaMalloc(&c->d_bin_keys, chunks * SS_BIN_CHUNK * 8ull));
+    SS_CUDA(cudaMalloc(&c->d_bin_fill, chunks * sizeof(uint32_t)));
+    SS_CUDA(cudaMalloc(&c->d_bin_n, 2 * SS_BIN_PMAX * sizeof(uint32_t)));
+    SS_CUDA(cudaMallocHost(&c->h_bin, 6 * sizeof(unsigned long long) + 2 * SS_BIN_PMAX * sizeof(uint32_t)));
+    c->bin_pool_chunks = chunks;
+    return SS_OK;
+}
+
+// One round of the binned mode over tiles [lo, hi) of a segment; on a bin overflow (all k-mers alike, e.g.
+// a poly-G tail that is in the set) the round is redone with direct probes -- nothing was counted yet.
+static int binned_round(ss_ctx *c, const ss_kmerset *s, const ss_segment &g, uint32_t lo, uint32_t hi,
+                        const ss_bin_view &bv, bool use_filter, unsigned long long *acc, uint32_t *n_binned) {
+    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
+    static cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+    if (dbg) {
+        if (!ev_t[0]) for (int i = 0; i < 3; i++) cudaEventCreate(&ev_t[i]);
+        cudaEventRecord(ev_t[0], c->stream);
+    }
+    uint32_t *h_n = reinterpret_cast<uint32_t *>(c->h_bin + 6);
+    SS_CUDA(cudaMemsetAsync(c->d_bin_n, 0, 2 * SS_BIN_PMAX * sizeof(uint32_t), c->stream));
+    SS_CUDA(cudaMemsetAsync(c->d_stats + 8, 0, 7 * sizeof(unsigned long long), c->stream));
+    SS_CUDA(ss_launch_bin_scan(g.d_text, g.len, lo, hi, g.d_tile_line, s->view(), bv, use_filter, c->d_stats + 8,
+                               c->d_stats + 4, c->n_sm, c->stream));
+    if (dbg) cudaEventRecord(ev_t[1], c->stream);
+    SS_CUDA(cudaMemcpyAsync(c->h_bin, c->d_stats + 8, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(h_n, c->d_bin_n, 2 * SS_BIN_PMAX * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_n[SS_BIN_PMAX]) {
+        SS_CUDA(ss_launch_probe_range(g.d_text, g.len, lo, hi, g.d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
+                                      c->n_sm, c->stream));
+        return SS_OK;
+    }
+    acc[0] += c->h_bin[0]; acc[3] += c->h_bin[3]; acc[5] += c->h_bin[5];
+    SS_CUDA(ss_launch_bin_probe(bv, h_n, s->view(), c->d_stats, c->d_stats + 8, c->n_sm, c->stream));
+    if (dbg) {
+        cudaEventRecord(ev_t[2], c->stream);
+        cudaEventSynchronize(ev_t[2]);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ev_t[0], ev_t[1]);
+        cudaEventElapsedTime(&b, ev_t[1], ev_t[2]);
+        uint64_t chunks = 0;
+        for (uint32_t p = 0; p < bv.P; p++) chunks += h_n[p];
+        fprintf(stderr, "[ss] binned round tiles %u..%u: scan %.3f ms, probe (+sync) %.3f ms, %llu chunks, %u bins, filter %d\n",
+                lo, hi, a, b, (unsigned long long)chunks, bv.P, (int)use_filter);
+    }
+    (*n_binned)++;
+    return SS_OK;
+}
+
 extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *dev_counts, ss_stats *st) {
     if (!c || !s || !r || !dev_counts) return fail(SS_ERR_ARG, "ss_count_device: NULL argument");
     if (s->ctx != c || r->ctx != c) return fail(SS_ERR_ARG, "ss_count_device: handle belongs to another context");
@@ -966,18 +1054,101 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
     int rc = reset_pass(c, s);
     if (rc) return rc;
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
-    uint32_t launches = 0;
-    for (const ss_segment &g : r->seg) {
+    uint32_t launches = 0, n_binned = 0;
+    unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};     // scan statistics of the binned rounds (summed on the host)
+
+    // ---- direct or binned?  Decided from the first tiles of the pass.
+    const int bin_mode = (int)env_double("SS_BIN", 1.0);
+    const uint64_t table_bytes = s->n_buckets * (sizeof(ss_bucket) + 4 * sizeof(uint32_t));
+    uint64_t total_tiles = 0;
+    for (const ss_segment &g : r->seg) total_tiles += g.n_tiles;
+    const bool force = bin_mode == 2;                   // tests: any size, SS_BIN_ROUND_TILES tiles per round
+    const uint32_t sample_tiles = force ? 64 : 16384;   // 16 MB of text
+    ss_bin_view bv = {};
+    uint32_t round_tiles = 0;
+    bool use_filter = true;
+    size_t first_seg = 0;
+    uint32_t first_lo = 0;
+    if (bin_mode > 0 && s->d_filter && total_tiles > 0 &&
+        (force || (total_tiles >= 8ull * sample_tiles &&
+                   table_bytes >= (uint64_t)(env_double("SS_BIN_MIN_TABLE_MB", 160.0) * 1048576.0)))) {
+        while (r->seg[first_seg].n_tiles == 0) first_seg++;
+        const ss_segment &g = r->seg[first_seg];
+        double rate, probes_per_tile, kmers_per_tile;
+        if (!force && s->seen_reads_id == r->id) {        // same set, same reads: the sample was taken before
+            rate = s->seen_rate; probes_per_tile = s->seen_per_tile; kmers_per_tile = s->seen_kmers_per_tile;
+        } else {
+            const uint32_t n_sample = g.n_tiles < sample_tiles ? g.n_tiles : sample_tiles;
+            SS_CUDA(ss_launch_probe_range(g.d_text, g.len, 0, n_sample, g.d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
+                                          c->n_sm, c->stream));
+            SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            SS_CUDA(cudaEventRecord(c->ev_d, c->stream));
+            // the GPU goes on with the next tiles (direct) while the host waits for the sample's numbers
+            first_lo = force ? n_sample : (g.n_tiles < 4 * sample_tiles ? g.n_tiles : 4 * sample_tiles);
+            SS_CUDA(ss_launch_probe_range(g.d_text, g.len, n_sample, first_lo, g.d_tile_line, s->view(), c->d_stats,
+                                          c->d_stats + 4, c->n_sm, c->stream));
+            launches += first_lo > n_sample ? 2 : 1;
+            SS_CUDA(cudaEventSynchronize(c->ev_d));
+            rate = c->h_stats[0] ? (double)c->h_stats[5] / (double)c->h_stats[0] : 0.0;
+            probes_per_tile = (double)c->h_stats[5] / (double)n_sample;
+            kmers_per_tile = (double)c->h_stats[0] / (double)n_sample;
+            s->seen_reads_id = r->id; s->seen_rate = rate; s->seen_per_tile = probes_per_tile; s->seen_kmers_per_tile = kmers_per_tile;
+        }
+        // SS_BIN_FILTER=0: bin every k-mer without asking the filter (one L2 load less per k-mer, more keys to bin;
+        // measured equal at 80 % hits, so the filter stays on by default)
+        use_filter = (int)env_double("SS_BIN_FILTER", 1.0) != 0;
+        const double per_tile = use_filter ? probes_per_tile : kmers_per_tile;               // keys to bin per tile
+        if ((force || rate >= env_double("SS_BIN_MIN_RATE", 0.08)) && ensure_bin_pool(c) == SS_OK) {
+            // table + counter bytes per bin: 3/4 of the L2 (measured on B200, 545 MB table at 80 % hits: 8 bins of
+            // 89 MB 20.4 ms, 16 bins 21.4 ms, 32 bins 26.4 ms -- every (warp, bin) pair is an open write stream of the
+            // scan, and fewer streams cost the scan less than the larger range costs the probes)
+            const uint64_t slice = (uint64_t)(env_double("SS_BIN_SLICE_MB", 0.75 * c->prop.l2CacheSize / 1048576.0) * 1048576.0);
+            uint32_t P = 2;
+            while (P < SS_BIN_PMAX && table_bytes / P > slice) P *= 2;
+            bv.keys = c->d_bin_keys; bv.fill = c->d_bin_fill; bv.n_chunks = c->d_bin_n;
+            bv.P = P; bv.cap = (uint32_t)(c->bin_pool_chunks / P);
+            bv.shift = 32; for (uint32_t q = P; q > 1; q >>= 1) bv.shift--;
+            // every warp of the scan kernel may hold one partly filled chunk per bin
+            const uint64_t warps = (uint64_t)c->n_sm * ss_bin_scan_ctas_per_sm() * SS_CTA_WARPS;
+            if (force) {
+                round_tiles = (uint32_t)env_double("SS_BIN_ROUND_TILES", 1024.0);
+                if (round_tiles < 1) round_tiles = 1;
+            } else if (bv.cap > warps + 64) {
+                const double usable = (double)(bv.cap - warps) * SS_BIN_CHUNK * P / 1.3;   // margin: sample error + bin skew
+                double rt = usable / (per_tile > 1.0 ? per_tile : 1.0);
+                round_tiles = rt > 4e9 ? 0xFFFFFFF0u : (uint32_t)rt;
+                if (round_tiles < 4 * sample_tiles) round_tiles = 0;                       // pool too small to pay off
+            }
+        }
+    }
+
+    for (size_t gi = 0; gi < r->seg.size(); gi++) {
+        const ss_segment &g = r->seg[gi];
         if (!g.n_tiles) continue;
-        SS_CUDA(ss_launch_probe(g.d_text, g.len, g.n_tiles, g.d_tile_line, s->view(), c->d_stats, c->d_stats + 4,
-                                c->n_sm, c->stream));
-        launches++;
+        uint32_t lo = (first_lo && gi == first_seg) ? first_lo : 0;
+        if (!round_tiles) {
+            SS_CUDA(ss_launch_probe_range(g.d_text, g.len, lo, g.n_tiles, g.d_tile_line, s->view(), c->d_stats,
+                                          c->d_stats + 4, c->n_sm, c->stream));
+            launches++;
+            continue;
+        }
+        // equal rounds, so that the last one is not a sliver
+        const uint32_t n_rounds = (g.n_tiles - lo + round_tiles - 1) / round_tiles;
+        const uint32_t step = n_rounds ? (g.n_tiles - lo + n_rounds - 1) / n_rounds : 0;
+        while (lo < g.n_tiles) {
+            uint32_t hi = g.n_tiles - lo > step ? lo + step : g.n_tiles;
+            rc = binned_round(c, s, g, lo, hi, bv, use_filter, acc, &n_binned);
+            if (rc) return rc;
+            launches += 2;
+            lo = hi;
+        }
     }
     SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
     SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, dev_counts, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
     SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
+    c->h_stats[0] += acc[0]; c->h_stats[3] += acc[3]; c->h_stats[5] += acc[5];
     rc = check_format_result(c, "ss_count");
     if (rc) return rc;
     if (st) {
@@ -989,6 +1160,8 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
         cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
         st->probe_launches = launches;
         st->total_launches = st->probe_launches + (s->n_records ? 1 : 0);
+        st->binned_rounds = n_binned;
+        st->bins = n_binned ? bv.P : 0;
         st->ms_total = now_ms() - t0;
     }
     return SS_OK;

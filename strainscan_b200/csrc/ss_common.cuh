@@ -76,6 +76,23 @@ struct ss_table_view {
     uint32_t n_filter_words;
 };
 
+// ---- binned probing (large table + many table probes) ------------------------------------------
+// The k-mers that pass the filter are not probed where they are found: they are appended to one of P
+// bins = contiguous ranges of the table (bin = top bits of the bucket hash), in chunks of
+// SS_BIN_CHUNK keys that a warp owns until they are full, and a second kernel probes bin after bin, so
+// that the table range (and its counters) a bin touches stays in L2 instead of costing one random
+// 128-byte DRAM line per probe.
+#define SS_BIN_CHUNK 128u            // keys per chunk (1 KiB, eight full 128-byte lines)
+#define SS_BIN_PMAX  64u
+struct ss_bin_view {
+    unsigned long long *keys;        // P * cap chunks of SS_BIN_CHUNK keys
+    uint32_t *fill;                  // keys in each chunk
+    uint32_t *n_chunks;              // [P] chunks handed out per bin; [SS_BIN_PMAX] = overflow flag
+    uint32_t cap;                    // chunks per bin
+    uint32_t shift;                  // bin = hash_hi >> shift  (P = 2^(32 - shift), P >= 2)
+    uint32_t P;
+};
+
 void ss_set_error(const std::string &msg);
 int ss_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 #define SS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } while (0)

@@ -13,6 +13,16 @@ cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *til
 cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *tile_line,
                             const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
                             cudaStream_t st);
+cudaError_t ss_launch_probe_range(const uint8_t *text, uint64_t text_len, uint32_t tile_lo, uint32_t tile_hi,
+                                  const uint32_t *sub_line, const ss_table_view &tv, unsigned long long *stats,
+                                  unsigned long long *err, int n_sm, cudaStream_t st);
+int ss_bin_scan_ctas_per_sm();
+cudaError_t ss_launch_bin_scan(const uint8_t *text, uint64_t text_len, uint32_t tile_lo, uint32_t tile_hi,
+                               const uint32_t *sub_line, const ss_table_view &tv, const ss_bin_view &bv, bool use_filter,
+                               unsigned long long *stats, unsigned long long *err, int n_sm, cudaStream_t st);
+cudaError_t ss_launch_bin_probe(const ss_bin_view &bv, const uint32_t *n_chunks, const ss_table_view &tv,
+                                unsigned long long *stats, const unsigned long long *scan_stats, int n_sm,
+                                cudaStream_t st);
 cudaError_t ss_launch_insert(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *slots,
                              uint64_t n_buckets, uint32_t *slot_of, uint32_t *last_ord,
                              unsigned long long *n_distinct, cudaStream_t st);

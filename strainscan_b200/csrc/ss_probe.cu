@@ -243,11 +243,45 @@ __device__ __forceinline__ void table_probe(const ss_table_view &tv, uint64_t km
     }
 }
 
-template <bool FILTER, bool K32, int UNROLL, int MINCTAS>
+// binned mode: append one surviving k-mer per active lane to its bin.  Every warp owns one open chunk per bin:
+// b_cnt[p] = keys already in it (SS_BIN_CHUNK = full / none open yet), b_base[p] = pool index of its first key.
+// Common case: one shared-memory atomicAdd hands out the place and the lane stores its key.  The lanes that find
+// their chunk full take a new one from the bin's pool (one global atomicAdd per SS_BIN_CHUNK keys).
+__device__ __forceinline__ void bin_emit(uint32_t *b_cnt, uint32_t *b_base, const ss_bin_view &bv, bool active,
+                                         uint64_t km, uint32_t hh, uint32_t lane, uint32_t lt_mask) {
+    uint32_t p = 0, old = 0;
+    if (active) {
+        p = hh >> bv.shift;
+        old = atomicAdd(b_cnt + p, 1u);
+        if (old < SS_BIN_CHUNK) bv.keys[b_base[p] + old] = km;
+    }
+    __syncwarp();
+    uint32_t ov = __ballot_sync(0xFFFFFFFFu, active && old >= SS_BIN_CHUNK);
+    while (ov) {                                            // rare: once per SS_BIN_CHUNK keys of a bin
+        const int l = __ffs(ov) - 1;
+        const uint32_t pb = __shfl_sync(0xFFFFFFFFu, p, l);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, active && old >= SS_BIN_CHUNK && p == pb);
+        if ((int)lane == l) {
+            uint32_t c = atomicAdd(bv.n_chunks + pb, 1u);
+            if (c >= bv.cap) { c = bv.cap - 1u; bv.n_chunks[SS_BIN_PMAX] = 1u; }   // flagged: the host redoes the round
+            c += pb * bv.cap;
+            bv.fill[c] = SS_BIN_CHUNK;                      // closed chunks are full; my last one is fixed up at the end
+            b_base[pb] = c * SS_BIN_CHUNK;
+            b_cnt[pb] = __popc(m);
+        }
+        __syncwarp();
+        if ((m >> lane) & 1u) bv.keys[b_base[pb] + __popc(m & lt_mask)] = km;
+        ov &= ~m;
+    }
+    __syncwarp();
+}
+
+template <bool FILTER, bool K32, int UNROLL, int MINCTAS, bool BIN>
 __global__ void __launch_bounds__(SS_CTA_THREADS, MINCTAS)
-ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_units,
-                const uint32_t *__restrict__ sub_line, ss_table_view tv,
+ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t unit_lo, uint32_t n_units,
+                const uint32_t *__restrict__ sub_line, ss_table_view tv, ss_bin_view bv,
                 unsigned long long *__restrict__ stats, unsigned long long *__restrict__ err) {
+    __shared__ uint32_t s_bcnt[BIN ? SS_CTA_WARPS * SS_BIN_PMAX : 1], s_bbase[BIN ? SS_CTA_WARPS * SS_BIN_PMAX : 1];
     static_assert(32 + 32 * UNROLL <= SS_QCAP, "survivor queue too small for this UNROLL");
     __shared__ ss_warp_smem s_warp[SS_CTA_WARPS];
     __shared__ uint64_t s_pat[FILTER ? SS_NPAT : 1];     // filter bit patterns (4 bits of a 64-bit word)
@@ -257,7 +291,7 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
     }
 
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const uint64_t gw = (uint64_t)blockIdx.x * SS_CTA_WARPS + wid;      // my global warp id
+    const uint64_t gw = (uint64_t)blockIdx.x * SS_CTA_WARPS + wid + unit_lo;   // my first unit
     const uint64_t nw = (uint64_t)gridDim.x * SS_CTA_WARPS;            // unit stride
     constexpr uint32_t kBytes = SS_TILE + SS_HALO;
     ss_warp_smem &ws = s_warp[wid];
@@ -283,9 +317,14 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
     if (lane < 4) ws.codes[2 * SS_WRUNS + lane] = 0;
     if (lane < 2) ws.valid[SS_WRUNS + lane] = 0;
     if (lane == 0) ws.qn = 0;
+    uint32_t *b_cnt = s_bcnt + (BIN ? wid * SS_BIN_PMAX : 0), *b_base = s_bbase + (BIN ? wid * SS_BIN_PMAX : 0);
+    if (BIN) {
+        b_cnt[lane] = SS_BIN_CHUNK; b_cnt[lane + 32] = SS_BIN_CHUNK;          // no chunk open yet
+        b_base[lane] = 0xFFFFFFFFu; b_base[lane + 32] = 0xFFFFFFFFu;
+    }
     __syncwarp();
 
-    uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0;
+    uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0, n_ones = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t half = lane >> 4;                    // which 32-bit word my window starts in
     const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside it
@@ -355,7 +394,10 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                 k1[u] = __funnelshift_r(w1, w2, fsh) & khi_mask;
                 if (K32) {
                     if (ok[u] && (k0[u] & k1[u]) == 0xFFFFFFFFu) {   // poly-T 32-mer: lives outside the table
-                        if (tv.has_ones) { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
+                        if (tv.has_ones) {
+                            if (BIN) n_ones++;          // applied by the bin-probe kernel once the round stands
+                            else { red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, 1u); n_hits++; }
+                        }
                         ok[u] = false;
                     }
                 }
@@ -375,7 +417,13 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                     pass[u] = ok[u] && (fw[u] & m) == m;
                     any |= pass[u];
                 }
-                if (any) {                              // rare per lane: queue survivors for an exact table probe
+                if (BIN) {                              // survivors are the rule here: no queue, straight to the bins
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        n_table += pass[u];
+                        bin_emit(b_cnt, b_base, bv, pass[u], (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), hh[u], lane, lt_mask);
+                    }
+                } else if (any) {                       // rare per lane: queue survivors for an exact table probe
 #pragma unroll
                     for (int u = 0; u < UNROLL; u++) {
                         if (pass[u]) {
@@ -385,7 +433,7 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                     }
                 }
                 __syncwarp();
-                uint32_t qn = ws.qn;                    // <= 31 + 32 * UNROLL
+                uint32_t qn = BIN ? 0u : ws.qn;         // <= 31 + 32 * UNROLL
                 while (qn >= 32u) {                     // probe the table 32 survivors at a time
                     qn -= 32u;
                     n_table++;
@@ -393,6 +441,12 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
                     __syncwarp();
                     if (lane == 0) ws.qn = qn;
                     __syncwarp();
+                }
+            } else if (BIN) {                           // most k-mers are in the set: the filter is skipped
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    n_table += ok[u];
+                    bin_emit(b_cnt, b_base, bv, ok[u], (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), hh[u], lane, lt_mask);
                 }
             } else {
 #pragma unroll
@@ -404,8 +458,11 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
         }
         __syncwarp();   // my codes/valid are rewritten by my next unit's phase 1
     }
-    if (FILTER) {       // drain the queue
-        __syncwarp();
+    __syncwarp();
+    if (BIN) {
+        for (uint32_t p = lane; p < bv.P; p += 32u)       // my open chunks are partly filled
+            if (b_base[p] != 0xFFFFFFFFu) bv.fill[b_base[p] / SS_BIN_CHUNK] = b_cnt[p];
+    } else if (FILTER) {       // drain the queue
         if (lane < ws.qn) {
             n_table++;
             table_probe(tv, ws.q_key[lane], n_hits, n_second);
@@ -420,6 +477,93 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t n_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
         if (lane == 0 && x) atomicAdd(stats + (i < 4 ? i : 5), x);
+    }
+    if (BIN && K32) {
+        unsigned long long x = n_ones;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0 && x) atomicAdd(stats + 6, x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3c: probe the binned k-mers, bin after bin (CTAs are numbered bin-major, so the CTAs in flight work on
+// one or two neighbouring bins and the table range + counters they touch stay in L2).  One warp per
+// chunk: 4 keys per lane, their 4 sector loads in flight together.
+// ---------------------------------------------------------------------------------------------
+struct ss_bin_sched { uint32_t start[SS_BIN_PMAX + 1]; };   // first chunk number of each bin (prefix sums), host-built
+
+__device__ __forceinline__ unsigned long long ld_key_stream(const unsigned long long *p, uint64_t policy) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// Persistent: warp w takes chunk numbers w, w + W, w + 2W, ... of the bin-major numbering, so all warps in
+// flight work on the same one or two bins.  The keys of the next chunk are requested before the current one
+// is probed.
+__global__ void __launch_bounds__(SS_CTA_THREADS)
+ss_bin_probe_kernel(ss_bin_view bv, ss_bin_sched sched, ss_table_view tv, unsigned long long *__restrict__ stats,
+                    const unsigned long long *__restrict__ scan_stats) {
+    constexpr int NK = SS_BIN_CHUNK / 32;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && tv.has_ones && scan_stats[6]) {   // the scan's poly-T 32-mers (side slot)
+        red_add_u32(tv.slot_cnt + 4 * tv.n_buckets, (uint32_t)scan_stats[6]);
+        atomicAdd(stats + 1, scan_stats[6]);
+    }
+    const uint32_t total = sched.start[SS_BIN_PMAX];
+    const uint32_t W = gridDim.x * SS_CTA_WARPS;
+    uint32_t n_hits = 0, n_second = 0;
+    uint64_t pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    uint32_t p = 0, n_next = 0;
+    unsigned long long kn[NK];
+    auto fetch = [&](uint32_t w) {          // request chunk number w's keys (bin p only moves forward)
+        while (sched.start[p + 1] <= w) p++;
+        const uint32_t c = p * bv.cap + (w - sched.start[p]);
+        n_next = bv.fill[c];
+        const unsigned long long *kp = bv.keys + (uint64_t)c * SS_BIN_CHUNK;
+#pragma unroll
+        for (int j = 0; j < NK; j++) kn[j] = (j * 32u + lane < n_next) ? ld_key_stream(kp + j * 32 + lane, pol_stream) : 0ull;
+    };
+    uint32_t w = blockIdx.x * SS_CTA_WARPS + wid;
+    if (w < total) fetch(w);
+    for (; w < total; w += W) {
+        unsigned long long km[NK], a[NK][4];
+        uint64_t b[NK];
+        const uint32_t n = n_next;
+#pragma unroll
+        for (int j = 0; j < NK; j++) km[j] = kn[j];
+#pragma unroll
+        for (int j = 0; j < NK; j++) {
+            uint32_t hh, hl;
+            ss_hash2((uint32_t)km[j], (uint32_t)(km[j] >> 32), hh, hl);
+            b[j] = __umulhi(hh, (uint32_t)tv.n_buckets);
+            if (j * 32u + lane < n) ld_bucket(tv.buckets + b[j], a[j][0], a[j][1], a[j][2], a[j][3]);
+        }
+        if (w + W < total) fetch(w + W);
+#pragma unroll
+        for (int j = 0; j < NK; j++) {
+            if (j * 32u + lane >= n) continue;
+            unsigned long long a0 = a[j][0], a1 = a[j][1], a2 = a[j][2], a3 = a[j][3];
+            uint64_t bb = b[j];
+            while (true) {
+                int f = (a0 == km[j]) ? 0 : (a1 == km[j]) ? 1 : (a2 == km[j]) ? 2 : (a3 == km[j]) ? 3 : -1;
+                if (f >= 0) { red_add_u32(tv.slot_cnt + 4 * bb + f, 1u); n_hits++; break; }
+                if (a3 == SS_EMPTY || a2 == SS_EMPTY || a1 == SS_EMPTY || a0 == SS_EMPTY) break;
+                bb = (bb + 1 == tv.n_buckets) ? 0 : bb + 1;
+                n_second++;
+                ld_bucket(tv.buckets + bb, a0, a1, a2, a3);
+            }
+        }
+    }
+    unsigned long long st[2] = {n_hits, n_second};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        unsigned long long x = st[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+        if (lane == 0 && x) atomicAdd(stats + 1 + i, x);
     }
 }
 
@@ -597,7 +741,8 @@ __global__ void __launch_bounds__(256) ss_random_gather_kernel(const ss_bucket *
 // ---------------------------------------------------------------------------------------------
 static int g_probe_ctas_per_sm = 0;
 
-#define SS_KERNEL(F, K) ss_probe_kernel<F, K, SS_PROBE_UNROLL, SS_PROBE_MIN_CTAS>
+#define SS_KERNEL(F, K) ss_probe_kernel<F, K, SS_PROBE_UNROLL, SS_PROBE_MIN_CTAS, false>
+#define SS_KERNEL_BIN(F, K) ss_probe_kernel<F, K, SS_PROBE_UNROLL, SS_PROBE_MIN_CTAS, true>
 
 int ss_probe_ctas_per_sm() {
     if (g_probe_ctas_per_sm == 0) {
@@ -633,19 +778,84 @@ cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *sub
     return cudaGetLastError();
 }
 
+cudaError_t ss_launch_probe_range(const uint8_t *text, uint64_t text_len, uint32_t tile_lo, uint32_t tile_hi,
+                                  const uint32_t *sub_line, const ss_table_view &tv, unsigned long long *stats,
+                                  unsigned long long *err, int n_sm, cudaStream_t st) {
+    if (tile_hi <= tile_lo) return cudaSuccess;
+    uint32_t n = tile_hi - tile_lo;
+    uint32_t grid = min((n + SS_CTA_WARPS - 1) / SS_CTA_WARPS, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
+    const bool k32 = tv.k == 32;
+    ss_bin_view nb = {};
+    if (tv.filter) {
+        if (k32) SS_KERNEL(true, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, nb, stats, err);
+        else SS_KERNEL(true, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, nb, stats, err);
+    } else {
+        if (k32) SS_KERNEL(false, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, nb, stats, err);
+        else SS_KERNEL(false, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, nb, stats, err);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *sub_line,
                             const ss_table_view &tv, unsigned long long *stats, unsigned long long *err, int n_sm,
                             cudaStream_t st) {
-    if (n_tiles == 0) return cudaSuccess;
-    uint32_t grid = min((n_tiles + SS_CTA_WARPS - 1) / SS_CTA_WARPS, (uint32_t)(n_sm * ss_probe_ctas_per_sm()));
-    const bool k32 = tv.k == 32;
-    if (tv.filter) {
-        if (k32) SS_KERNEL(true, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
-        else SS_KERNEL(true, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
-    } else {
-        if (k32) SS_KERNEL(false, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
-        else SS_KERNEL(false, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, n_tiles, sub_line, tv, stats, err);
+    return ss_launch_probe_range(text, text_len, 0, n_tiles, sub_line, tv, stats, err, n_sm, st);
+}
+
+// binned mode, phase 1: scan tiles [tile_lo, tile_hi) and append the k-mers that pass the filter to the bins
+int ss_bin_scan_ctas_per_sm() {
+    static int n_cached = 0;
+    if (n_cached == 0) {
+        int best = 1 << 30;
+        const void *fns[4] = {(const void *)SS_KERNEL_BIN(true, false), (const void *)SS_KERNEL_BIN(true, true),
+                              (const void *)SS_KERNEL_BIN(false, false), (const void *)SS_KERNEL_BIN(false, true)};
+        for (int i = 0; i < 4; i++) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[i], SS_CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+            best = n < best ? n : best;
+        }
+        n_cached = best;
     }
+    return n_cached;
+}
+
+cudaError_t ss_launch_bin_scan(const uint8_t *text, uint64_t text_len, uint32_t tile_lo, uint32_t tile_hi,
+                               const uint32_t *sub_line, const ss_table_view &tv, const ss_bin_view &bv, bool use_filter,
+                               unsigned long long *stats, unsigned long long *err, int n_sm, cudaStream_t st) {
+    if (tile_hi <= tile_lo) return cudaSuccess;
+    uint32_t n = tile_hi - tile_lo;
+    uint32_t grid = min((n + SS_CTA_WARPS - 1) / SS_CTA_WARPS, (uint32_t)(n_sm * ss_bin_scan_ctas_per_sm()));
+    const bool k32 = tv.k == 32;
+    if (use_filter && tv.filter) {
+        if (k32) SS_KERNEL_BIN(true, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, bv, stats, err);
+        else SS_KERNEL_BIN(true, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, bv, stats, err);
+    } else {
+        if (k32) SS_KERNEL_BIN(false, true)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, bv, stats, err);
+        else SS_KERNEL_BIN(false, false)<<<grid, SS_CTA_THREADS, 0, st>>>(text, text_len, tile_lo, tile_hi, sub_line, tv, bv, stats, err);
+    }
+    return cudaGetLastError();
+}
+
+// binned mode, phase 2: n_chunks[p] = chunks handed out in bin p (host copy, no bin overflowed)
+cudaError_t ss_launch_bin_probe(const ss_bin_view &bv, const uint32_t *n_chunks, const ss_table_view &tv,
+                                unsigned long long *stats, const unsigned long long *scan_stats, int n_sm,
+                                cudaStream_t st) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ss_bin_probe_kernel, SS_CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+        ctas_per_sm = n;
+    }
+    ss_bin_sched sched;
+    uint32_t total = 0;
+    for (uint32_t p = 0; p < SS_BIN_PMAX; p++) {
+        sched.start[p] = total;
+        if (p < bv.P) total += n_chunks[p];
+    }
+    sched.start[SS_BIN_PMAX] = total;
+    if (total == 0 && !tv.has_ones) return cudaSuccess;
+    uint32_t grid = min((total + SS_CTA_WARPS - 1) / SS_CTA_WARPS, (uint32_t)(n_sm * ctas_per_sm));
+    ss_bin_probe_kernel<<<grid ? grid : 1, SS_CTA_THREADS, 0, st>>>(bv, sched, tv, stats, scan_stats);
     return cudaGetLastError();
 }
 

@@ -449,3 +449,42 @@ def test_small_and_odd_k(eng, k):
     assert st.n_kmers == adapters.count_windows([fq], k)
     got2, _ = eng.count_host(ks, [fq])
     assert np.array_equal(got2, got)
+
+
+@pytest.mark.parametrize("k,slice_mb,pool_mb,round_tiles,bin_filter", [
+    (31, "0.02", "64", "300", "1"), (21, "0.3", "256", "1500", "0"), (32, "0.02", "0.0625", "300", "1"),
+    (31, "0.05", "2", "97", "0"), (32, "0.1", "64", "700", "0")])
+def test_binned_mode_vs_oracle(eng, k, slice_mb, pool_mb, round_tiles, bin_filter, monkeypatch):
+    """Binned probing (large table + many table probes: survivors of the filter are grouped by table range, then
+    probed range after range) forced on at test size: many bins, several rounds per segment, a pool so small
+    that bins overflow (the round is then redone with direct probes), with and without the filter in front of
+    the bins, against the oracle and the direct mode."""
+    monkeypatch.setenv("SS_FILTER", "1")
+    rng = np.random.default_rng(4242 + k)
+    G = util.rand_genome(rng, 300_000)
+    fa = util.make_db(rng, G, k, 60_000, both_strands=True, lower_frac=0.02, junk=40)
+    fq1 = util.make_reads(rng, G, 12000, 150, var_len=False, lower_frac=0.05, offtarget=0.1)
+    fq2 = util.make_reads(rng, G, 4000, 100, var_len=True)
+    poly = b"".join(b"@p%d\n%s\n+\n%s\n" % (i, b"T" * 150, b"I" * 150) for i in range(300))   # one bin gets everything
+    fa += b">1\n" + b"T" * k + b"\n"
+    ks = eng.kmerset_from_text(fa, k)
+    d = adapters.count_dense(fa, k, [fq1, poly, fq2])
+    reads = eng.reads_from_host([fq1, poly, fq2])
+    monkeypatch.setenv("SS_BIN", "0")
+    direct, st0 = eng.count(ks, reads)
+    assert st0.binned_rounds == 0 and np.array_equal(direct.astype(np.uint64), d.cnt)
+    monkeypatch.setenv("SS_BIN", "2")
+    monkeypatch.setenv("SS_BIN_SLICE_MB", slice_mb)
+    monkeypatch.setenv("SS_BIN_POOL_MB", pool_mb)
+    monkeypatch.setenv("SS_BIN_ROUND_TILES", round_tiles)
+    monkeypatch.setenv("SS_BIN_FILTER", bin_filter)
+    got, st = eng.count(ks, reads)
+    assert np.array_equal(got.astype(np.uint64), d.cnt)
+    assert (st.n_kmers, st.n_reads, st.n_hits) == (st0.n_kmers, st0.n_reads, st0.n_hits)
+    if float(pool_mb) >= 64:                   # no overflow: every round after the sample was binned
+        assert st.binned_rounds >= 2 and st.bins >= 2
+        if bin_filter == "1":
+            assert st.n_table_probes == st0.n_table_probes
+    # idempotent: a second pass over the same cache gives the same vector
+    again, _ = eng.count(ks, reads)
+    assert np.array_equal(again, got)

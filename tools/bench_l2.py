@@ -59,7 +59,8 @@ def main():
             "records": int(kset.n_records), "table_mb": kset.table_bytes / 1e6, "offtarget": off,
             "filter": bool(st.n_table_probes), "hit_rate": h, "table_probe_rate": st.n_table_probes / st.n_kmers,
             "probe_ms": t, "kmers_per_s": st.n_kmers / (t * 1e-3), "algorithmic_gbps": st.n_kmers * bpk / (t * 1e-3) / 1e9,
-            "hbm_sector_probes_per_s": (st.n_table_probes or st.n_kmers) / (t * 1e-3)})
+            "hbm_sector_probes_per_s": (st.n_table_probes or st.n_kmers) / (t * 1e-3),
+            "binned_rounds": st.binned_rounds, "bins": st.bins, "probe_launches": st.probe_launches})
         del reads, text, counts, kset
         torch.cuda.empty_cache()
     out["random_sector_gather_gbps_1GiB"] = rand
