@@ -248,7 +248,7 @@ def run_reference_arm(args, rank, world):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -256,7 +256,25 @@ def run_reference_arm(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else that lands on fd 1 (NCCL's version banner,
+    library chatter) was re-pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -430,7 +448,22 @@ def main():
                "d2h_bytes_per_step": 4 * kset.n_records, "ms_per_step": e_ms,
                "reads_per_s": tot_reads / (e_ms * 1e-3), "wall_ms_per_step": float(te[1]) / args.steps,
                "api": "ss_count_host (C ABI) from pinned host FASTQ text, 32 MiB chunks over 4 device slots, copy/compute overlapped; bytes are per rank"}
-        del host_text
+        # what the platform gives a bare copy of the same pinned buffer, all ranks copying at once: e2e is bound by it
+        dst = torch.empty(min(n_bytes, 1 << 30), dtype=torch.uint8, device=dev)
+        dst.copy_(host_text[:dst.numel()], non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        ev0.record()
+        for _ in range(3):
+            dst.copy_(host_text[:dst.numel()], non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        tc = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        e2e["bare_h2d_gbps_per_rank"] = 3 * dst.numel() / (float(tc[0]) * 1e-3) / 1e9
+        e2e["h2d_gbps_per_rank"] = n_bytes / (e_ms * 1e-3) / 1e9
+        del host_text, dst
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------
     base = None
@@ -459,7 +492,7 @@ def main():
             "gpu_launches": launches, "clocks": sampler.summary(),
             "device": info["name"], "n_sm": info["n_sm"],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
