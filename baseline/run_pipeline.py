@@ -22,8 +22,9 @@
 --engine b200-full : as b200, plus the SURVEY 8f mirrors in place of the reference's per-node and per-strain
                      reductions: match_node of identify / identify_low_mem / identify_low_depth (a5, a7) ->
                      identify_shim.match_node[_low_depth] (array gathers of the dense GPU vector), and
-                     cal_cov_all / get_candidate_arr / get_remainc of identify_strains_L2_Enet_Pscan_new_sp
-                     (a11, a12) -> l2_shim (ss_strain_reduce on the GPU).  Decisions stay the reference's.
+                     cal_cov_all / get_candidate_arr / get_remainc / optimize_dominat_y / get_avg_depth of
+                     identify_strains_L2_Enet_Pscan_new_sp (a11, a12) -> l2_shim (ss_strain_reduce on the GPU,
+                     order statistics on the sparse columns).  Decisions stay the reference's.
 Both engines seed numpy / random identically (identify.py:214 draws unseeded Poisson samples).
 Reports (final_report.txt, C*/StrainVote.report, strain_prob.txt) must come out byte-identical.
 """
@@ -87,6 +88,8 @@ def install_b200_reducers():
         return l2_shim.get_remainc(dominat, used_kmer, pXt_tem.T, py, strain_remainc)
 
     ids.cal_cov_all, ids.get_candidate_arr, ids.get_remainc = cal_cov_all, get_candidate_arr, get_remainc
+    ids.optimize_dominat_y = l2_shim.optimize_dominat_y           # identify_strains...:136-175, same signature
+    ids.get_avg_depth = l2_shim.get_avg_depth                     # identify_strains...:109-119
 
 
 def install_plasmid_db(src_dir):

@@ -283,3 +283,52 @@ def candidate_counts(X_dense, y):
         t[t > 1] = 1
         out.append(int(t.sum()))
     return out
+
+
+def _percentile_nearest(a, q):
+    """np.percentile(a, q, interpolation='nearest') as the reference calls it (the keyword is `method` in NumPy >= 1.22)."""
+    return np.percentile(a, q, method="nearest")
+
+
+def optimize_dominat_y(X_dense, y):
+    """identify_strains_L2_Enet_Pscan_new_sp.py:136-175, dense as the reference: per strain the sum of the y values of
+    its rows that lie inside the 5th..95th percentile (nearest) of its non-zero values; the first maximum wins."""
+    res = []
+    for c in range(X_dense.shape[1]):
+        ix = X_dense[:, c].astype(np.int64)
+        da = ix * y
+        da_noz = da[da != 0]
+        if np.sum(da_noz) == 0 or len(da_noz) < 1:
+            res.append(0)
+        else:
+            f25 = _percentile_nearest(da_noz, 5)
+            f75 = _percentile_nearest(da_noz, 95)
+            tem = np.copy(y)
+            tem[tem < f25] = 0
+            tem[tem > f75] = 0
+            res.append(int(np.dot(ix, tem)))
+    res = np.array(res)
+    return int(np.where(res == np.max(res))[0][0]), res
+
+
+def get_avg_depth(dominat, X_dense, y):
+    """identify_strains...:109-119: mean of the strain's y values (1 -> 0, zeros dropped) inside their 25th..75th
+    percentile (nearest)."""
+    doarr = X_dense[:, dominat].astype(np.int64) * y
+    doarr[doarr == 1] = 0
+    noz = doarr[doarr != 0]
+    f25 = _percentile_nearest(noz, 25)
+    f75 = _percentile_nearest(noz, 75)
+    noz = noz.copy()
+    noz[noz < f25] = 0
+    noz[noz > f75] = 0
+    return np.mean(noz[noz != 0])
+
+
+def unique_cluster_rows(om_dense, all_cls):
+    """detect_strains (identify_strains...:183-197): ln[row] = 1 when the row's k-mer belongs to exactly one of the
+    identified clusters `all_cls` (1-based cluster ids = columns + 1 of overlap_matrix.npz), else 0."""
+    cols = [int(a) - 1 for a in all_cls]
+    ln = np.sum(om_dense[:, cols].astype(np.int64), axis=1)
+    ln[ln > 1] = 0
+    return ln

@@ -9,6 +9,11 @@
   get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc)        ...:94-108
         integer reductions on the GPU over the CSC form of all_strains_re.npz (no X.A densification,
         identify_strains...:200-201); the ratios are formed on the host exactly as the reference does.
+  optimize_dominat_y(ix, iy)                    ...:136-175
+  get_avg_depth(dominat, pX, py)                ...:109-119
+  unique_cluster_rows(omatrix, all_cls)         ...:183-197  (`ln`, so that py_u = py * ln)
+        order statistics ('nearest' percentiles) over one strain's rows: host NumPy on the CSC columns,
+        O(nnz) instead of O(rows x strains).
 
 The multi-GPU form sums the raw dense vectors first and applies remove_1 afterwards
 (strainscan_b200/dist.py) -- never before the sum.
@@ -102,3 +107,49 @@ def get_remainc(dominat, used_kmer, X, py, strain_remainc, engine=None):
             continue
         strain_remainc[i] = 0 if total[i] == 0 else covered[i] / total[i]
     return strain_remainc
+
+
+def _column_values(X, y, j):
+    """y restricted to the rows of strain j (the non-zero part of X[:, j] * y needs nothing else: X is 0/1)."""
+    if not isinstance(X, StrainMatrix):
+        X = StrainMatrix(X)
+    rows = X.rows[int(X.col_ptr[j]):int(X.col_ptr[j + 1])]
+    return np.asarray(y)[rows]
+
+
+def optimize_dominat_y(X, y):
+    """identify_strains...:136-175: the strain whose rows carry the largest sum of y inside the 5th..95th
+    percentile ('nearest') of its non-zero values; the first maximum wins (np.where(...)[0][0])."""
+    if not isinstance(X, StrainMatrix):
+        X = StrainMatrix(X)
+    y = np.asarray(y)
+    res = np.zeros(X.n_strains, dtype=np.result_type(y.dtype, np.int64))
+    for j in range(X.n_strains):
+        v = _column_values(X, y, j)
+        nz = v[v != 0]
+        if nz.size < 1 or nz.sum() == 0:
+            continue
+        lo, hi = np.percentile(nz, 5, method="nearest"), np.percentile(nz, 95, method="nearest")
+        res[j] = v[(v >= lo) & (v <= hi)].sum()
+    return int(np.where(res == np.max(res))[0][0])
+
+
+def get_avg_depth(dominat, X, y):
+    """identify_strains...:109-119: mean of the dominant strain's y values (1 -> 0, zeros dropped) inside their
+    25th..75th percentile ('nearest')."""
+    v = _column_values(X, y, int(dominat)).copy()
+    v[v == 1] = 0
+    nz = v[v != 0]
+    lo, hi = np.percentile(nz, 25, method="nearest"), np.percentile(nz, 75, method="nearest")
+    return np.mean(nz[(nz >= lo) & (nz <= hi)])
+
+
+def unique_cluster_rows(omatrix, all_cls):
+    """detect_strains' `ln` (identify_strains...:183-197): 1 for the rows whose k-mer belongs to exactly one of the
+    identified clusters (overlap_matrix.npz column = cluster id - 1), else 0; sparse, no `.A`."""
+    import scipy.sparse as sp
+    om = sp.load_npz(omatrix) if isinstance(omatrix, (str, os.PathLike)) else sp.csr_matrix(omatrix)
+    cols = [int(a) - 1 for a in all_cls]
+    ln = np.asarray(om.tocsc()[:, cols].astype(np.int64).sum(axis=1)).ravel()
+    ln[ln > 1] = 0
+    return ln

@@ -133,3 +133,72 @@ def test_read_paths_follow_reference_convention():
     assert identify_shim.read_paths(("a.fq", "")) == ["a.fq"]
     assert identify_shim.read_paths(("a.fq.gz", "b.fq.gz")) == ["a.fq.gz", "b.fq.gz"]
     assert identify_shim.read_paths("a.fq b.fq") == ["a.fq", "b.fq"]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_dominant_strain_and_depth_mirrors_equal_the_dense_reference_code(seed):
+    """optimize_dominat_y / get_avg_depth / the unique-cluster row mask (identify_strains...:109-119, 136-175,
+    183-197) on the sparse columns against the dense restatement, incl. empty strains, all-zero y and ties."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n, S = 4000, 9
+    X = (rng.random((n, S)) < rng.uniform(0.02, 0.5, S)).astype(np.int8)
+    X[:, 4] = 0                                           # a strain without rows
+    X[:, 7] = X[:, 2]                                     # a tie: the first maximum wins
+    y = rng.poisson(6, n).astype(np.int64) * (rng.random(n) < 0.7)
+    y[y == 1] = 0                                         # remove_1 ran before (Vote_...:386-403)
+    if seed == 3:
+        y[:] = 0
+        y[:50] = 7
+    dom, res = adapters.optimize_dominat_y(X, y)
+    assert l2_shim.optimize_dominat_y(sp.csr_matrix(X), y) == dom
+    assert l2_shim.optimize_dominat_y(l2_shim.StrainMatrix(X), y) == dom
+    if res[dom] > 0:
+        a, b = adapters.get_avg_depth(dom, X, y), l2_shim.get_avg_depth(dom, l2_shim.StrainMatrix(X), y)
+        assert a == b and type(a) is type(b)
+    om = (rng.random((n, 5)) < 0.4).astype(np.int8)
+    for cls in ([1], [2, 5], [1, 3, 4]):
+        assert np.array_equal(l2_shim.unique_cluster_rows(sp.csr_matrix(om), cls), adapters.unique_cluster_rows(om, cls))
+
+
+_REF_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "library")
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_LIB), reason="baseline/_ref not present (python baseline/setup_ref.py)")
+def test_per_strain_restatements_pinned_against_the_reference_module():
+    """The oracle's restatements of identify_strains_L2_Enet_Pscan_new_sp.py (and therefore the mirrors checked
+    against them) against the reference's own functions, imported from the sandbox, on random dense inputs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, warnings
+import numpy as np
+warnings.simplefilter("ignore")
+sys.path[:0] = [%r, %r, %r]
+import ss_compat; ss_compat.apply()
+import identify_strains_L2_Enet_Pscan_new_sp as ref
+from oracle import adapters
+for seed in range(6):
+    rng = np.random.default_rng(seed)
+    n, S = 3000, 7
+    X = (rng.random((n, S)) < rng.uniform(0.05, 0.5, S)).astype(np.int8)
+    X[:, 5] = X[:, 1]
+    y = rng.poisson(5, n).astype(np.int64) * (rng.random(n) < 0.8)
+    y[y == 1] = 0
+    dom, _ = adapters.optimize_dominat_y(X, y)
+    assert dom == ref.optimize_dominat_y(X, y), seed
+    assert adapters.get_avg_depth(dom, X, y) == ref.get_avg_depth(dom, X, y), seed
+    assert [c for c, _ in adapters.stat_cov_all(X, y)] == [ref.stat_cov(X[:, j], y)[1] for j in range(S)]
+    cand = adapters.candidate_counts(X, y)
+    c, chk = ref.get_candidate_arr(X.T, y)
+    assert cand[c] == chk == max(cand) and c == int(np.argmax(cand))
+    used = (rng.random(n) < 0.3).astype(np.int64)
+    rem = ref.get_remainc(0, used, X.T.astype(np.int64), y, {})
+    for j, (check, all_k) in enumerate(adapters.remain_cov(used, X, y)):
+        if j:
+            assert rem[j] == (0 if all_k == 0 else check / all_k)
+print("ok")
+''' % (os.path.join(root, "baseline", "shims"), _REF_LIB, root)
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-3000:]
