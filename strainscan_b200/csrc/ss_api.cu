@@ -94,6 +94,10 @@ struct ss_kmerset {
     ss_bucket *d_buckets = nullptr;
     uint32_t *d_slot_cnt = nullptr;   // 4*n_buckets + 1
     uint32_t *d_slot_of = nullptr;    // n_records
+    uint32_t *d_ord_of_slot = nullptr;   // 4*n_buckets + 1: the last record ordinal that holds the slot's k-mer
+    uint32_t *d_dup = nullptr;           // records that are not their slot's representative (duplicate k-mers)
+    uint64_t n_dup = 0;
+    mutable bool counters_clean = false; // the last pass left every slot counter at zero (K3b clears what it reads)
     uint8_t *d_flags = nullptr;       // n_records
     uint32_t *d_row_of = nullptr;     // n_records or null (kid order == ordinal order)
     unsigned long long *d_filter = nullptr;   // L2-resident prefilter (64-bit blocks) or null
@@ -414,7 +418,7 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
     uint64_t *d_keys = nullptr; uint8_t *d_ok = nullptr; uint32_t *d_last = nullptr;
     unsigned long long *d_nd = nullptr;
     const uint64_t n_slots = 4 * s->n_buckets + 1;
-    auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_ok); cudaFree(d_last); cudaFree(d_nd); };
+    auto cleanup = [&]() { cudaFree(d_keys); cudaFree(d_ok); cudaFree(d_nd); };
 #define SS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ss_kmerset_free(s); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
     SS_TRY(cudaMalloc(&s->d_buckets, s->n_buckets * sizeof(ss_bucket)));
     SS_TRY(cudaMalloc(&s->d_slot_cnt, n_slots * sizeof(uint32_t)));
@@ -422,7 +426,8 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
     SS_TRY(cudaMalloc(&s->d_flags, std::max<uint64_t>(n, 1)));
     SS_TRY(cudaMalloc(&d_keys, std::max<uint64_t>(n, 1) * sizeof(uint64_t)));
     SS_TRY(cudaMalloc(&d_ok, std::max<uint64_t>(n, 1)));
-    SS_TRY(cudaMalloc(&d_last, n_slots * sizeof(uint32_t)));
+    SS_TRY(cudaMalloc(&s->d_ord_of_slot, n_slots * sizeof(uint32_t)));
+    d_last = s->d_ord_of_slot;
     SS_TRY(cudaMalloc(&d_nd, sizeof(unsigned long long)));
     SS_TRY(cudaMemsetAsync(s->d_buckets, 0xFF, s->n_buckets * sizeof(ss_bucket), c->stream));
     SS_TRY(cudaMemsetAsync(s->d_slot_cnt, 0, n_slots * sizeof(uint32_t), c->stream));
@@ -461,6 +466,17 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
     SS_TRY(cudaMemcpyAsync(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost, c->stream));
     SS_TRY(cudaStreamSynchronize(c->stream));
     s->n_distinct = nd + (s->has_ones ? 1 : 0);
+    {   // duplicate records: in the set, but not the last record of their k-mer
+        std::vector<uint32_t> dup;
+        for (uint64_t i = 0; i < n; i++)
+            if ((s->flags[i] & SS_REC_IN_SET) && !(s->flags[i] & SS_REC_IS_LAST)) dup.push_back((uint32_t)i);
+        s->n_dup = dup.size();
+        if (s->n_dup) {
+            SS_TRY(cudaMalloc(&s->d_dup, s->n_dup * sizeof(uint32_t)));
+            SS_TRY(cudaMemcpy(s->d_dup, dup.data(), s->n_dup * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
+    s->counters_clean = true;       // zeroed above, nothing counted yet
 
     // L2 row order: sorted by kid (Vote_...:386); identity when headers are 1..n in order
     bool perm = n > 0;
@@ -589,6 +605,7 @@ extern "C" int ss_kmerset_free(ss_kmerset *s) {
     if (!s) return SS_OK;
     cudaSetDevice(s->ctx->device);
     cudaFree(s->d_buckets); cudaFree(s->d_slot_cnt); cudaFree(s->d_slot_of); cudaFree(s->d_flags);
+    cudaFree(s->d_ord_of_slot); cudaFree(s->d_dup);
     cudaFree(s->d_row_of); cudaFree(s->d_filter);
     delete s;
     return SS_OK;
@@ -958,7 +975,9 @@ static int check_format_result(ss_ctx *c, const char *what) {
 }
 
 static int reset_pass(ss_ctx *c, const ss_kmerset *s) {
-    SS_CUDA(cudaMemsetAsync(s->d_slot_cnt, 0, (4 * s->n_buckets + 1) * sizeof(uint32_t), c->stream));
+    if (!s->counters_clean)     // a pass that failed half-way; normally K3b has cleared what the last pass counted
+        SS_CUDA(cudaMemsetAsync(s->d_slot_cnt, 0, (4 * s->n_buckets + 1) * sizeof(uint32_t), c->stream));
+    s->counters_clean = false;
     SS_CUDA(cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
     SS_CUDA(cudaMemsetAsync(c->d_stats + 4, 0xFF, sizeof(unsigned long long), c->stream));
     SS_CUDA(cudaMemsetAsync(c->d_stats + 5, 0, sizeof(unsigned long long), c->stream));
@@ -1144,10 +1163,12 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
         }
     }
     SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
-    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, dev_counts, c->stream));
+    SS_CUDA(ss_launch_scatter(s->d_slot_cnt, s->d_ord_of_slot, s->n_buckets, s->d_dup, s->n_dup, s->d_slot_of, s->n_records,
+                              dev_counts, c->n_sm, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
     SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
+    s->counters_clean = true;
     c->h_stats[0] += acc[0]; c->h_stats[3] += acc[3]; c->h_stats[5] += acc[5];
     rc = check_format_result(c, "ss_count");
     if (rc) return rc;
@@ -1159,7 +1180,7 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
         cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;
         cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
         st->probe_launches = launches;
-        st->total_launches = st->probe_launches + (s->n_records ? 1 : 0);
+        st->total_launches = st->probe_launches + (s->n_records ? 1 + (s->n_dup ? 1 : 0) : 0);
         st->binned_rounds = n_binned;
         st->bins = n_binned ? bv.P : 0;
         st->ms_total = now_ms() - t0;
@@ -1259,12 +1280,14 @@ static int stream_text(ss_ctx *c, const ss_kmerset *s, const char *buf, size_t l
 static int finish_streamed(ss_ctx *c, const ss_kmerset *s, stream_state &ss, uint32_t *counts, ss_stats *st, double t0,
                            const char *what) {
     SS_CUDA(cudaEventRecord(c->ev_b, c->stream));
-    SS_CUDA(ss_launch_gather(s->d_slot_of, s->d_slot_cnt, s->n_records, c->d_dense, c->stream));
+    SS_CUDA(ss_launch_scatter(s->d_slot_cnt, s->d_ord_of_slot, s->n_buckets, s->d_dup, s->n_dup, s->d_slot_of, s->n_records,
+                              c->d_dense, c->n_sm, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_c, c->stream));
     if (s->n_records)
         SS_CUDA(cudaMemcpyAsync(counts, c->d_dense, s->n_records * sizeof(uint32_t), cudaMemcpyDefault, c->stream));
     SS_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
+    s->counters_clean = true;
     int rc = check_format_result(c, what);
     if (rc) return rc;
     if (st) {
@@ -1275,7 +1298,7 @@ static int finish_streamed(ss_ctx *c, const ss_kmerset *s, stream_state &ss, uin
         cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;   // copies + index + probe, overlapped
         cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
         st->probe_launches = ss.probe_launches;
-        st->total_launches = ss.total_launches + 1;
+        st->total_launches = ss.total_launches + (s->n_records ? 1 + (s->n_dup ? 1 : 0) : 0);
         st->ms_total = now_ms() - t0;
     }
     return SS_OK;

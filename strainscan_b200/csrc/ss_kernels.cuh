@@ -32,6 +32,10 @@ cudaError_t ss_launch_flags(const uint32_t *slot_of, const uint32_t *last_ord, u
                             cudaStream_t st);
 cudaError_t ss_launch_gather(const uint32_t *slot_of, const uint32_t *slot_cnt, uint64_t n, uint32_t *dense,
                              cudaStream_t st);
+// K3b: dense[record] = counter of the record's slot (dense is zeroed here), counters cleared for the next pass
+cudaError_t ss_launch_scatter(uint32_t *slot_cnt, const uint32_t *ord_of_slot, uint64_t n_buckets, const uint32_t *dup,
+                              uint64_t n_dup, const uint32_t *slot_of, uint64_t n_records, uint32_t *dense, int n_sm,
+                              cudaStream_t st);
 cudaError_t ss_launch_l2_finalize(const uint32_t *dense, const uint8_t *flags, const uint32_t *row_of, uint64_t n,
                                   long long *py_o, cudaStream_t st);
 cudaError_t ss_launch_node_reduce(const uint32_t *dense, const uint8_t *flags, const unsigned long long *node_ptr,

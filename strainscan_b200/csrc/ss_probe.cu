@@ -637,6 +637,40 @@ __global__ void ss_gather_kernel(const uint32_t *__restrict__ slot_of, const uin
     dense[i] = (s == SS_NOSLOT) ? 0u : slot_cnt[s];
 }
 
+// K3b, streaming form: the slot counters are read in order (16 bytes = one bucket's four counters per load), the
+// non-zero ones are written to dense[ordinal of the slot's record] (dense is zeroed beforehand and, at 4 bytes per
+// record, mostly lives in L2) and cleared for the next pass.  Against the gather above this reads the counter array
+// once as a stream instead of fetching one 128-byte DRAM line per record.
+__global__ void __launch_bounds__(256) ss_scatter_kernel(uint32_t *__restrict__ slot_cnt,
+                                                         const uint32_t *__restrict__ ord_of_slot, uint64_t n_buckets,
+                                                         uint32_t *__restrict__ dense) {
+    uint4 *c4 = reinterpret_cast<uint4 *>(slot_cnt);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += stride) {
+        uint4 v = c4[b];
+        if (v.x | v.y | v.z | v.w) {
+            if (v.x) dense[ord_of_slot[4 * b + 0]] = v.x;
+            if (v.y) dense[ord_of_slot[4 * b + 1]] = v.y;
+            if (v.z) dense[ord_of_slot[4 * b + 2]] = v.z;
+            if (v.w) dense[ord_of_slot[4 * b + 3]] = v.w;
+            c4[b] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {          // the side slot of the all-ones key (k = 32 poly-T)
+        uint32_t v = slot_cnt[4 * n_buckets];
+        if (v) { dense[ord_of_slot[4 * n_buckets]] = v; slot_cnt[4 * n_buckets] = 0u; }
+    }
+}
+
+// records that repeat an earlier/later record's k-mer take the count of the slot's representative (its last record)
+__global__ void ss_dup_fill_kernel(const uint32_t *__restrict__ dup, uint64_t n_dup, const uint32_t *__restrict__ slot_of,
+                                   const uint32_t *__restrict__ ord_of_slot, uint32_t *__restrict__ dense) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dup) return;
+    uint32_t r = dup[i];
+    dense[r] = dense[ord_of_slot[slot_of[r]]];
+}
+
 // L2 adapter: py_o[kid-1] = (raw_upper && c != 1) ? c : 0   (remove_1)
 __global__ void ss_l2_finalize_kernel(const uint32_t *__restrict__ dense, const uint8_t *__restrict__ flags,
                                       const uint32_t *__restrict__ row_of, uint64_t n, long long *__restrict__ py_o) {
@@ -886,6 +920,19 @@ cudaError_t ss_launch_gather(const uint32_t *slot_of, const uint32_t *slot_cnt, 
                              cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     ss_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(slot_of, slot_cnt, n, dense);
+    return cudaGetLastError();
+}
+
+cudaError_t ss_launch_scatter(uint32_t *slot_cnt, const uint32_t *ord_of_slot, uint64_t n_buckets, const uint32_t *dup,
+                              uint64_t n_dup, const uint32_t *slot_of, uint64_t n_records, uint32_t *dense, int n_sm,
+                              cudaStream_t st) {
+    if (n_records == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dense, 0, n_records * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    uint64_t want = (n_buckets + 255) / 256;
+    unsigned grid = (unsigned)(want < (uint64_t)n_sm * 16 ? want : (uint64_t)n_sm * 16);
+    ss_scatter_kernel<<<grid ? grid : 1, 256, 0, st>>>(slot_cnt, ord_of_slot, n_buckets, dense);
+    if (n_dup) ss_dup_fill_kernel<<<(unsigned)((n_dup + 255) / 256), 256, 0, st>>>(dup, n_dup, slot_of, ord_of_slot, dense);
     return cudaGetLastError();
 }
 
