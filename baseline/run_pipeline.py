@@ -75,6 +75,33 @@ def install_b200_reducers():
     identify.match_node = identify_shim.match_node
     identify_low_mem.match_node = identify_shim.match_node
     identify_low_depth.match_node = identify_shim.match_node_low_depth
+
+    def make_adjust_profile(mod):
+        """adjust_profile (identify.py:167-228) with its gather branch (:167-191) on the array mirror; the Poisson
+        overlap correction (:192-228) stays the reference's own code."""
+        ref_adjust = mod.adjust_profile
+
+        def adjust_profile(node, results, valid_kmers, length, abundance, cov, match_results, cov_cutoff, db_dir, overlapping_info):
+            delete_pos, taken = [], []
+            for i in results:                  # identify.py:173-179; the stored values are one-shot map() iterators
+                if i.identifier in overlapping_info and node.identifier in overlapping_info[i.identifier]:
+                    lst = list(overlapping_info[i.identifier][node.identifier])
+                    taken.append((i.identifier, lst))
+                    delete_pos.extend(lst)
+            res = identify_shim.adjust_profile_gather(match_results, db_dir, node.identifier, delete_pos)
+            if res is None:                    # fewer than 1000 k-mers remain: hand the same iterators back
+                for ident, lst in taken:
+                    overlapping_info[ident][node.identifier] = iter(lst)
+                return ref_adjust(node, results, valid_kmers, length, abundance, cov, match_results, cov_cutoff, db_dir, overlapping_info)
+            length[node], k_profile = res
+            cov[node] = len(k_profile) / length[node]
+            abundance[node] = mod.piecewise(cov_cutoff, cov[node], node.data[0], k_profile)
+            return 1 if length[node] < 3000 else 2
+
+        return adjust_profile
+
+    identify.adjust_profile = make_adjust_profile(identify)
+    identify_low_mem.adjust_profile = make_adjust_profile(identify_low_mem)
     import identify_strains_L2_Enet_Pscan_new_sp as ids          # the module Vote_... imports (library/ on sys.path)
 
     def cal_cov_all(ix, iy):                                      # ix: rows x strains (identify_strains...:44-49)

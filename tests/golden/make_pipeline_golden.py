@@ -33,7 +33,7 @@ def run_case(engine, db_dir, name, work):
     """db_dir: one DB directory, or the {low_mem: dir} dict of synth_db.write_dbs()."""
     db = synth_db.SynthDB()
     if isinstance(db_dir, dict):
-        db_dir = db_dir[bool(synth_db.CASES[name].get("low_mem", False))]
+        db_dir = db_dir[synth_db.CASES[name].get("db", bool(synth_db.CASES[name].get("low_mem", False)))]
     args = synth_db.make_case_inputs(db, name, work)
     out = os.path.join(work, "out_%s_%s" % (engine, name))
     opts = []

@@ -94,8 +94,12 @@ class SynthDB:
                     out[own].append(revcomp(km))
         return out
 
-    def write(self, db_dir, low_mem=False):
-        """low_mem: the `-e 1` memory-efficient layout -- kmer.fa keeps only the lexicographically smaller
+    def write(self, db_dir, low_mem=False, overlap=False):
+        """overlap: leaf 4 is a *reconstructed* node (reconstructed_nodes.txt, label 'o2'): its kmers/4 list also
+        holds 3000 ordinals of leaf 1's k-mers, and overlapping_info/1 (+ 1_supple) lists their positions in that
+        list, so that once cluster 1 is identified the search corrects node 4's profile (adjust_profile,
+        identify.py:167-191) instead of taking it at face value.
+        low_mem: the `-e 1` memory-efficient layout -- kmer.fa keeps only the lexicographically smaller
         strand of every k-mer (Build_tree_mem.py:107-110) and <DB>/Memory_DB makes StrainScan.py:188-196 route
         the search through identify_low_mem (reads are still counted without -C: only same-strand hits)."""
         rng = np.random.default_rng(self.seed + 1)
@@ -114,13 +118,23 @@ class SynthDB:
                 v, km = allk[j]
                 f.write(b">1\n" + km + b"\n")
                 node_ord[v].append(idx)
+        if overlap:
+            shared = node_ord[1][:3000]
+            first = len(node_ord[4])
+            node_ord[4] = node_ord[4] + shared
+            os.makedirs(os.path.join(tdb, "overlapping_info"), exist_ok=True)
+            with open(os.path.join(tdb, "overlapping_info", "1"), "w") as f:
+                f.write(" ".join(str(first + i) for i in range(len(shared))) + "\n")
+            with open(os.path.join(tdb, "overlapping_info", "1_supple"), "w") as f:
+                f.write("4 0\n")
         for v in range(1, 8):
             with open(os.path.join(tdb, "kmers", str(v)), "w") as f:
                 f.write("".join("%d " % x for x in node_ord[v]))
         with open(os.path.join(tdb, "node_length.txt"), "w") as f:
             for v in range(1, 8):
                 f.write("%d\t%d\n" % (v, len(node_ord[v])))
-        open(os.path.join(tdb, "reconstructed_nodes.txt"), "w").close()
+        with open(os.path.join(tdb, "reconstructed_nodes.txt"), "w") as f:
+            f.write("4\n" if overlap else "")
         with open(os.path.join(tdb, "tree_structure.txt"), "w") as f:
             for v in range(1, 8):
                 par = "N" if self.parent[v] is None else str(self.parent[v])
@@ -215,6 +229,8 @@ CASES = {
     # (baseline/run_pipeline.py --plasmid-db stands in for the StrainScan_build.py call); `pmix` = reads drawn
     # from ITS strains, added to the sample.  -p 2: reference genomes given by -r; -p 1: short contigs of the
     # strains of the identified multi-strain clusters (load_db_cls, StrainScan.py:47-94), default_cov = 0.
+    # a reconstructed node whose k-mer list overlaps an identified cluster's (adjust_profile, identify.py:167-191)
+    "reconstructed_node": dict(mix=[((1, 2), 10), ((4, 1), 8)], flags=[], pe=False, gz=False, db="overlap"),
     "plasmid_mode_2": dict(mix=[((1, 2), 10)], pmix=[((2, 1), 12), ((4, 2), 7)], flags=["-p", "2"], pe=False, gz=False),
     "plasmid_mode_1": dict(mix=[((1, 1), 9), ((2, 2), 6)], pmix=[((1, 3), 10), ((1, 1), 5)], flags=["-p", "1"], pe=True,
                            gz=True),
@@ -224,7 +240,7 @@ CASES = {
 # read-sampling seeds, fixed per case (the committed golden reports depend on them)
 CASE_SEEDS = {"extra_region": 1, "low_depth_prob": 2, "same_cluster_two_strains": 3, "singleton_cluster": 4,
               "two_clusters_pe_gz": 5, "two_clusters_se": 6, "low_mem_db": 7, "two_strains_pe_bgzf": 8,
-              "plasmid_mode_2": 9, "plasmid_mode_1": 10}
+              "plasmid_mode_2": 9, "plasmid_mode_1": 10, "reconstructed_node": 11}
 
 
 def plasmid_db():
@@ -269,4 +285,5 @@ def write_plasmid_db(base_dir):
 def write_dbs(base_dir):
     """Both database layouts the cases use: {low_mem flag: DB directory}."""
     db = SynthDB()
-    return {False: db.write(os.path.join(base_dir, "DB")), True: db.write(os.path.join(base_dir, "DB_mem"), low_mem=True)}
+    return {False: db.write(os.path.join(base_dir, "DB")), True: db.write(os.path.join(base_dir, "DB_mem"), low_mem=True),
+            "overlap": db.write(os.path.join(base_dir, "DB_ovl"), overlap=True)}

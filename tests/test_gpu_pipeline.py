@@ -8,7 +8,8 @@ Covers single-end / paired-end + gz, two clusters, two strains in one cluster (E
 an all-singleton result, -l 2 -b 1 (low depth + probability report), -e 1 (extraRegion_mode), a
 memory-efficient database (Memory_DB -> identify_low_mem, canonical-strand k-mer set), paired
 blocked-gzip inputs (inflated on the device) and plasmid_mode -p 1 / -p 2 (the run-time StrainScan_build.py
-call is answered with a pre-made DB_plasmid, baseline/run_pipeline.py --plasmid-db).
+call is answered with a pre-made DB_plasmid, baseline/run_pipeline.py --plasmid-db) and a reconstructed
+node whose k-mer list overlaps an identified cluster's (adjust_profile, identify.py:167-191).
 A second test repeats every case with the per-node and per-strain reductions (match_node, cal_cov_all,
 get_candidate_arr, get_remainc) replaced by the GPU-backed mirrors as well (--engine b200-full).
 Needs baseline/_ref (git-ignored, travels to the GPU box with gpurun); skipped when it is absent."""
