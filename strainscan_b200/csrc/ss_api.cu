@@ -1258,8 +1258,9 @@ static int stream_text(ss_ctx *c, const ss_kmerset *s, const char *buf, size_t l
     const bool pinned = len ? is_pinned(buf) : true;
     const size_t chunk = c->chunk_bytes;
     while (pos < len) {
-        size_t end = pos + chunk >= len ? len : find_record_start(buf, len, pos + chunk - SS_INGEST_BOUNDARY);
-        if (end > pos + chunk || end <= pos) return fail(SS_ERR_FORMAT, "reads: no FASTQ record boundary within 64 KiB");
+        size_t end = pos + chunk >= len ? len : ss_find_cut(buf, pos, pos + chunk);
+        if (end > pos + chunk || end <= pos)
+            return fail(SS_ERR_FORMAT, "reads: no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)");
         size_t n = end - pos;
         int b = ss.slot;
         const char *src = buf + pos;

@@ -53,6 +53,19 @@ size_t ss_find_record_start(const char *buf, size_t len, size_t from) {
     return len;
 }
 
+// a record start in (lo, hi) to cut a chunk at, as late as a cheap search finds one: the window before `hi` starts at
+// SS_INGEST_BOUNDARY and is widened 4x at a time down to `lo` (long-read files: one record can be megabytes).
+// Returns 0 when [lo, hi) holds no record start after lo.
+size_t ss_find_cut(const char *buf, size_t lo, size_t hi) {
+    for (size_t win = SS_INGEST_BOUNDARY;; win *= 4) {
+        const bool whole = win >= hi - lo;
+        size_t from = whole ? lo + 1 : hi - win;
+        size_t cut = ss_find_record_start(buf, hi, from);
+        if (cut < hi) return cut;
+        if (whole) return 0;
+    }
+}
+
 static bool ends_with_gz(const char *path) {   // identify.py:81: re.split('\.', path)[-1] == 'gz'
     const char *dot = strrchr(path, '.');
     return dot && strcmp(dot + 1, "gz") == 0;
@@ -392,9 +405,7 @@ static size_t cut_chunk(ss_chunk *c, size_t fill, bool last, bool file_end = tru
         if (n) t[n++] = '\n';       // slack behind cap
         return n;
     }
-    size_t from = fill > SS_INGEST_BOUNDARY ? fill - SS_INGEST_BOUNDARY : 1;
-    size_t cut = ss_find_record_start(t, fill, from);
-    return cut >= fill ? 0 : cut;   // 0: no boundary found
+    return ss_find_cut(t, 0, fill);   // 0: no boundary found
 }
 
 void ss_text_source::run_plain(const job &j) {
@@ -425,7 +436,7 @@ void ss_text_source::run_plain(const job &j) {
         const bool last = pos >= j.hi;
         size_t cut = cut_chunk(c, fill, last, j.hi >= f.size);
         if (!last) {
-            if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within 64 KiB"); return; }
+            if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); return; }
             carry.assign(c->text + cut, c->text + fill);
         }
         c->len = cut;
@@ -463,7 +474,7 @@ void ss_text_source::run_gz(const job &j) {
         size_t cut = cut_chunk(c, fill, last);
         ss_chunk *c2 = nullptr;
         if (!last) {
-            if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within 64 KiB"); break; }
+            if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); break; }
             c2 = acquire();
             if (!c2) { release(c); break; }
             // carry the tail (the bytes after the cut) and keep 32 KiB of history in front of the point
@@ -505,7 +516,7 @@ bool ss_text_source::stream_writer::append(size_t n, const std::function<void(ui
             first = false;
         }
         size_t cut = cut_chunk(c, fill, false);
-        if (cut == 0) { abandon(); src->fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within 64 KiB"); return false; }
+        if (cut == 0) { abandon(); src->fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); return false; }
         ss_chunk *c2 = src->acquire();
         if (!c2) { abandon(); return false; }
         size_t tail = fill - cut;

@@ -17,7 +17,7 @@
 #include <vector>
 
 #define SS_INGEST_HIST 32768u            // deflate history kept in front of every chunk's text area
-#define SS_INGEST_BOUNDARY (64u << 10)   // a FASTQ record boundary is searched in the last 64 KiB of a chunk
+#define SS_INGEST_BOUNDARY (64u << 10)   // a FASTQ record boundary is searched in the last 64 KiB of a chunk first (ss_find_cut)
 
 // One independently inflatable gzip member (BGZF block) of a batch; the device kernel's work item.
 struct ss_member {
@@ -52,6 +52,7 @@ struct ss_chunk {
 int ss_read_whole_file(const char *path, std::vector<char> &out, std::string &err);
 size_t ss_trim_tail(const char *buf, size_t len);
 size_t ss_find_record_start(const char *buf, size_t len, size_t from);
+size_t ss_find_cut(const char *buf, size_t lo, size_t hi);
 
 class ss_text_source {
 public:

@@ -488,3 +488,28 @@ def test_binned_mode_vs_oracle(eng, k, slice_mb, pool_mb, round_tiles, bin_filte
     # idempotent: a second pass over the same cache gives the same vector
     again, _ = eng.count(ks, reads)
     assert np.array_equal(again, got)
+
+
+def test_long_reads_vs_oracle(eng, tmp_path):
+    """Sequence and quality lines far longer than a 992-byte unit (long-read FASTQ: 3 kb .. 120 kb per line), through
+    the resident, the streaming-host and the file paths, with and without the filter."""
+    rng = np.random.default_rng(777)
+    G = util.rand_genome(rng, 400_000)
+    fa = util.make_db(rng, G, 31, 30_000, both_strands=True)
+    fq = b"".join(util.make_reads(rng, G, n, L, p_sub=0.02, p_n=0.001) for n, L in ((40, 3000), (6, 40_000), (2, 120_000), (30, 150)))
+    d = adapters.count_dense(fa, 31, [fq])
+    path = tmp_path / "long.fq"
+    path.write_bytes(fq)
+    for filt in (None, "1"):
+        if filt:
+            os.environ["SS_FILTER"] = filt
+        try:
+            ks = eng.kmerset_from_text(fa, 31)
+        finally:
+            os.environ.pop("SS_FILTER", None)
+        for how, (got, st) in (("resident", eng.count(ks, eng.reads_from_host([fq]))), ("host", eng.count_host(ks, [fq])),
+                               ("files", eng.count_files(ks, [str(path)]))):
+            assert np.array_equal(got.astype(np.uint64), d.cnt), how
+            assert st.n_kmers == adapters.count_windows([fq], 31), (how, st.n_kmers)
+            assert st.n_reads == 78, (how, st.n_reads)
+    assert d.cnt.sum() > 10_000

@@ -365,3 +365,23 @@ def test_fasta_and_wrapped_fastq_are_rewritten(tmp_path):
             assert got.count(b"\n") == 4 * len(seqs) and got.startswith(b"@s0 some text\r\n")
         parts = [ingest([p], s, 2, chunk=256 << 10)[0] for s in range(2)]
         assert sorted(b"".join(parts).split(b"\n")) == sorted(got.split(b"\n"))
+
+
+def test_long_records_cut_with_a_widening_window(tmp_path):
+    """Long-read FASTQ: records of 6 kb .. 240 kb.  The chunker looks for a record start in the last 64 KiB of a chunk
+    first and widens the window 4x at a time; only a record longer than the chunk itself is refused (loudly)."""
+    rng = np.random.default_rng(5)
+    G = util.rand_genome(rng, 300_000)
+    fq = b"".join(util.make_reads(rng, G, n, L) for n, L in ((20, 3000), (5, 40_000), (2, 120_000), (20, 150)))
+    p = tmp_path / "long.fq"
+    p.write_bytes(fq)
+    pg = tmp_path / "long.fq.gz"
+    pg.write_bytes(gzip.compress(fq, 4))
+    for path in (p, pg):
+        for chunk in (1 << 19, 1 << 20):
+            for threads in (1, 4):
+                text, _ = ingest([str(path)], chunk=chunk, threads=threads)
+                assert sorted(records(text)) == sorted(records(fq)), (path.name, chunk, threads)
+    with pytest.raises(_lib.StrainScanB200Error) as ei:
+        ingest([str(p)], chunk=1 << 18, threads=2)
+    assert ei.value.code == 4 and "record boundary" in str(ei.value)
