@@ -452,11 +452,12 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
         if (const char *e = getenv("SS_FILTER_MAX_MB")) { double v = atof(e); if (v >= 1 && v <= 1024) max_mb = v; }
         bool want = force >= 0 ? force != 0 : (double)s->n_buckets * sizeof(ss_bucket) > min_table_mb * 1e6;
         if (want && n_ok > 0) {
-            double words = std::min((double)n_ok * bits_per_key / 64.0, max_mb * 1e6 / 8.0);
+            // SS_FILTER_PAIRS: two (k-1)-mers per key go in
+            double words = std::min((double)n_ok * (SS_FILTER_PAIRS ? 2.0 : 1.0) * bits_per_key / 64.0, max_mb * 1e6 / 8.0);
             s->n_filter_words = (uint32_t)std::max(1024.0, words);
             SS_TRY(cudaMalloc(&s->d_filter, (uint64_t)s->n_filter_words * 8));
             SS_TRY(cudaMemsetAsync(s->d_filter, 0, (uint64_t)s->n_filter_words * 8, c->stream));
-            SS_TRY(ss_launch_filter_build(d_keys, d_ok, n, s->d_filter, s->n_filter_words, c->stream));
+            SS_TRY(ss_launch_filter_build(d_keys, d_ok, n, s->d_filter, s->n_filter_words, s->view().kmask, c->stream));
         }
     }
     SS_TRY(ss_launch_flags(s->d_slot_of, d_last, n, s->d_flags, c->stream));

@@ -26,6 +26,17 @@
 #endif                                               // classification and lands during the (long) probe phase
 #define SS_TEXT_PAD (8192 + 256)                     // '\n' padding after the text on device
 
+// Experiment, off by default (-DSS_FILTER_PAIRS=1 builds it): key the L2-resident filter by (k-1)-mers -- it then holds
+// the first and the last k-1 bases of every k-mer of the set, and the scan asks it only about the (k-1)-mers at EVEN
+// text positions: the one at position j answers for the k-mer that starts at j (its prefix) and for the k-mer that
+// starts at j-1 (its suffix), i.e. 17 filter loads per 32 k-mers instead of 32.  Bit-exact (all parity tests pass), same
+// table-probe rate (2.6 %), but SLOWER on B200: probe 7.39 ms vs 6.29 ms per 10 M reads.  Halving the L1 tag lookups and
+// L2 requests does not pay for the ballot / shuffle / select added to every group and for the half-empty load
+// instructions: the kernel is bound by issue slots and load latency, not by the request rate.
+#ifndef SS_FILTER_PAIRS
+#define SS_FILTER_PAIRS 0
+#endif
+
 #define SS_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SS_NOSLOT 0xFFFFFFFFu
 

@@ -329,6 +329,7 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
     const uint32_t half = lane >> 4;                    // which 32-bit word my window starts in
     const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside it
     const uint32_t khi_mask = (uint32_t)(tv.kmask >> 32), klo_mask = (uint32_t)tv.kmask;
+    const uint32_t phi_mask = (uint32_t)(tv.kmask >> 34), plo_mask = (uint32_t)(tv.kmask >> 2);   // the first k-1 bases
 
     uint32_t it = 0;
     for (uint64_t unit = gw; unit < n_units; unit += nw, ++it) {
@@ -401,27 +402,43 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
                         ok[u] = false;
                     }
                 }
-                ss_hash2(k0[u], k1[u], hh[u], hl[u]);
+                if (FILTER && SS_FILTER_PAIRS) ss_hash2(k0[u] & plo_mask, k1[u] & phi_mask, hh[u], hl[u]);   // my (k-1)-mer
+                else ss_hash2(k0[u], k1[u], hh[u], hl[u]);
             }
             if (FILTER) {
                 uint64_t fw[UNROLL];
+                bool need[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
+                    if (SS_FILTER_PAIRS) {
+                        // even lanes ask for their own k-mer and for the one before them; lane 31 asks for itself
+                        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok[u]);
+                        need[u] = (lane & 1u) ? (lane == 31u && ok[u]) : (((okm | (okm << 1)) >> lane) & 1u);
+                    } else {
+                        need[u] = ok[u];
+                    }
                     fw[u] = 0ull;
-                    if (ok[u]) fw[u] = ld_filter(tv.filter + __umulhi(hl[u], tv.n_filter_words), pol_keep);
+                    if (need[u]) fw[u] = ld_filter(tv.filter + __umulhi(hl[u], tv.n_filter_words), pol_keep);
                 }
                 bool pass[UNROLL], any = false;
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     uint64_t m = s_pat[hl[u] & (SS_NPAT - 1)];
-                    pass[u] = ok[u] && (fw[u] & m) == m;
+                    bool hit = need[u] && (fw[u] & m) == m;
+                    if (SS_FILTER_PAIRS) {
+                        const bool next = __shfl_down_sync(0xFFFFFFFFu, hit, 1);
+                        hit = ((lane & 1u) && lane != 31u) ? next : hit;
+                    }
+                    pass[u] = ok[u] && hit;
                     any |= pass[u];
                 }
                 if (BIN) {                              // survivors are the rule here: no queue, straight to the bins
 #pragma unroll
                     for (int u = 0; u < UNROLL; u++) {
                         n_table += pass[u];
-                        bin_emit(b_cnt, b_base, bv, pass[u], (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), hh[u], lane, lt_mask);
+                        uint32_t bh = hh[u];
+                        if (SS_FILTER_PAIRS) { uint32_t t; ss_hash2(k0[u], k1[u], bh, t); }   // the bin is the k-mer's bucket range
+                        bin_emit(b_cnt, b_base, bv, pass[u], (uint64_t)k0[u] | ((uint64_t)k1[u] << 32), bh, lane, lt_mask);
                     }
                 } else if (any) {                       // rare per lane: queue survivors for an exact table probe
 #pragma unroll
@@ -608,12 +625,20 @@ __global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_
 
 // L2-resident prefilter: every key sets 4 bits of one 64-bit word
 __global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ rec_ok, uint64_t n,
-                                       unsigned long long *__restrict__ filter, uint32_t n_words) {
+                                       unsigned long long *__restrict__ filter, uint32_t n_words, uint64_t kmask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !rec_ok[i] || keys[i] == SS_EMPTY) return;
     uint32_t hh, hl;
+#if SS_FILTER_PAIRS
+    const uint64_t pre = keys[i] & (kmask >> 2), suf = keys[i] >> 2;      // first / last k-1 bases
+    ss_hash2((uint32_t)pre, (uint32_t)(pre >> 32), hh, hl);
+    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+    ss_hash2((uint32_t)suf, (uint32_t)(suf >> 32), hh, hl);
+    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+#else
     ss_hash2((uint32_t)keys[i], (uint32_t)(keys[i] >> 32), hh, hl);
     atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+#endif
 }
 
 // flags[i] |= IS_LAST where record i is the highest ordinal stored at its slot
@@ -894,9 +919,9 @@ cudaError_t ss_launch_bin_probe(const ss_bin_view &bv, const uint32_t *n_chunks,
 }
 
 cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *filter,
-                                   uint32_t n_words, cudaStream_t st) {
+                                   uint32_t n_words, uint64_t kmask, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    ss_filter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, rec_ok, n, filter, n_words);
+    ss_filter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, rec_ok, n, filter, n_words, kmask);
     return cudaGetLastError();
 }
 
