@@ -400,8 +400,8 @@ def main():
                 "bytes_per_kmer": bytes_per_kmer, "kmers_per_launch": st.n_kmers, "launch_ms": probe_avg_ms,
                 "note": "achieved = algorithmic bytes (SURVEY 8d: 32 B table sector + 1 B text per k-mer, + second sectors and "
                         "counter updates) / launch time; an L2-resident filter answers ~97 % of the probes, so the DRAM traffic "
-                        "(`traffic`, ncu) is ~4x smaller than the algorithmic bytes; what binds the kernel is the L1 tag stage "
-                        "and the L2 random-sector rate (~4.0 ms per launch each, DESIGN.md section 3)",
+                        "(`traffic`, ncu) is ~4x smaller than the algorithmic bytes; what binds the kernel is issue slots (64 % busy) "
+                        "and the latency of the L2 filter loads -- halving the filter requests did not speed it up (DESIGN.md section 3)",
                 "random_sector_gather_gbps": rand_gbps,
                 "frac_of_random_gather": (st.n_kmers * 32.0 * (1 + p2) / (probe_avg_ms * 1e-3) / 1e9 / rand_gbps)
                 if rand_gbps else None}

@@ -319,6 +319,16 @@ def test_file_ingest_many_chunks_and_segments(tmp_path, monkeypatch):
         got, st = e.count(ks, reads)
         assert np.array_equal(got.astype(np.uint64), d.cnt)
         assert st.n_reads == 21_000 and st.probe_launches >= 4          # one launch per cache segment
+        # the same cache of several segments in binned mode (rounds per segment, the sample taken from the first one)
+        monkeypatch.setenv("SS_FILTER", "1")
+        ksf = e.kmerset_from_text(fa, 31)
+        monkeypatch.delenv("SS_FILTER")
+        for k, v in (("SS_BIN", "2"), ("SS_BIN_SLICE_MB", "0.1"), ("SS_BIN_POOL_MB", "64"), ("SS_BIN_ROUND_TILES", "400")):
+            monkeypatch.setenv(k, v)
+        gotb, stb = e.count(ksf, reads)
+        assert np.array_equal(gotb, got) and stb.binned_rounds >= 8 and stb.n_reads == 21_000 and stb.n_kmers == st.n_kmers
+        for k in ("SS_BIN", "SS_BIN_SLICE_MB", "SS_BIN_POOL_MB", "SS_BIN_ROUND_TILES"):
+            monkeypatch.delenv(k)
         got2, st2 = e.count_files(ks, [str(p1), str(p2)])
         assert np.array_equal(got2, got) and st2.n_kmers == st.n_kmers and st2.probe_launches >= 16
         for n in (2, 5):

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit: parity tests, the bench line, the ncu launch list and one --set full capture of the
-# probe kernel.  Usage (under gpurun): bash tools/gpu_round.sh <tag> [skip-tests]
+# probe kernel (the 4th launch: the first pass of a set over a read cache is split into sample / head / rest).  Usage (under gpurun): bash tools/gpu_round.sh <tag> [skip-tests]
 TAG=${1:-rXX}
 mkdir -p gpurun_out
 if [ "$2" != "skip-tests" ]; then
@@ -10,6 +10,6 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_ou
 tail -c 3000 gpurun_out/${TAG}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ss_probe_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_probe \
+ncu --set full --clock-control none --import-source on -k regex:ss_probe_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_probe \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_full_bench.log 2>&1
 ls -la gpurun_out/${TAG}_*
