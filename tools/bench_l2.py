@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--only", type=int, default=-1, help="run only case number N (for ncu captures)")
+    ap.add_argument("--verify", action="store_true",
+                    help="also run every case with SS_BIN=0 (direct probing) and require the two dense vectors to be identical")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -50,6 +52,19 @@ def main():
             st = eng.count_device(kset, reads, counts.data_ptr())
             ms.append(st.ms_probe)
         assert int(counts.to(torch.int64)[torch.from_numpy(kset.valid).cuda()].sum()) == st.n_hits
+        same = None
+        if a.verify:
+            prev = os.environ.get("SS_BIN")
+            os.environ["SS_BIN"] = "0"
+            direct = torch.zeros_like(counts)
+            st0 = eng.count_device(kset, reads, direct.data_ptr())
+            if prev is None:
+                os.environ.pop("SS_BIN")
+            else:
+                os.environ["SS_BIN"] = prev
+            same = bool(torch.equal(direct, counts)) and st0.n_hits == st.n_hits and st0.n_kmers == st.n_kmers
+            assert same and st0.binned_rounds == 0, "binned and direct probing disagree"
+            del direct
         t = sum(ms) / len(ms)
         h, p2 = st.n_hits / st.n_kmers, st.n_second_probe / st.n_kmers
         bpk = 33.0 + 32.0 * p2 + 8.0 * h
@@ -60,7 +75,8 @@ def main():
             "filter": bool(st.n_table_probes), "hit_rate": h, "table_probe_rate": st.n_table_probes / st.n_kmers,
             "probe_ms": t, "kmers_per_s": st.n_kmers / (t * 1e-3), "algorithmic_gbps": st.n_kmers * bpk / (t * 1e-3) / 1e9,
             "hbm_sector_probes_per_s": (st.n_table_probes or st.n_kmers) / (t * 1e-3),
-            "binned_rounds": st.binned_rounds, "bins": st.bins, "probe_launches": st.probe_launches})
+            "binned_rounds": st.binned_rounds, "bins": st.bins, "probe_launches": st.probe_launches,
+            "identical_to_direct_probing": same})
         del reads, text, counts, kset
         torch.cuda.empty_cache()
     out["random_sector_gather_gbps_1GiB"] = rand
