@@ -100,7 +100,7 @@ struct ss_kmerset {
     mutable bool counters_clean = false; // the last pass left every slot counter at zero (K3b clears what it reads)
     uint8_t *d_flags = nullptr;       // n_records
     uint32_t *d_row_of = nullptr;     // n_records or null (kid order == ordinal order)
-    unsigned long long *d_filter = nullptr;   // L2-resident prefilter (64-bit blocks) or null
+    ss_fword *d_filter = nullptr;     // L2-resident prefilter or null
     uint32_t n_filter_words = 0;
     std::vector<uint8_t> flags;
     std::vector<uint64_t> header_ids;
@@ -453,10 +453,11 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
         bool want = force >= 0 ? force != 0 : (double)s->n_buckets * sizeof(ss_bucket) > min_table_mb * 1e6;
         if (want && n_ok > 0) {
             // SS_FILTER_PAIRS: two (k-1)-mers per key go in
-            double words = std::min((double)n_ok * (SS_FILTER_PAIRS ? 2.0 : 1.0) * bits_per_key / 64.0, max_mb * 1e6 / 8.0);
+            const double wbits = 8.0 * sizeof(ss_fword);
+            double words = std::min((double)n_ok * (SS_FILTER_PAIRS ? 2.0 : 1.0) * bits_per_key / wbits, max_mb * 1e6 * 8.0 / wbits);
             s->n_filter_words = (uint32_t)std::max(1024.0, words);
-            SS_TRY(cudaMalloc(&s->d_filter, (uint64_t)s->n_filter_words * 8));
-            SS_TRY(cudaMemsetAsync(s->d_filter, 0, (uint64_t)s->n_filter_words * 8, c->stream));
+            SS_TRY(cudaMalloc(&s->d_filter, (uint64_t)s->n_filter_words * sizeof(ss_fword)));
+            SS_TRY(cudaMemsetAsync(s->d_filter, 0, (uint64_t)s->n_filter_words * sizeof(ss_fword), c->stream));
             SS_TRY(ss_launch_filter_build(d_keys, d_ok, n, s->d_filter, s->n_filter_words, s->view().kmask, c->stream));
         }
     }
@@ -616,7 +617,7 @@ extern "C" uint64_t ss_kmerset_distinct(const ss_kmerset *s) { return s ? s->n_d
 extern "C" int ss_kmerset_k(const ss_kmerset *s) { return s ? s->k : 0; }
 extern "C" uint64_t ss_kmerset_table_bytes(const ss_kmerset *s) {
     return s ? s->n_buckets * sizeof(ss_bucket) + (4 * s->n_buckets + 1) * 4 + s->n_records * 5 +
-                   (uint64_t)s->n_filter_words * 8 : 0;
+                   (uint64_t)s->n_filter_words * sizeof(ss_fword) : 0;
 }
 extern "C" int ss_kmerset_flags(const ss_kmerset *s, uint8_t *flags) {
     if (!s || !flags) return fail(SS_ERR_ARG, "ss_kmerset_flags: NULL argument");

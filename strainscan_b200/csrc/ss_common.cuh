@@ -37,6 +37,17 @@
 #define SS_FILTER_PAIRS 0
 #endif
 
+// Filter word: 32-bit blocks (all four bits of a key in one 32-bit word: 32-bit load / pattern / test in the probe
+// loop) or the first design's 64-bit blocks (two bits in each half).  Same bytes per key either way.
+#ifndef SS_FILTER_WORD32
+#define SS_FILTER_WORD32 1
+#endif
+#if SS_FILTER_WORD32
+typedef uint32_t ss_fword;
+#else
+typedef unsigned long long ss_fword;
+#endif
+
 #define SS_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define SS_NOSLOT 0xFFFFFFFFu
 
@@ -63,15 +74,19 @@ __device__ __forceinline__ void ss_hash2(uint32_t k0, uint32_t k1, uint32_t &hh,
     hh = (uint32_t)u;
     hl = (uint32_t)(u >> 32);
 }
-// Pattern-based blocked Bloom filter: a key sets the 4 bits of pattern (hl mod SS_NPAT) in its 64-bit
-// word; the probe kernel keeps the SS_NPAT patterns in shared memory (one LDS instead of ~8 ALU ops).
+// Pattern-based blocked Bloom filter: a key sets the 4 bits of pattern (hl mod SS_NPAT) in its filter word
+// (ss_fword, below); the probe kernel keeps the SS_NPAT patterns in shared memory (one LDS instead of ~8 ALU ops).
 #define SS_NPAT 1024
-__device__ __forceinline__ uint64_t ss_filter_pattern(uint32_t i) {
+__device__ __forceinline__ ss_fword ss_filter_pattern(uint32_t i) {
     uint32_t x = (i + 1u) * 0x9E3779B1u;
     x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
     uint32_t a = (1u << (x & 31u)) | (1u << ((x >> 5) & 31u));
     uint32_t b = (1u << ((x >> 10) & 31u)) | (1u << ((x >> 15) & 31u));
+#if SS_FILTER_WORD32
+    return a | b;
+#else
     return (uint64_t)a | ((uint64_t)b << 32);
+#endif
 }
 #endif
 
@@ -83,7 +98,7 @@ struct ss_table_view {
     uint32_t vmask;                // low k bits
     int k;
     int has_ones;                  // the key 0xFFFF...F (k = 32 poly-T) is in the set
-    const unsigned long long *filter;   // L2-resident blocked Bloom filter (64-bit blocks) or NULL
+    const ss_fword *filter;             // L2-resident blocked Bloom filter or NULL
     uint32_t n_filter_words;
 };
 

@@ -26,7 +26,7 @@ cudaError_t ss_launch_bin_probe(const ss_bin_view &bv, const uint32_t *n_chunks,
 cudaError_t ss_launch_insert(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *slots,
                              uint64_t n_buckets, uint32_t *slot_of, uint32_t *last_ord,
                              unsigned long long *n_distinct, cudaStream_t st);
-cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *filter,
+cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, ss_fword *filter,
                                    uint32_t n_words, uint64_t kmask, cudaStream_t st);
 cudaError_t ss_launch_flags(const uint32_t *slot_of, const uint32_t *last_ord, uint64_t n, uint8_t *flags,
                             cudaStream_t st);

@@ -65,10 +65,15 @@ __device__ __forceinline__ void ld_bucket(const ss_bucket *p, unsigned long long
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                  : "l"(p));
 }
-// one filter word (8 bytes of an L2-resident blocked Bloom filter), kept in L2 with evict_last
+// one filter word of the L2-resident blocked Bloom filter, kept in L2 with evict_last
 __device__ __forceinline__ unsigned long long ld_filter(const unsigned long long *p, uint64_t policy) {
     unsigned long long v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
     return v;
 }
 __device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
@@ -284,7 +289,7 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
     __shared__ uint32_t s_bcnt[BIN ? SS_CTA_WARPS * SS_BIN_PMAX : 1], s_bbase[BIN ? SS_CTA_WARPS * SS_BIN_PMAX : 1];
     static_assert(32 + 32 * UNROLL <= SS_QCAP, "survivor queue too small for this UNROLL");
     __shared__ ss_warp_smem s_warp[SS_CTA_WARPS];
-    __shared__ uint64_t s_pat[FILTER ? SS_NPAT : 1];     // filter bit patterns (4 bits of a 64-bit word)
+    __shared__ ss_fword s_pat[FILTER ? SS_NPAT : 1];     // filter bit patterns (4 bits of a filter word)
     if (FILTER) {
         for (uint32_t i = threadIdx.x; i < SS_NPAT; i += SS_CTA_THREADS) s_pat[i] = ss_filter_pattern(i);
         __syncthreads();
@@ -406,7 +411,7 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
                 else ss_hash2(k0[u], k1[u], hh[u], hl[u]);
             }
             if (FILTER) {
-                uint64_t fw[UNROLL];
+                ss_fword fw[UNROLL];
                 bool need[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
@@ -417,13 +422,13 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
                     } else {
                         need[u] = ok[u];
                     }
-                    fw[u] = 0ull;
+                    fw[u] = 0;
                     if (need[u]) fw[u] = ld_filter(tv.filter + __umulhi(hl[u], tv.n_filter_words), pol_keep);
                 }
                 bool pass[UNROLL], any = false;
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    uint64_t m = s_pat[hl[u] & (SS_NPAT - 1)];
+                    const ss_fword m = s_pat[hl[u] & (SS_NPAT - 1)];
                     bool hit = need[u] && (fw[u] & m) == m;
                     if (SS_FILTER_PAIRS) {
                         const bool next = __shfl_down_sync(0xFFFFFFFFu, hit, 1);
@@ -625,19 +630,19 @@ __global__ void ss_insert_kernel(const uint64_t *__restrict__ keys, const uint8_
 
 // L2-resident prefilter: every key sets 4 bits of one 64-bit word
 __global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ rec_ok, uint64_t n,
-                                       unsigned long long *__restrict__ filter, uint32_t n_words, uint64_t kmask) {
+                                       ss_fword *__restrict__ filter, uint32_t n_words, uint64_t kmask) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !rec_ok[i] || keys[i] == SS_EMPTY) return;
     uint32_t hh, hl;
 #if SS_FILTER_PAIRS
     const uint64_t pre = keys[i] & (kmask >> 2), suf = keys[i] >> 2;      // first / last k-1 bases
     ss_hash2((uint32_t)pre, (uint32_t)(pre >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
     ss_hash2((uint32_t)suf, (uint32_t)(suf >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
 #else
     ss_hash2((uint32_t)keys[i], (uint32_t)(keys[i] >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), (unsigned long long)ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
 #endif
 }
 
@@ -918,7 +923,7 @@ cudaError_t ss_launch_bin_probe(const ss_bin_view &bv, const uint32_t *n_chunks,
     return cudaGetLastError();
 }
 
-cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, unsigned long long *filter,
+cudaError_t ss_launch_filter_build(const uint64_t *keys, const uint8_t *rec_ok, uint64_t n, ss_fword *filter,
                                    uint32_t n_words, uint64_t kmask, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     ss_filter_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, rec_ok, n, filter, n_words, kmask);
