@@ -20,8 +20,11 @@
  *
  * All functions return SS_OK (0) or an SS_ERR_* code; ss_last_error() gives the message of the
  * calling thread's last failure.  There is NO CPU fallback: ss_init fails with SS_ERR_NO_DEVICE
- * when no sm_100 GPU is usable.  Calls block; handles are not re-entrant (one caller at a time
- * per ss_ctx).  No temp files are written (the reference writes temp_<uuid>.jf/.fa into cwd).
+ * when no sm_100 GPU is usable.  Calls block.  A context and the k-mer sets / read caches made from it carry
+ * per-pass state (statistics, slot counters, scratch vectors, streaming slots): the count / load / reduce entry
+ * points serialise on a per-context lock, so sharing a context between threads is safe but not concurrent --
+ * use one context per thread (or per stream, ss_set_stream) to run passes side by side.  No temp files are
+ * written (the reference writes temp_<uuid>.jf/.fa into cwd).
  */
 #ifndef STRAINSCAN_B200_H
 #define STRAINSCAN_B200_H
@@ -50,6 +53,8 @@ extern "C" {
 typedef struct ss_ctx     ss_ctx;      /* one GPU: streams, staging buffers, scratch */
 typedef struct ss_kmerset ss_kmerset;  /* GPU-resident probe table seeded from a k-mer FASTA */
 typedef struct ss_reads   ss_reads;    /* GPU-resident FASTQ text (the read cache) */
+typedef struct ss_node_index    ss_node_index;     /* GPU-resident CSR node -> record ordinals (kmers/<node>) */
+typedef struct ss_strain_matrix ss_strain_matrix;  /* GPU-resident CSC strain -> rows (all_strains_re.npz) */
 
 typedef struct ss_stats {
     uint64_t text_bytes;      /* FASTQ bytes scanned */
@@ -57,7 +62,7 @@ typedef struct ss_stats {
     uint64_t n_kmers;         /* valid k-windows probed (the unit of work) */
     uint64_t n_hits;          /* probes that found their k-mer */
     uint64_t n_second_probe;  /* probes that needed a second 32-byte sector */
-    double   ms_index;        /* device time: newline index + scan kernels (CUDA events) */
+    double   ms_index;        /* device time: line-index kernel K1 (0 when the read cache was indexed by an earlier pass) */
     double   ms_probe;        /* device time: fused scan/encode/probe/count kernel */
     double   ms_gather;       /* device time: slot -> record-ordinal gather */
     double   ms_h2d;          /* device time of host->device copies issued by this call */
@@ -137,6 +142,11 @@ int ss_reads_from_device(ss_ctx *ctx, void *dev_ptr, size_t len, size_t capacity
 size_t ss_reads_device_capacity(size_t len);
 uint64_t ss_reads_bytes(const ss_reads *reads);
 int ss_reads_free(ss_reads *reads);
+/* The line index of a read cache (line number mod 4 at every 992-byte unit, K1) is built by the first
+ * counting pass over it -- inside that pass, reported as ss_stats.ms_index -- and reused by the later
+ * passes (one per identified cluster, Vote_...:295-296).  This forgets it, so that the next pass pays
+ * for it again: what a one-shot L1 pass costs (used by bench.py for `value`). */
+int ss_reads_drop_index(ss_reads *reads);
 
 /* ---- match + count: replaces `jellyfish count` + `jellyfish dump -c` + the dump parse -------- */
 
@@ -159,7 +169,9 @@ int ss_count_files(ss_ctx *ctx, const ss_kmerset *set, const char *const *paths,
 
 /* L2 adapter on a dense DEVICE vector (after any cross-GPU sum): rows whose raw record is not a
  * dumped key -> 0, count == 1 -> 0 (remove_1, Vote_...:312-322), rows ordered by kid.
- * py_o[n_records] int64 HOST output. */
+ * Row order, one rule everywhere (also l2_shim.kid_row_order): rows follow the FASTA header ids when these are an
+ * exact permutation of 1..n (all_kmer.fasta: ">kid", Build_kmer_sets_...:397-399); any other header layout keeps
+ * FASTA record order.  py_o[n_records] int64 HOST output. */
 int ss_l2_finalize(ss_ctx *ctx, const ss_kmerset *set, const uint32_t *dev_counts, int64_t *py_o);
 
 /* ---- reducers over a dense DEVICE count vector ------------------------------------------------ */
@@ -180,6 +192,24 @@ int ss_node_reduce(ss_ctx *ctx, const ss_kmerset *set, const uint32_t *dev_count
 int ss_strain_reduce(ss_ctx *ctx, const uint64_t *col_ptr, const uint32_t *rows, uint32_t n_strains,
                      const int64_t *y, const uint8_t *row_mask, uint64_t n_rows,
                      uint64_t *total, uint64_t *covered, uint64_t *sum);
+
+/* Persistent forms of the two reducers: the index structure is validated and uploaded ONCE and every reduction
+ * moves only its inputs and its per-node / per-strain outputs.  identify_low_depth.identify_ranks visits every
+ * node twice (identify_low_depth.py:113-132) and Pre_Scan asks for up to ~45 per-strain reductions per cluster
+ * (identify_strains...:241-334), all over the same kmers/<node> lists resp. the same all_strains_re.npz.
+ * ss_node_index_reduce also returns max_count[n_nodes] (may be NULL): with max < 100 the 100x-median outlier trim of
+ * del_outlier (identify.py:106-112) cannot remove anything, so coverage = covered / length needs no host gather.
+ * ss_strain_matrix_reduce: y (int64[n_rows]) and row_mask (uint8[n_rows] or NULL) may be HOST or DEVICE pointers. */
+int ss_node_index_create(ss_ctx *ctx, const uint64_t *node_ptr, const uint32_t *ordinals, uint32_t n_nodes,
+                         ss_node_index **index);
+int ss_node_index_free(ss_node_index *index);
+int ss_node_index_reduce(ss_ctx *ctx, const ss_kmerset *set, const ss_node_index *index, const uint32_t *dev_counts,
+                         uint32_t *length, uint32_t *covered, uint64_t *sum, uint32_t *max_count);
+int ss_strain_matrix_create(ss_ctx *ctx, const uint64_t *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                            uint64_t n_rows, ss_strain_matrix **matrix);
+int ss_strain_matrix_free(ss_strain_matrix *matrix);
+int ss_strain_matrix_reduce(ss_ctx *ctx, ss_strain_matrix *matrix, const int64_t *y, const uint8_t *row_mask,
+                            uint64_t *total, uint64_t *covered, uint64_t *sum);
 
 /* ---- measurement + synthetic workload helpers (bench.py, full-size parity tests) ---------------- */
 

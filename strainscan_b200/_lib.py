@@ -76,6 +76,7 @@ SIGNATURES = {
     "ss_reads_device_capacity": (C.c_size_t, [C.c_size_t]),
     "ss_reads_bytes": (C.c_uint64, [_P]),
     "ss_reads_free": (C.c_int, [_P]),
+    "ss_reads_drop_index": (C.c_int, [_P]),
     "ss_count": (C.c_int, [_P, _P, _P, _P, C.POINTER(Stats)]),
     "ss_count_device": (C.c_int, [_P, _P, _P, _P, C.POINTER(Stats)]),
     "ss_count_host": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), _SIZES, C.c_int, _P, C.POINTER(Stats)]),
@@ -83,6 +84,12 @@ SIGNATURES = {
     "ss_l2_finalize": (C.c_int, [_P, _P, _P, _P]),
     "ss_node_reduce": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, _P, _P, _P]),
     "ss_strain_reduce": (C.c_int, [_P, _P, _P, C.c_uint32, _P, _P, C.c_uint64, _P, _P, _P]),
+    "ss_node_index_create": (C.c_int, [_P, _P, _P, C.c_uint32, _PP]),
+    "ss_node_index_free": (C.c_int, [_P]),
+    "ss_node_index_reduce": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "ss_strain_matrix_create": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint64, _PP]),
+    "ss_strain_matrix_free": (C.c_int, [_P]),
+    "ss_strain_matrix_reduce": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "ss_bench_random_gather": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "ss_synth_read_record_bytes": (C.c_size_t, [C.POINTER(SynthParams)]),
     "ss_synth_db_record_bytes": (C.c_size_t, [C.POINTER(SynthParams)]),

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -52,6 +53,10 @@ static double now_ms() {
 #define SS_NGZ 8                         // BGZF batches in flight on the device
 
 struct ss_ctx {
+    // Per-pass state (statistics, scratch vector, slot counters of the sets, streaming slots) is per context: the
+    // count / load / reduce entry points take this lock, so two threads sharing a context serialise instead of
+    // mixing their counters (one context per thread or per stream is the way to run passes concurrently).
+    std::recursive_mutex mu;
     int device = 0;
     int n_sm = 0;
     cudaDeviceProp prop;
@@ -65,7 +70,7 @@ struct ss_ctx {
     uint32_t *d_chunk_line[SS_NSLOT] = {};
     cudaEvent_t ev_copied[SS_NSLOT] = {}, ev_done[SS_NSLOT] = {};
     uint8_t *h_pinned[SS_NSLOT] = {};            // staging for pageable sources
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_i = nullptr;
     size_t chunk_bytes = SS_CHUNK_DEFAULT, seg_bytes = SS_SEG_DEFAULT;
     // device inflate of BGZF batches (ss_gunzip.cu): compressed staging + member tables, double buffered
     bool device_bgzf = true;
@@ -128,8 +133,9 @@ struct ss_segment {
     uint32_t n_tiles = 0;
     uint32_t *d_tile_line = nullptr;
     bool owns_text = false;
+    bool indexed = false;             // d_tile_line holds the line index (built by the first pass over the segment)
 };
-static uint64_t g_reads_id = 0;
+static std::atomic<uint64_t> g_reads_id{0};
 struct ss_reads {
     ss_ctx *ctx = nullptr;
     std::vector<ss_segment> seg;
@@ -168,7 +174,7 @@ extern "C" int ss_init(int device, ss_ctx **out) {
     SS_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));   // [8..13]: one binned round's scan statistics
     SS_CUDA(cudaMallocHost(&c->h_stats, 8 * sizeof(unsigned long long)));
     SS_CUDA(cudaEventCreate(&c->ev_a)); SS_CUDA(cudaEventCreate(&c->ev_b));
-    SS_CUDA(cudaEventCreate(&c->ev_c)); SS_CUDA(cudaEventCreate(&c->ev_d));
+    SS_CUDA(cudaEventCreate(&c->ev_c)); SS_CUDA(cudaEventCreate(&c->ev_d)); SS_CUDA(cudaEventCreate(&c->ev_i));
     for (int i = 0; i < SS_NSLOT; i++) {
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         SS_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -208,7 +214,7 @@ extern "C" int ss_shutdown(ss_ctx *c) {
     for (int i = 0; i < SS_NPEND; i++) cudaEventDestroy(c->ev_pend[i]);
     cudaFree(c->d_dense); cudaFree(c->d_stats); cudaFreeHost(c->h_stats);
     cudaFree(c->d_bin_keys); cudaFree(c->d_bin_fill); cudaFree(c->d_bin_n); cudaFreeHost(c->h_bin);
-    cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d);
+    cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_c); cudaEventDestroy(c->ev_d); cudaEventDestroy(c->ev_i);
     cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
     delete c;
     return SS_OK;
@@ -396,6 +402,7 @@ static int build_set(ss_ctx *c, const char *text, size_t len, int k, ss_kmerset 
 
 static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out) {
     *out = nullptr;
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     SS_CUDA(cudaSetDevice(c->device));
     const uint64_t n = ps.n;
     std::vector<uint64_t> &keys = ps.keys;
@@ -650,15 +657,33 @@ extern "C" int ss_reads_free(ss_reads *r) {
     return SS_OK;
 }
 
-// pad + index one segment whose text (whole records) is already on the device
+// pad one segment whose text (whole records) is already on the device.  Its line index (K1) is built by the first
+// pass that scans it (ensure_index, inside that pass's timed region) and kept for the later passes.
 static int finish_segment(ss_ctx *c, ss_segment &g) {
     g.n_tiles = (uint32_t)((g.len + SS_TILE - 1) / SS_TILE);
     size_t need = ss_reads_device_capacity(g.len);
     if (g.cap < need) return fail(SS_ERR_ARG, "reads: device buffer capacity too small (see ss_reads_device_capacity)");
     SS_CUDA(cudaMemsetAsync(g.d_text + g.len, '\n', need - g.len, c->stream));
-    SS_CUDA(cudaMalloc(&g.d_tile_line, (uint64_t)(g.n_tiles + 2) * sizeof(uint32_t)));
-    SS_CUDA(ss_launch_index(g.d_text, g.n_tiles, g.d_tile_line, 0, c->n_sm, c->stream));
+    SS_CUDA(cudaMalloc(&g.d_tile_line, ss_index_words(g.n_tiles) * sizeof(uint32_t)));
+    g.indexed = false;
     SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+static int ensure_index(ss_ctx *c, const ss_reads *r, uint32_t *launches) {
+    for (const ss_segment &cg : r->seg) {
+        ss_segment &g = const_cast<ss_segment &>(cg);
+        if (g.indexed || !g.n_tiles) continue;
+        SS_CUDA(ss_launch_index(g.d_text, g.n_tiles, g.d_tile_line, 0, c->n_sm, c->stream));
+        g.indexed = true;
+        if (launches) (*launches)++;
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_reads_drop_index(ss_reads *r) {
+    if (!r) return fail(SS_ERR_ARG, "ss_reads_drop_index: reads is NULL");
+    for (ss_segment &g : r->seg) g.indexed = false;
     return SS_OK;
 }
 
@@ -712,6 +737,7 @@ static int reads_from_vector(ss_ctx *c, const char *data, size_t len, ss_reads *
 
 extern "C" int ss_reads_from_host(ss_ctx *c, const char *const *bufs, const size_t *lens, int n, ss_reads **out) {
     if (!c || !out || (n > 0 && (!bufs || !lens))) return fail(SS_ERR_ARG, "ss_reads_from_host: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     *out = nullptr;
     SS_CUDA(cudaSetDevice(c->device));
     std::vector<char> all;
@@ -817,6 +843,7 @@ static int gz_check(ss_ctx *c, const char *what) {
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     *out = nullptr;
     SS_CUDA(cudaSetDevice(c->device));
     int rc = ensure_source(c);
@@ -947,6 +974,7 @@ extern "C" int ss_ingest_files_host(const char *const *paths, int n_paths, int s
 
 extern "C" int ss_reads_from_device(ss_ctx *c, void *dev_ptr, size_t len, size_t capacity, ss_reads **out) {
     if (!c || !out || (!dev_ptr && len)) return fail(SS_ERR_ARG, "ss_reads_from_device: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     *out = nullptr;
     if (((uintptr_t)dev_ptr & 255u) != 0) return fail(SS_ERR_ARG, "ss_reads_from_device: pointer must be 256-byte aligned");
     SS_CUDA(cudaSetDevice(c->device));
@@ -1069,13 +1097,17 @@ static int binned_round(ss_ctx *c, const ss_kmerset *s, const ss_segment &g, uin
 
 extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *dev_counts, ss_stats *st) {
     if (!c || !s || !r || !dev_counts) return fail(SS_ERR_ARG, "ss_count_device: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     if (s->ctx != c || r->ctx != c) return fail(SS_ERR_ARG, "ss_count_device: handle belongs to another context");
     double t0 = now_ms();
     SS_CUDA(cudaSetDevice(c->device));
     int rc = reset_pass(c, s);
     if (rc) return rc;
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
-    uint32_t launches = 0, n_binned = 0;
+    uint32_t launches = 0, n_binned = 0, index_launches = 0;
+    rc = ensure_index(c, r, &index_launches);           // first pass over these reads: K1 (kept for later passes)
+    if (rc) return rc;
+    SS_CUDA(cudaEventRecord(c->ev_i, c->stream));
     unsigned long long acc[6] = {0, 0, 0, 0, 0, 0};     // scan statistics of the binned rounds (summed on the host)
 
     // ---- direct or binned?  Decided from the first tiles of the pass.
@@ -1179,10 +1211,11 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
         fill_stats(c, st);
         st->text_bytes = r->len;
         float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); st->ms_probe = ms;
+        cudaEventElapsedTime(&ms, c->ev_a, c->ev_i); st->ms_index = index_launches ? ms : 0.0;
+        cudaEventElapsedTime(&ms, c->ev_i, c->ev_b); st->ms_probe = ms;
         cudaEventElapsedTime(&ms, c->ev_b, c->ev_c); st->ms_gather = ms;
         st->probe_launches = launches;
-        st->total_launches = st->probe_launches + (s->n_records ? 1 + (s->n_dup ? 1 : 0) : 0);
+        st->total_launches = st->probe_launches + index_launches + (s->n_records ? 1 + (s->n_dup ? 1 : 0) : 0);
         st->binned_rounds = n_binned;
         st->bins = n_binned ? bv.P : 0;
         st->ms_total = now_ms() - t0;
@@ -1192,6 +1225,7 @@ extern "C" int ss_count_device(ss_ctx *c, const ss_kmerset *s, const ss_reads *r
 
 extern "C" int ss_count(ss_ctx *c, const ss_kmerset *s, const ss_reads *r, uint32_t *counts, ss_stats *st) {
     if (!c || !s || !r || !counts) return fail(SS_ERR_ARG, "ss_count: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     double t0 = now_ms();
     SS_CUDA(cudaSetDevice(c->device));
     int rc = ensure_dense(c, s->n_records);
@@ -1210,7 +1244,7 @@ static int ensure_chunks(ss_ctx *c) {
     uint32_t tiles = (uint32_t)(text_cap / SS_TILE) + 2;
     for (int i = 0; i < SS_NSLOT; i++) {
         SS_CUDA(cudaMalloc(&c->d_chunk[i], cap));
-        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], (uint64_t)(tiles + 2) * sizeof(uint32_t)));
+        SS_CUDA(cudaMalloc(&c->d_chunk_line[i], ss_index_words(tiles) * sizeof(uint32_t)));
     }
     return SS_OK;
 }
@@ -1249,7 +1283,7 @@ static int stream_chunk(ss_ctx *c, const ss_kmerset *s, const char *src, size_t 
                             c->n_sm, c->stream));
     SS_CUDA(cudaEventRecord(c->ev_done[b], c->stream));
     ss.used[b] = true;
-    ss.probe_launches++; ss.total_launches += 3; ss.bytes += n;
+    ss.probe_launches++; ss.total_launches += 2; ss.bytes += n;
     ss.slot = (b + 1) % SS_NSLOT;
     return SS_OK;
 }
@@ -1337,6 +1371,7 @@ static int count_streamed(ss_ctx *c, const ss_kmerset *s, const char *const *buf
 extern "C" int ss_count_host(ss_ctx *c, const ss_kmerset *s, const char *const *bufs, const size_t *lens, int n,
                              uint32_t *counts, ss_stats *st) {
     if (!c || !s || !counts || (n > 0 && (!bufs || !lens))) return fail(SS_ERR_ARG, "ss_count_host: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     if (s->ctx != c) return fail(SS_ERR_ARG, "ss_count_host: set belongs to another context");
     return count_streamed(c, s, bufs, lens, n, counts, st);
 }
@@ -1346,6 +1381,7 @@ extern "C" int ss_count_host(ss_ctx *c, const ss_kmerset *s, const char *const *
 extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const *paths, int n_paths, int shard,
                               int n_shards, uint32_t *counts, ss_stats *st) {
     if (!c || !s || !counts || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_count_files: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     if (s->ctx != c) return fail(SS_ERR_ARG, "ss_count_files: set belongs to another context");
     double t0 = now_ms();
     SS_CUDA(cudaSetDevice(c->device));
@@ -1388,6 +1424,7 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
 
 extern "C" int ss_l2_finalize(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, int64_t *py_o) {
     if (!c || !s || !dev_counts || !py_o) return fail(SS_ERR_ARG, "ss_l2_finalize: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
     SS_CUDA(cudaSetDevice(c->device));
     uint64_t n = s->n_records;
     if (!n) return SS_OK;
@@ -1411,25 +1448,163 @@ struct dev_buf {
     cudaError_t alloc(uint64_t n) { return cudaMalloc(&p, std::max<uint64_t>(n, 1) * sizeof(T)); }
 };
 
+// Persistent device forms of the two index structures the reducers walk: the CSR node -> record ordinals of
+// Tree_database/kmers/<node> (K4) and the CSC strain -> rows of all_strains_re.npz (K5).  Uploaded and validated
+// once; a reduction then moves only its inputs (y, mask) and its few outputs.
+struct ss_node_index {
+    ss_ctx *ctx = nullptr;
+    uint32_t n_nodes = 0;
+    uint64_t nnz = 0;
+    unsigned long long *d_ptr = nullptr, *d_sum = nullptr;
+    uint32_t *d_ord = nullptr, *d_len = nullptr, *d_cov = nullptr, *d_max = nullptr;
+};
+
+struct ss_strain_matrix {
+    ss_ctx *ctx = nullptr;
+    uint32_t n_strains = 0;
+    uint64_t n_rows = 0, nnz = 0;
+    unsigned long long *d_ptr = nullptr, *d_out = nullptr;      // d_out: total | covered | sum
+    uint32_t *d_rows = nullptr;
+    long long *d_y = nullptr;
+    uint8_t *d_mask = nullptr;
+};
+
+extern "C" int ss_node_index_free(ss_node_index *x) {
+    if (!x) return SS_OK;
+    cudaSetDevice(x->ctx->device);
+    cudaFree(x->d_ptr); cudaFree(x->d_sum); cudaFree(x->d_ord); cudaFree(x->d_len); cudaFree(x->d_cov); cudaFree(x->d_max);
+    delete x;
+    return SS_OK;
+}
+
+extern "C" int ss_node_index_create(ss_ctx *c, const uint64_t *node_ptr, const uint32_t *ordinals, uint32_t n_nodes,
+                                    ss_node_index **out) {
+    if (!c || !node_ptr || !out) return fail(SS_ERR_ARG, "ss_node_index_create: NULL argument");
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_nodes; i++)
+        if (node_ptr[i + 1] < node_ptr[i]) return fail(SS_ERR_ARG, "ss_node_index_create: node_ptr is not non-decreasing");
+    const uint64_t nnz = node_ptr[n_nodes] - node_ptr[0];
+    if (nnz && !ordinals) return fail(SS_ERR_ARG, "ss_node_index_create: ordinals is NULL");
+    SS_CUDA(cudaSetDevice(c->device));
+    ss_node_index *x = new ss_node_index();
+    x->ctx = c; x->n_nodes = n_nodes; x->nnz = nnz;
+    const uint64_t nn = std::max<uint32_t>(n_nodes, 1);
+    cudaError_t e = cudaMalloc(&x->d_ptr, (nn + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_sum, nn * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_ord, std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_len, nn * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_cov, nn * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_max, nn * sizeof(uint32_t));
+    if (e == cudaSuccess) {
+        std::vector<unsigned long long> rel(n_nodes + 1);           // offsets relative to ordinals[node_ptr[0]]
+        for (uint32_t i = 0; i <= n_nodes; i++) rel[i] = node_ptr[i] - node_ptr[0];
+        e = cudaMemcpy(x->d_ptr, rel.data(), (n_nodes + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(x->d_ord, ordinals + node_ptr[0], nnz * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { ss_node_index_free(x); return ss_cuda_fail(e, "ss_node_index_create", __FILE__, __LINE__); }
+    *out = x;
+    return SS_OK;
+}
+
+extern "C" int ss_node_index_reduce(ss_ctx *c, const ss_kmerset *s, const ss_node_index *x, const uint32_t *dev_counts,
+                                    uint32_t *length, uint32_t *covered, uint64_t *sum, uint32_t *max_count) {
+    if (!c || !s || !x || !dev_counts || !length || !covered || !sum) return fail(SS_ERR_ARG, "ss_node_index_reduce: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
+    if (x->ctx != c || s->ctx != c) return fail(SS_ERR_ARG, "ss_node_index_reduce: handle belongs to another context");
+    SS_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = x->n_nodes;
+    if (n == 0) return SS_OK;
+    SS_CUDA(ss_launch_node_reduce(dev_counts, s->d_flags, x->d_ptr, x->d_ord, n, s->n_records, x->d_len, x->d_cov, x->d_sum,
+                                  x->d_max, c->stream));
+    SS_CUDA(cudaMemcpyAsync(length, x->d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(covered, x->d_cov, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(sum, x->d_sum, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (max_count) SS_CUDA(cudaMemcpyAsync(max_count, x->d_max, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
 extern "C" int ss_node_reduce(ss_ctx *c, const ss_kmerset *s, const uint32_t *dev_counts, const uint64_t *node_ptr,
                               const uint32_t *ordinals, uint32_t n_nodes, uint32_t *length, uint32_t *covered,
                               uint64_t *sum) {
     if (!c || !s || !dev_counts || !node_ptr || !length || !covered || !sum)
         return fail(SS_ERR_ARG, "ss_node_reduce: NULL argument");
-    SS_CUDA(cudaSetDevice(c->device));
     if (n_nodes == 0) return SS_OK;
-    uint64_t nnz = node_ptr[n_nodes];
-    dev_buf<unsigned long long> d_ptr, d_sum;
-    dev_buf<uint32_t> d_ord, d_len, d_cov;
-    SS_CUDA(d_ptr.alloc(n_nodes + 1)); SS_CUDA(d_sum.alloc(n_nodes)); SS_CUDA(d_ord.alloc(nnz));
-    SS_CUDA(d_len.alloc(n_nodes)); SS_CUDA(d_cov.alloc(n_nodes));
-    SS_CUDA(cudaMemcpyAsync(d_ptr.p, node_ptr, (n_nodes + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    if (nnz) SS_CUDA(cudaMemcpyAsync(d_ord.p, ordinals, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    SS_CUDA(ss_launch_node_reduce(dev_counts, s->d_flags, d_ptr.p, d_ord.p, n_nodes, s->n_records, d_len.p, d_cov.p,
-                                  d_sum.p, c->stream));
-    SS_CUDA(cudaMemcpyAsync(length, d_len.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaMemcpyAsync(covered, d_cov.p, n_nodes * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaMemcpyAsync(sum, d_sum.p, n_nodes * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    ss_node_index *x = nullptr;
+    int rc = ss_node_index_create(c, node_ptr, ordinals, n_nodes, &x);
+    if (rc) return rc;
+    rc = ss_node_index_reduce(c, s, x, dev_counts, length, covered, sum, nullptr);
+    ss_node_index_free(x);
+    return rc;
+}
+
+extern "C" int ss_strain_matrix_free(ss_strain_matrix *m) {
+    if (!m) return SS_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->d_ptr); cudaFree(m->d_out); cudaFree(m->d_rows); cudaFree(m->d_y); cudaFree(m->d_mask);
+    delete m;
+    return SS_OK;
+}
+
+extern "C" int ss_strain_matrix_create(ss_ctx *c, const uint64_t *col_ptr, const uint32_t *rows, uint32_t n_strains,
+                                       uint64_t n_rows, ss_strain_matrix **out) {
+    if (!c || !col_ptr || !out) return fail(SS_ERR_ARG, "ss_strain_matrix_create: NULL argument");
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_strains; i++)
+        if (col_ptr[i + 1] < col_ptr[i]) return fail(SS_ERR_ARG, "ss_strain_matrix_create: col_ptr is not non-decreasing");
+    const uint64_t nnz = col_ptr[n_strains] - col_ptr[0];
+    if (nnz && !rows) return fail(SS_ERR_ARG, "ss_strain_matrix_create: rows is NULL");
+    for (uint64_t i = 0; i < nnz; i++)                            // once per matrix, not per reduction
+        if (rows[col_ptr[0] + i] >= n_rows) return fail(SS_ERR_ARG, "ss_strain_matrix_create: row index out of range");
+    SS_CUDA(cudaSetDevice(c->device));
+    ss_strain_matrix *m = new ss_strain_matrix();
+    m->ctx = c; m->n_strains = n_strains; m->n_rows = n_rows; m->nnz = nnz;
+    const uint64_t ns = std::max<uint32_t>(n_strains, 1);
+    cudaError_t e = cudaMalloc(&m->d_ptr, (ns + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_out, 3 * ns * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_rows, std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_y, std::max<uint64_t>(n_rows, 1) * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_mask, std::max<uint64_t>(n_rows, 1));
+    if (e == cudaSuccess) {
+        std::vector<unsigned long long> rel(n_strains + 1);
+        for (uint32_t i = 0; i <= n_strains; i++) rel[i] = col_ptr[i] - col_ptr[0];
+        e = cudaMemcpy(m->d_ptr, rel.data(), (n_strains + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(m->d_rows, rows + col_ptr[0], nnz * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { ss_strain_matrix_free(m); return ss_cuda_fail(e, "ss_strain_matrix_create", __FILE__, __LINE__); }
+    *out = m;
+    return SS_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
+
+extern "C" int ss_strain_matrix_reduce(ss_ctx *c, ss_strain_matrix *m, const int64_t *y, const uint8_t *row_mask,
+                                       uint64_t *total, uint64_t *covered, uint64_t *sum) {
+    if (!c || !m || !y || !total || !covered || !sum) return fail(SS_ERR_ARG, "ss_strain_matrix_reduce: NULL argument");
+    std::lock_guard<std::recursive_mutex> lock_(c->mu);
+    if (m->ctx != c) return fail(SS_ERR_ARG, "ss_strain_matrix_reduce: handle belongs to another context");
+    SS_CUDA(cudaSetDevice(c->device));
+    const uint32_t n = m->n_strains;
+    if (n == 0) return SS_OK;
+    const long long *d_y = (const long long *)y;                  // y (and the mask) may already live on the device
+    if (!is_device_ptr(y)) {
+        if (m->n_rows) SS_CUDA(cudaMemcpyAsync(m->d_y, y, m->n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        d_y = m->d_y;
+    }
+    const uint8_t *d_mask = row_mask;
+    if (row_mask && !is_device_ptr(row_mask)) {
+        if (m->n_rows) SS_CUDA(cudaMemcpyAsync(m->d_mask, row_mask, m->n_rows, cudaMemcpyHostToDevice, c->stream));
+        d_mask = m->d_mask;
+    }
+    SS_CUDA(ss_launch_strain_reduce(m->d_ptr, m->d_rows, n, d_y, d_mask, m->d_out, m->d_out + n, m->d_out + 2 * (uint64_t)n,
+                                    c->stream));
+    SS_CUDA(cudaMemcpyAsync(total, m->d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(covered, m->d_out + n, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA(cudaMemcpyAsync(sum, m->d_out + 2 * (uint64_t)n, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA(cudaStreamSynchronize(c->stream));
     return SS_OK;
 }
@@ -1438,31 +1613,13 @@ extern "C" int ss_strain_reduce(ss_ctx *c, const uint64_t *col_ptr, const uint32
                                 const int64_t *y, const uint8_t *row_mask, uint64_t n_rows, uint64_t *total,
                                 uint64_t *covered, uint64_t *sum) {
     if (!c || !col_ptr || !y || !total || !covered || !sum) return fail(SS_ERR_ARG, "ss_strain_reduce: NULL argument");
-    SS_CUDA(cudaSetDevice(c->device));
     if (n_strains == 0) return SS_OK;
-    uint64_t nnz = col_ptr[n_strains];
-    for (uint64_t i = 0; i < nnz; i++)
-        if (rows[i] >= n_rows) return fail(SS_ERR_ARG, "ss_strain_reduce: row index out of range");
-    dev_buf<unsigned long long> d_ptr, d_tot, d_cov, d_sum;
-    dev_buf<uint32_t> d_rows;
-    dev_buf<long long> d_y;
-    dev_buf<uint8_t> d_mask;
-    SS_CUDA(d_ptr.alloc(n_strains + 1)); SS_CUDA(d_tot.alloc(n_strains)); SS_CUDA(d_cov.alloc(n_strains));
-    SS_CUDA(d_sum.alloc(n_strains)); SS_CUDA(d_rows.alloc(nnz)); SS_CUDA(d_y.alloc(n_rows));
-    SS_CUDA(cudaMemcpyAsync(d_ptr.p, col_ptr, (n_strains + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    if (nnz) SS_CUDA(cudaMemcpyAsync(d_rows.p, rows, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    if (n_rows) SS_CUDA(cudaMemcpyAsync(d_y.p, y, n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    if (row_mask) {
-        SS_CUDA(d_mask.alloc(n_rows));
-        if (n_rows) SS_CUDA(cudaMemcpyAsync(d_mask.p, row_mask, n_rows, cudaMemcpyHostToDevice, c->stream));
-    }
-    SS_CUDA(ss_launch_strain_reduce(d_ptr.p, d_rows.p, n_strains, d_y.p, row_mask ? d_mask.p : nullptr, d_tot.p,
-                                    d_cov.p, d_sum.p, c->stream));
-    SS_CUDA(cudaMemcpyAsync(total, d_tot.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaMemcpyAsync(covered, d_cov.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaMemcpyAsync(sum, d_sum.p, n_strains * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA(cudaStreamSynchronize(c->stream));
-    return SS_OK;
+    ss_strain_matrix *m = nullptr;
+    int rc = ss_strain_matrix_create(c, col_ptr, rows, n_strains, n_rows, &m);
+    if (rc) return rc;
+    rc = ss_strain_matrix_reduce(c, m, y, row_mask, total, covered, sum);
+    ss_strain_matrix_free(m);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1517,40 +1674,19 @@ extern "C" int ss_synth_reads_device(ss_ctx *c, const ss_synth_params *p, void *
     return SS_OK;
 }
 
-static uint64_t gcd64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
-
 extern "C" int ss_synth_db_host(ss_ctx *c, const ss_synth_params *p, const uint32_t *node_sizes, uint32_t n_nodes,
                                 char *text_out, uint32_t *node_of_record) {
     if (!c || !node_sizes || !text_out) return fail(SS_ERR_ARG, "ss_synth_db_host: NULL argument");
     int rc = check_synth(p);
     if (rc) return rc;
-    if (n_nodes != 2 * p->n_leaves - 1) return fail(SS_ERR_ARG, "ss_synth_db_host: n_nodes must be 2*n_leaves-1");
     SS_CUDA(cudaSetDevice(c->device));
-    // blocks grouped by owner depth
-    uint32_t maxd = ss_synth_max_depth(p->n_leaves);
-    uint32_t n_blocks = p->genome_len / p->block_len;
-    std::vector<std::vector<uint32_t>> by_depth(maxd + 1);
-    for (uint32_t b = 0; b < n_blocks; b++) by_depth[ss_synth_block_depth(p, b)].push_back(b);
-    std::vector<uint32_t> blk_list, blk_off(maxd + 2, 0);
-    for (uint32_t d = 0; d <= maxd; d++) {
-        blk_off[d] = (uint32_t)blk_list.size();
-        blk_list.insert(blk_list.end(), by_depth[d].begin(), by_depth[d].end());
-    }
-    blk_off[maxd + 1] = (uint32_t)blk_list.size();
-    std::vector<unsigned long long> node_off(n_nodes + 1, 0);
-    const uint32_t per_block = p->block_len - p->k + 1;
-    for (uint32_t v = 0; v < n_nodes; v++) {
-        uint32_t d = ss_synth_depth(v);
-        uint64_t avail = (uint64_t)by_depth[d].size() * per_block * 2;
-        if (node_sizes[v] & 1u) return fail(SS_ERR_ARG, "ss_synth_db_host: node sizes must be even (both strands)");
-        if (node_sizes[v] > avail) return fail(SS_ERR_ARG, "ss_synth_db_host: node larger than its owned blocks");
-        node_off[v + 1] = node_off[v] + node_sizes[v];
-    }
-    uint64_t N = node_off[n_nodes];
+    ss_synth_db_layout lay;
+    std::string why = ss_synth_db_layout_build(p, node_sizes, n_nodes, lay);
+    if (!why.empty()) return fail(why == "too many records" ? SS_ERR_UNSUPPORTED : SS_ERR_ARG, "ss_synth_db_host: " + why);
+    const std::vector<unsigned long long> &node_off = lay.node_off;
+    const std::vector<uint32_t> &blk_list = lay.blk_list, &blk_off = lay.blk_off;
+    const uint64_t N = lay.n_records, a = lay.perm_a;
     if (N == 0) return SS_OK;
-    if (N >= (1ull << 32)) return fail(SS_ERR_UNSUPPORTED, "ss_synth_db_host: too many records");
-    uint64_t a = (uint64_t)((double)N * 0.6180339887) | 1ull;
-    while (gcd64(a, N) != 1) a += 2;
     ss_synth_db_plan plan;
     dev_buf<unsigned long long> d_off;
     dev_buf<uint32_t> d_list, d_boff, d_node;

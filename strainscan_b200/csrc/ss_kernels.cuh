@@ -8,6 +8,8 @@
 
 int ss_probe_ctas_per_sm();
 
+// K1: line index of n_tiles (+1) units; `tile_line` must hold ss_index_words(n_tiles) 32-bit words (index + scratch)
+size_t ss_index_words(uint32_t n_tiles);
 cudaError_t ss_launch_index(const uint8_t *text, uint32_t n_tiles, uint32_t *tile_line, uint32_t line_base,
                             int n_sm, cudaStream_t st);
 cudaError_t ss_launch_probe(const uint8_t *text, uint64_t text_len, uint32_t n_tiles, const uint32_t *tile_line,
@@ -40,7 +42,7 @@ cudaError_t ss_launch_l2_finalize(const uint32_t *dense, const uint8_t *flags, c
                                   long long *py_o, cudaStream_t st);
 cudaError_t ss_launch_node_reduce(const uint32_t *dense, const uint8_t *flags, const unsigned long long *node_ptr,
                                   const uint32_t *ordinals, uint32_t n_nodes, uint64_t n_records, uint32_t *length,
-                                  uint32_t *covered, unsigned long long *sum, cudaStream_t st);
+                                  uint32_t *covered, unsigned long long *sum, uint32_t *max_count, cudaStream_t st);
 cudaError_t ss_launch_strain_reduce(const unsigned long long *col_ptr, const uint32_t *rows, uint32_t n_strains,
                                     const long long *y, const uint8_t *row_mask, unsigned long long *total,
                                     unsigned long long *covered, unsigned long long *sum, cudaStream_t st);

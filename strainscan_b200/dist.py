@@ -99,6 +99,9 @@ def reduce_then_remove_1(local_counts, raw_upper, header_ids=None, group=None):
     c = t.cpu().numpy().astype(np.int64)
     c = np.where(np.asarray(raw_upper).astype(bool), c, 0)
     c[c == 1] = 0
-    if header_ids is not None and len(header_ids) and np.all(np.asarray(header_ids) > 0):
-        c = c[np.argsort(np.asarray(header_ids), kind="stable")]
+    if header_ids is not None:
+        from .l2_shim import kid_row_order
+        order = kid_row_order(header_ids)                 # the same rule as remove_1 / ss_l2_finalize
+        if order is not None:
+            c = c[order]
     return c

@@ -145,14 +145,17 @@ class Engine:
         check(self.lib.ss_count_host(self.h, kset.h, arr, ln, len(ptrs), C.c_void_p(int(out_ptr)), C.byref(st)))
         return out, st
 
-    def count_files(self, kset, paths, shard=0, n_shards=1, out=None):
+    def count_files(self, kset, paths, shard=0, n_shards=1, out=None, out_ptr=None):
+        """End to end from files.  The dense vector goes to `out` (host uint32 array) or to `out_ptr` (host or device)."""
         paths = [p for p in ([paths] if isinstance(paths, str) else list(paths)) if p]
         n = kset.n_records
-        if out is None:
-            out = np.zeros(n, dtype=np.uint32)
+        if out_ptr is None:
+            if out is None:
+                out = np.zeros(n, dtype=np.uint32)
+            out_ptr = out.ctypes.data
         st = Stats()
         check(self.lib.ss_count_files(self.h, kset.h, _cstr_array(paths), len(paths), int(shard), int(n_shards),
-                                      C.c_void_p(out.ctypes.data), C.byref(st)))
+                                      C.c_void_p(int(out_ptr)), C.byref(st)))
         return out, st
 
     def l2_finalize(self, kset, dev_ptr):
@@ -188,6 +191,51 @@ class Engine:
                                         C.c_void_p(row_mask.ctypes.data) if row_mask is not None else None,
                                         y.size, C.c_void_p(total.ctypes.data), C.c_void_p(covered.ctypes.data),
                                         C.c_void_p(ssum.ctypes.data)))
+        return total, covered, ssum
+
+    # ---- persistent reducer handles ---------------------------------------------------------
+    def node_index_create(self, node_ptr, ordinals):
+        node_ptr = np.ascontiguousarray(node_ptr, dtype=np.uint64)
+        ordinals = np.ascontiguousarray(ordinals, dtype=np.uint32)
+        h = C.c_void_p()
+        check(self.lib.ss_node_index_create(self.h, C.c_void_p(node_ptr.ctypes.data), C.c_void_p(ordinals.ctypes.data),
+                                            node_ptr.size - 1, C.byref(h)))
+        return NodeIndex(self, h, node_ptr.size - 1)
+
+    def node_index_reduce(self, kset, index, dev_counts_ptr):
+        """(length, covered, sum, max) per node of a NodeIndex over a dense DEVICE count vector (one K4 launch)."""
+        n = index.n_nodes
+        length, covered = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        total, mx = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
+        check(self.lib.ss_node_index_reduce(self.h, kset.h, index.h, C.c_void_p(int(dev_counts_ptr)),
+                                            C.c_void_p(length.ctypes.data), C.c_void_p(covered.ctypes.data),
+                                            C.c_void_p(total.ctypes.data), C.c_void_p(mx.ctypes.data)))
+        return length, covered, total, mx
+
+    def strain_matrix_create(self, col_ptr, rows, n_rows):
+        col_ptr = np.ascontiguousarray(col_ptr, dtype=np.uint64)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        h = C.c_void_p()
+        check(self.lib.ss_strain_matrix_create(self.h, C.c_void_p(col_ptr.ctypes.data), C.c_void_p(rows.ctypes.data),
+                                               col_ptr.size - 1, int(n_rows), C.byref(h)))
+        return (h, col_ptr.size - 1, int(n_rows))
+
+    def strain_matrix_free(self, handle):
+        if self.h and handle[0]:
+            self.lib.ss_strain_matrix_free(handle[0])
+
+    def strain_matrix_reduce(self, handle, y, row_mask=None):
+        h, n, n_rows = handle
+        y = np.ascontiguousarray(y, dtype=np.int64)
+        assert y.size == n_rows
+        if row_mask is not None:
+            row_mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+            assert row_mask.size == n_rows
+        total, covered, ssum = (np.zeros(n, dtype=np.uint64) for _ in range(3))
+        check(self.lib.ss_strain_matrix_reduce(self.h, h, C.c_void_p(y.ctypes.data),
+                                               C.c_void_p(row_mask.ctypes.data) if row_mask is not None else None,
+                                               C.c_void_p(total.ctypes.data), C.c_void_p(covered.ctypes.data),
+                                               C.c_void_p(ssum.ctypes.data)))
         return total, covered, ssum
 
     # ---- measurement / synthetic workload ---------------------------------------------------
@@ -263,11 +311,34 @@ class KmerSet:
             pass
 
 
+class NodeIndex:
+    """Persistent device CSR node -> record ordinals (ss_node_index)."""
+
+    def __init__(self, eng, h, n_nodes):
+        self.eng, self.h, self.n_nodes = eng, h, n_nodes
+
+    def free(self):
+        if self.h:
+            self.eng.lib.ss_node_index_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.eng.h:
+                self.free()
+        except Exception:
+            pass
+
+
 class Reads:
     def __init__(self, eng, h):
         self.eng, self.h = eng, h
         self.n_bytes = int(eng.lib.ss_reads_bytes(h))
         self._keepalive = None
+
+    def drop_index(self):
+        """Forget the line index: the next counting pass rebuilds it (and pays for it) as a first pass does."""
+        check(self.eng.lib.ss_reads_drop_index(self.h))
 
     def free(self):
         if self.h:

@@ -23,12 +23,18 @@ from collections.abc import Mapping, Set
 
 import numpy as np
 
+from ._lib import SS_ERR_NOMEM, StrainScanB200Error
 from .engine import Engine
 
 _ENGINE = None
-_SETS = {}    # (device, fasta path, k, mtime) -> KmerSet
+_SETS = {}    # (device, fasta path, k, mtime) -> KmerSet, least recently used first
 _READS = {}   # (device, paths, mtimes, shard, n_shards) -> Reads     (the read cache for pass 2..n)
+_NODES = {}   # (db_dir, mtime of kmers/) -> {node id: de-duplicated ordinals}; (.., "csr", ids) -> (ptr, ord, NodeIndex)
 _MAX_CACHED_READS = 2
+# GPU tables kept alive: the L1 set (used by every sample) plus the sets of the clusters under work.  vote_strain_L2
+# uses each cluster's set once per run (Vote_...:295-296), and an E. coli-scale table is ~1.8 GB, so the cache is a
+# small LRU instead of growing with the number of identified clusters (SS_MAX_CACHED_SETS to change).
+_MAX_CACHED_SETS = int(os.environ.get("SS_MAX_CACHED_SETS", "4"))
 
 
 def default_engine():
@@ -55,12 +61,28 @@ def _db_cache_path(fasta_path, k):
 
 def cached_kmerset(engine, fasta_path, k):
     key = (engine.device, os.path.abspath(fasta_path), int(k), os.path.getmtime(fasta_path))
-    if key not in _SETS:
-        cache = _db_cache_path(fasta_path, k)
+    if key in _SETS:
+        _SETS[key] = _SETS.pop(key)                      # most recently used last
+        return _SETS[key]
+    while len(_SETS) >= max(1, _MAX_CACHED_SETS):
+        _SETS.pop(next(iter(_SETS)))                     # evict the least recently used table: its device memory is
+                                                         # released when the last reference (a live CountVector?) goes
+    cache = _db_cache_path(fasta_path, k)
+
+    def load():
         if cache:
-            _SETS[key] = engine.kmerset_from_fasta_cached(fasta_path, k, cache)[0]
-        else:
-            _SETS[key] = engine.kmerset_from_fasta(fasta_path, k)
+            return engine.kmerset_from_fasta_cached(fasta_path, k, cache)[0]
+        return engine.kmerset_from_fasta(fasta_path, k)
+
+    try:
+        _SETS[key] = load()
+    except StrainScanB200Error as e:
+        if e.code != SS_ERR_NOMEM and "out of memory" not in str(e):
+            raise
+        import gc
+        _SETS.clear()                                    # device memory is short: drop every cached table and retry once
+        gc.collect()
+        _SETS[key] = load()
     return _SETS[key]
 
 
@@ -89,6 +111,10 @@ def drop_caches():
     for s in _SETS.values():
         s.free()
     _SETS.clear()
+    for v in _NODES.values():
+        if isinstance(v, tuple) and hasattr(v[2], "free"):
+            v[2].free()
+    _NODES.clear()
 
 
 class ValidKmers(Set):
@@ -120,10 +146,11 @@ class ValidKmers(Set):
 class CountVector(Mapping):
     """match_results (identify.py:96-103): {record ordinal: count}, keys = valid ordinals only."""
 
-    def __init__(self, counts, valid_mask, stats=None):
+    def __init__(self, counts, valid_mask, stats=None, kset=None, dev=None, engine=None):
         self.counts = counts          # np.uint32[n_records], dense by ordinal
         self.valid_mask = valid_mask  # np.bool_[n_records]
         self.stats = stats
+        self.kset, self.dev, self.engine = kset, dev, engine   # the same vector on the GPU (torch.int32), for K4
 
     def __getitem__(self, k):
         if not (0 <= k < self.counts.size) or not self.valid_mask[k]:
@@ -153,8 +180,11 @@ def jellyfish_count(fq_path, db_dir, engine=None, k=31):
     eng = engine or default_engine()
     kset = cached_kmerset(eng, os.path.join(db_dir, "kmer.fa"), k)
     reads = cached_reads(eng, fq_path)
-    counts, st = eng.count(kset, reads)
-    return CountVector(counts, kset.valid, st)
+    import torch                                          # owner of the device buffer only
+    dev = torch.empty(max(kset.n_records, 1), dtype=torch.int32, device=torch.device("cuda", eng.device))
+    st = eng.count_device(kset, reads, dev.data_ptr())
+    counts = dev[:kset.n_records].cpu().numpy().view(np.uint32)
+    return CountVector(counts, kset.valid, st, kset=kset, dev=dev, engine=eng)
 
 
 def del_outlier(profile):
@@ -175,12 +205,29 @@ def _parse_ints(line):
     return np.array(line.split(), dtype=np.int64)
 
 
+def _node_cache(db_dir):
+    """Per database: {node id: de-duplicated ordinals of kmers/<node> (None for an empty file)} -- the text of a node
+    list is parsed once per process, not once per match_node call (the tree search visits nodes repeatedly and
+    identify_low_depth.identify_ranks visits every node twice, identify_low_depth.py:113-132)."""
+    kd = os.path.join(db_dir, "kmers")
+    key = (os.path.abspath(db_dir), os.path.getmtime(kd) if os.path.isdir(kd) else 0.0)
+    if key not in _NODES:
+        for old in [k for k in _NODES if k[0] == key[0]]:
+            v = _NODES.pop(old)
+            if isinstance(v, tuple) and hasattr(v[2], "free"):
+                v[2].free()
+        _NODES[key] = {}
+    return key, _NODES[key]
+
+
 def _node_ordinals(db_dir, node_id):
-    with open(os.path.join(db_dir, "kmers", str(node_id)), "r") as f:
-        lines = f.readlines()
-    if len(lines) == 0:
-        return None
-    return np.unique(_parse_ints(lines[0]))   # the reference builds a set
+    _, cache = _node_cache(db_dir)
+    nid = str(node_id)
+    if nid not in cache:
+        with open(os.path.join(db_dir, "kmers", nid), "r") as f:
+            lines = f.readlines()
+        cache[nid] = None if len(lines) == 0 else np.unique(_parse_ints(lines[0]))   # the reference builds a set
+    return cache[nid]
 
 
 def _profile(match_results, d):
@@ -232,9 +279,29 @@ def adjust_profile_gather(match_results, db_dir, node_id, delete_positions, vali
 def node_coverage_all(match_results, db_dir, node_ids, min_valid=1000):
     """Coverage part of identify_ranks (identify_low_depth.py:113-132) for every node at once:
     {node_id: len(k_profile) / length, or -1 when the node has fewer than `min_valid` valid k-mers or an
-    empty list}.  Same numbers as calling match_node_low_depth per node; the per-node vectors are gathers
-    of the GPU-produced dense count vector."""
+    empty list}.  Same numbers as calling match_node_low_depth per node.  With a GPU-backed CountVector the
+    per-node (length, covered, max) come from ONE K4 launch over a persistent CSR of the whole tree
+    (ss_node_index); only nodes whose largest count reaches 100 -- where del_outlier (identify.py:106-112) could
+    remove something -- are re-done with the exact host gather."""
+    node_ids = list(node_ids)
     out = {}
+    if getattr(match_results, "dev", None) is not None and min_valid and node_ids:
+        key, _ = _node_cache(db_dir)
+        ckey = key + ("csr", tuple(str(n) for n in node_ids))
+        if ckey not in _NODES:
+            ptr, ords = load_node_csr(db_dir, node_ids)
+            _NODES[ckey] = (ptr, ords, match_results.engine.node_index_create(ptr, ords))
+        ptr, _, index = _NODES[ckey]
+        length, covered, _, mx = match_results.engine.node_index_reduce(match_results.kset, index, match_results.dev.data_ptr())
+        for i, nid in enumerate(node_ids):
+            if ptr[i + 1] == ptr[i] or length[i] < min_valid:
+                out[nid] = -1
+            elif mx[i] < 100:                                  # median >= 1, so nothing is >= 100 * median
+                out[nid] = int(covered[i]) / int(length[i])
+            else:
+                ln, prof = match_node_low_depth(match_results, db_dir, nid)
+                out[nid] = -1 if ln == 0 else len(prof) / ln
+        return out
     for nid in node_ids:
         length, prof = match_node_low_depth(match_results, db_dir, nid) if min_valid else match_node(match_results, db_dir, nid)
         out[nid] = -1 if length == 0 else len(prof) / length

@@ -5,10 +5,11 @@
            (kid - 1 = record ordinal of C<id>/all_kmer.fasta), absent -> 0, count == 1 -> 0
            (remove_1, Vote_...:312-322).
   stat_cov / cal_cov_all(ix, iy)                library/identify_strains_L2_Enet_Pscan_new_sp.py:33-49
-  get_candidate_arr(ix, iy)                     ...:121-134
-  get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc)        ...:94-108
-        integer reductions on the GPU over the CSC form of all_strains_re.npz (no X.A densification,
-        identify_strains...:200-201); the ratios are formed on the host exactly as the reference does.
+  get_candidate_arr(ix, iy)                     ...:121-134   (ix: strains x rows, as the reference passes npXt)
+  get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc)        ...:94-108   (pXt_tem: strains x rows)
+        integer reductions on the GPU over the CSC form of all_strains_re.npz (K5; the matrix is uploaded once
+        into a persistent device handle); the ratios are formed on the host exactly as the reference does.
+        Orientations are the reference's; a matrix whose row count does not match len(y) raises ValueError.
   optimize_dominat_y(ix, iy)                    ...:136-175
   get_avg_depth(dominat, pX, py)                ...:109-119
   unique_cluster_rows(omatrix, all_cls)         ...:183-197  (`ln`, so that py_u = py * ln)
@@ -36,44 +37,131 @@ def count_cluster(input_fq, fq2, db_dir, ksize, engine=None, return_stats=False)
     return (py_o, st) if return_stats else py_o
 
 
+def kid_row_order(header_ids):
+    """The ONE rule for the row order of py_o, shared with ss_l2_finalize (csrc/ss_api.cu) and dist.py: the reference
+    orders rows by kid (all_kid.pkl, Vote_...:386-388), and the builder writes kid as the FASTA header, a 1..n counter
+    (Build_kmer_sets_...:397-399).  So: rows follow the header ids when they are an exact permutation of 1..n; any
+    other header layout (all ">1" as in kmer.fa, gaps, duplicates) keeps FASTA record order.  Returns the gather
+    index (py_o = c[index]) or None for the identity."""
+    hid = np.asarray(header_ids)
+    n = hid.size
+    if n == 0 or np.array_equal(hid, np.arange(1, n + 1, dtype=hid.dtype)):
+        return None
+    if hid.min() < 1 or hid.max() > n:
+        return None
+    seen = np.zeros(n, dtype=bool)
+    seen[(hid - 1).astype(np.int64)] = True
+    if not seen.all():
+        return None
+    return np.argsort(hid, kind="stable")
+
+
 def remove_1(counts, kset):
     """Vote_...:312-322 + :386-388 on the dense vector: raw string not a dumped key -> 0,
-    count == 1 -> 0, rows sorted by kid."""
+    count == 1 -> 0, rows in kid order (kid_row_order)."""
     c = np.where((kset.flags & SS_REC_RAW_UPPER) != 0, counts, 0).astype(np.int64)
     c[c == 1] = 0
-    hid = kset.header_ids
-    n = c.size
-    if n and not np.array_equal(hid, np.arange(1, n + 1, dtype=np.uint64)):
-        if hid.min() >= 1 and np.unique(hid).size == n:
-            c = c[np.argsort(hid, kind="stable")]
-    return c
+    order = kid_row_order(kset.header_ids)
+    return c if order is None else c[order]
 
 
 class StrainMatrix:
-    """CSC view of the 0/1 strain matrix (all_strains_re.npz, Recls_withR_new.py:110-112)."""
+    """CSC view of the 0/1 strain matrix (all_strains_re.npz, Recls_withR_new.py:110-112), rows x strains.
+    `.T` is the strains x rows orientation the reference's get_candidate_arr / get_remainc take (a view, no copy).
+    With `engine` (or at first use on the GPU) the CSC arrays are uploaded once into a persistent device handle
+    (ss_strain_matrix_create), so that the ~45 reductions Pre_Scan asks for per cluster move only y and the mask."""
 
-    def __init__(self, X):
+    def __init__(self, X, engine=None):
         import scipy.sparse as sp
         X = sp.csc_matrix(X)
         X.eliminate_zeros()
         X.sort_indices()
         self.n_rows, self.n_strains = X.shape
+        self.shape = (self.n_rows, self.n_strains)
         self.col_ptr = X.indptr.astype(np.uint64)
         self.rows = X.indices.astype(np.uint32)
+        self._dev = None
+        self._eng = engine
 
     @classmethod
-    def load(cls, npz_path):
+    def load(cls, npz_path, engine=None):
         import scipy.sparse as sp
-        return cls(sp.load_npz(npz_path))
+        return cls(sp.load_npz(npz_path), engine)
+
+    @property
+    def T(self):
+        return _StrainsByRows(self)
+
+    def device(self, engine):
+        """The persistent device copy (created at first use, freed with the object)."""
+        if self._dev is None or self._eng is not engine:
+            self.free()
+            self._eng = engine
+            self._dev = engine.strain_matrix_create(self.col_ptr, self.rows, self.n_rows)
+        return self._dev
+
+    def free(self):
+        if self._dev is not None:
+            self._eng.strain_matrix_free(self._dev)
+            self._dev = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _StrainsByRows:
+    """StrainMatrix seen as strains x rows (what the reference calls pXt / npXt)."""
+
+    def __init__(self, m):
+        self.m = m
+        self.shape = (m.n_strains, m.n_rows)
+
+    @property
+    def T(self):
+        return self.m
+
+
+def _rows_by_strains(X, y_len, what):
+    """X in the rows x strains orientation (cal_cov_all's ix) as a StrainMatrix; raises when its row count is not len(y)."""
+    m = X if isinstance(X, StrainMatrix) else None
+    if m is None:
+        if isinstance(X, _StrainsByRows):
+            raise ValueError("%s: got a strains x rows matrix where rows x strains is expected" % what)
+        m = StrainMatrix(X)
+    if m.n_rows != y_len:
+        raise ValueError("%s: matrix has %d rows but y has %d entries (wrong orientation?)" % (what, m.n_rows, y_len))
+    return m
+
+
+def _strains_by_rows(X, y_len, what):
+    """X in the strains x rows orientation (get_candidate_arr's ix, get_remainc's pXt_tem) as a rows x strains
+    StrainMatrix; raises when its column count is not len(y)."""
+    if isinstance(X, _StrainsByRows):
+        m = X.m
+    elif isinstance(X, StrainMatrix):
+        raise ValueError("%s: got a rows x strains StrainMatrix where strains x rows is expected (pass X.T)" % what)
+    else:
+        if getattr(X, "ndim", 2) != 2 or X.shape[1] != y_len:
+            raise ValueError("%s: matrix is %s but y has %d entries: expected strains x rows" % (what, getattr(X, "shape", None), y_len))
+        import scipy.sparse as sp
+        m = StrainMatrix(sp.csr_matrix(X).T)          # CSR of strains x rows = CSC of rows x strains
+    if m.n_rows != y_len:
+        raise ValueError("%s: matrix has %d rows but y has %d entries" % (what, m.n_rows, y_len))
+    return m
 
 
 def strain_hits(X, y, row_mask=None, engine=None):
     """Per strain: (total, covered, sum) = (#rows X=1, #rows X=1 and y>1, sum of those y); rows limited
-    to row_mask != 0 when given."""
+    to row_mask != 0 when given.  X: rows x strains (StrainMatrix, scipy sparse or dense)."""
     eng = engine or identify_shim.default_engine()
-    if not isinstance(X, StrainMatrix):
-        X = StrainMatrix(X)
-    return eng.strain_reduce(X.col_ptr, X.rows, np.asarray(y, dtype=np.int64), row_mask)
+    y = np.ascontiguousarray(y, dtype=np.int64)
+    m = _rows_by_strains(X, y.size, "strain_hits")
+    if row_mask is not None and np.asarray(row_mask).size != y.size:
+        raise ValueError("strain_hits: row_mask has %d entries, y has %d" % (np.asarray(row_mask).size, y.size))
+    return eng.strain_matrix_reduce(m.device(eng), y, row_mask)
 
 
 def stat_cov_all(X, y, engine=None):
@@ -85,23 +173,33 @@ def stat_cov_all(X, y, engine=None):
     return out
 
 
-def cal_cov_all(X, y, engine=None):
-    """identify_strains...:44-49."""
-    return [r[0] for r in stat_cov_all(X, y, engine=engine)]
+def cal_cov_all(ix, iy, engine=None):
+    """identify_strains...:44-49; ix: rows x strains, as the reference passes pX."""
+    return [r[0] for r in stat_cov_all(ix, iy, engine=engine)]
 
 
-def get_candidate_arr(X, y, engine=None):
-    """identify_strains...:121-134: (argmax strain, its count) of #rows with X=1 and y>1; ties go to
-    the lowest index, as Python's stable sort with reverse=True keeps first-seen order."""
-    _, covered, _ = strain_hits(X, y, engine=engine)
+def get_candidate_arr(ix, iy, row_mask=None, engine=None):
+    """identify_strains...:121-134: (argmax strain, its count) of #rows with ix=1 and iy>1; ties go to the lowest
+    index, as Python's stable sort with reverse=True keeps first-seen order.  ix: STRAINS x ROWS, as the reference
+    passes npXt (identify_strains...:332) -- dense, scipy sparse, or `StrainMatrix.T` (then `row_mask` stands in
+    for the masking npXt carries: rows with row_mask == 0 are skipped)."""
+    iy = np.asarray(iy)
+    m = _strains_by_rows(ix, iy.size, "get_candidate_arr")
+    _, covered, _ = strain_hits(m, iy, row_mask=row_mask, engine=engine)
     best = int(np.argmax(covered))
     return best, int(covered[best])
 
 
-def get_remainc(dominat, used_kmer, X, py, strain_remainc, engine=None):
-    """identify_strains...:94-108: per strain i != dominat, check/all_k over rows not yet used."""
-    mask = (np.asarray(used_kmer) == 0).astype(np.uint8)
-    total, covered, _ = strain_hits(X, py, row_mask=mask, engine=engine)
+def get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc, engine=None):
+    """identify_strains...:94-108: per strain i != dominat, check/all_k over the rows not yet used.
+    pXt_tem: STRAINS x ROWS, as the reference passes it (identify_strains...:316); used_kmer: 0/1 per row."""
+    py = np.asarray(py)
+    m = _strains_by_rows(pXt_tem, py.size, "get_remainc")
+    used = np.asarray(used_kmer)
+    if used.size != py.size:
+        raise ValueError("get_remainc: used_kmer has %d entries, py has %d" % (used.size, py.size))
+    mask = (used == 0).astype(np.uint8)
+    total, covered, _ = strain_hits(m, py, row_mask=mask, engine=engine)
     for i in range(total.size):
         if i == dominat:
             continue
@@ -113,6 +211,8 @@ def _column_values(X, y, j):
     """y restricted to the rows of strain j (the non-zero part of X[:, j] * y needs nothing else: X is 0/1)."""
     if not isinstance(X, StrainMatrix):
         X = StrainMatrix(X)
+    if X.n_rows != np.asarray(y).size:
+        raise ValueError("matrix has %d rows but y has %d entries (expected rows x strains)" % (X.n_rows, np.asarray(y).size))
     rows = X.rows[int(X.col_ptr[j]):int(X.col_ptr[j + 1])]
     return np.asarray(y)[rows]
 

@@ -375,7 +375,7 @@ def test_bgzf_device_inflate(tmp_path, monkeypatch):
         assert np.array_equal(got.astype(np.uint64), d.cnt) and st.n_reads == 21_000
         got2, st2 = e.count_files(ks, [str(p1), str(p2)])
         assert np.array_equal(got2, got) and st2.n_kmers == st.n_kmers
-        assert st2.total_launches > 3 * st2.probe_launches      # index + probe + gather ... plus the inflate launches
+        assert st2.total_launches > 2 * st2.probe_launches      # index + probe per chunk, gather ... plus the inflate launches
         got3, _ = e.count_files(ks, [str(p1), str(p3)])
         assert np.array_equal(got3, got)
         for n in (2, 3):
@@ -523,3 +523,43 @@ def test_long_reads_vs_oracle(eng, tmp_path):
             assert st.n_kmers == adapters.count_windows([fq], 31), (how, st.n_kmers)
             assert st.n_reads == 78, (how, st.n_reads)
     assert d.cnt.sum() > 10_000
+
+
+def test_line_index_many_blocks_and_rebuild(eng):
+    """K1 (one-pass line index: per-unit newline counts + decoupled look-back scan over 512-unit blocks): text of
+    several thousand units with ragged line lengths, first pass (index built inside it), a second pass (index kept) and
+    a pass after ss_reads_drop_index give the oracle's vector and the same read / k-mer totals."""
+    rng = np.random.default_rng(77)
+    G = util.rand_genome(rng, 200_000)
+    fa = util.make_db(rng, G, 31, 30_000, both_strands=True)
+    fq = util.make_reads(rng, G, 30_000, 150, var_len=True)           # ~9 MB: ~9500 units, 19 index blocks
+    ks = eng.kmerset_from_text(fa, 31)
+    reads = eng.reads_from_host([fq])
+    o = adapters.count_dense(fa, 31, [fq])
+    got1, st1 = eng.count(ks, reads)
+    got2, st2 = eng.count(ks, reads)
+    reads.drop_index()
+    got3, st3 = eng.count(ks, reads)
+    for got, st in ((got1, st1), (got2, st2), (got3, st3)):
+        assert np.array_equal(got.astype(np.uint64), o.cnt)
+        assert st.n_reads == 30_000 and st.n_kmers == adapters.count_windows([fq], 31)
+    assert st1.ms_index > 0 and st2.ms_index == 0 and st3.ms_index > 0
+
+
+def test_host_generator_equals_device_generator(eng):
+    """tools/libss_synth_host.so (what bench.py --impl reference feeds the reference engine) writes the same bytes as the
+    device generators the GPU arm uses."""
+    import torch
+    from strainscan_b200 import synth
+    from tools import synth_host
+    p = synth.default_params(n_leaves=37, seed=5)
+    sizes = synth.node_sizes(p, seed=5)
+    db_d, node_d = eng.synth_db_host(p, sizes, want_nodes=True)
+    db_h, node_h = synth_host.db(p, sizes, want_nodes=True, threads=3)
+    assert np.array_equal(db_d, db_h) and np.array_equal(node_d, node_h)
+    n, first = 20_000, 123_456_789
+    rec = eng.synth_read_record_bytes(p)
+    assert rec == synth_host.read_record_bytes(p)
+    buf = torch.empty(n * rec, dtype=torch.uint8, device="cuda")
+    eng.synth_reads_device(p, buf.data_ptr(), n, first)
+    assert np.array_equal(buf.cpu().numpy(), synth_host.reads(p, n, first, threads=3))
