@@ -104,17 +104,13 @@ def install_b200_reducers():
     identify_low_mem.adjust_profile = make_adjust_profile(identify_low_mem)
     import identify_strains_L2_Enet_Pscan_new_sp as ids          # the module Vote_... imports (library/ on sys.path)
 
-    def cal_cov_all(ix, iy):                                      # ix: rows x strains (identify_strains...:44-49)
-        return l2_shim.cal_cov_all(ix, iy)
-
-    def get_candidate_arr(ix, iy):                                # ix: strains x rows (identify_strains...:121-134)
-        cand, check = l2_shim.get_candidate_arr(ix.T, iy)
+    # the mirrors take the reference's own orientations (cal_cov_all: rows x strains; get_candidate_arr / get_remainc:
+    # strains x rows), so they go in directly -- INTEGRATION.md section 3 as written
+    def get_candidate_arr(ix, iy):
+        cand, check = l2_shim.get_candidate_arr(ix, iy)
         return cand, np.result_type(ix.dtype, np.asarray(iy).dtype).type(check)   # np.sum()'s scalar type is printed
 
-    def get_remainc(dominat, used_kmer, pXt_tem, py, strain_remainc):             # identify_strains...:94-108
-        return l2_shim.get_remainc(dominat, used_kmer, pXt_tem.T, py, strain_remainc)
-
-    ids.cal_cov_all, ids.get_candidate_arr, ids.get_remainc = cal_cov_all, get_candidate_arr, get_remainc
+    ids.cal_cov_all, ids.get_candidate_arr, ids.get_remainc = l2_shim.cal_cov_all, get_candidate_arr, l2_shim.get_remainc
     ids.optimize_dominat_y = l2_shim.optimize_dominat_y           # identify_strains...:136-175, same signature
     ids.get_avg_depth = l2_shim.get_avg_depth                     # identify_strains...:109-119
 

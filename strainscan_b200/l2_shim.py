@@ -156,11 +156,11 @@ def _strains_by_rows(X, y_len, what):
 def strain_hits(X, y, row_mask=None, engine=None):
     """Per strain: (total, covered, sum) = (#rows X=1, #rows X=1 and y>1, sum of those y); rows limited
     to row_mask != 0 when given.  X: rows x strains (StrainMatrix, scipy sparse or dense)."""
-    eng = engine or identify_shim.default_engine()
     y = np.ascontiguousarray(y, dtype=np.int64)
     m = _rows_by_strains(X, y.size, "strain_hits")
     if row_mask is not None and np.asarray(row_mask).size != y.size:
         raise ValueError("strain_hits: row_mask has %d entries, y has %d" % (np.asarray(row_mask).size, y.size))
+    eng = engine or identify_shim.default_engine()
     return eng.strain_matrix_reduce(m.device(eng), y, row_mask)
 
 

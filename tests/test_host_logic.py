@@ -202,3 +202,39 @@ print("ok")
 ''' % (os.path.join(root, "baseline", "shims"), _REF_LIB, root)
     out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-3000:]
+
+
+def test_l2_mirrors_reject_a_transposed_matrix():
+    """the per-strain mirrors take the reference's orientations (cal_cov_all: rows x strains,
+    get_candidate_arr / get_remainc: strains x rows) and raise when the side that must equal len(y) does not --
+    before anything reaches the GPU (so this runs without one)."""
+    rng = np.random.default_rng(0)
+    X = (rng.random((50, 7)) < 0.3).astype(np.int8)          # rows x strains
+    y = rng.poisson(3, 50).astype(np.int64)
+    with pytest.raises(ValueError):
+        l2_shim.get_candidate_arr(X, y)                      # rows x strains where strains x rows is expected
+    with pytest.raises(ValueError):
+        l2_shim.get_remainc(0, np.zeros(50), X, y, {})
+    with pytest.raises(ValueError):
+        l2_shim.cal_cov_all(X.T, y)                          # strains x rows where rows x strains is expected
+    with pytest.raises(ValueError):
+        l2_shim.get_candidate_arr(l2_shim.StrainMatrix(X), y)    # the sparse form: pass X.T
+    with pytest.raises(ValueError):
+        l2_shim.cal_cov_all(l2_shim.StrainMatrix(X).T, y)
+    with pytest.raises(ValueError):
+        l2_shim.optimize_dominat_y(X.T, y)
+    m = l2_shim.StrainMatrix(X)
+    assert m.T.T is m and m.T.shape == (7, 50) and m.shape == (50, 7)
+
+
+def test_kid_row_order_is_one_rule():
+    """Rows follow the FASTA header ids only when these are an exact permutation of 1..n; every other layout keeps
+    FASTA order (l2_shim.remove_1, dist.reduce_then_remove_1 and ss_l2_finalize share this rule)."""
+    f = l2_shim.kid_row_order
+    assert f(np.array([], dtype=np.uint64)) is None
+    assert f(np.arange(1, 9, dtype=np.uint64)) is None                       # identity
+    assert f(np.ones(8, dtype=np.uint64)) is None                            # kmer.fa: all ">1"
+    assert f(np.array([1, 2, 2, 4], dtype=np.uint64)) is None                # duplicates
+    assert f(np.array([2, 3, 4, 5], dtype=np.uint64)) is None                # not 1..n
+    assert f(np.array([0, 1, 2, 3], dtype=np.uint64)) is None
+    assert f(np.array([3, 1, 4, 2], dtype=np.uint64)).tolist() == [1, 3, 0, 2]
