@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=10_000_000, help="c2: reads per GPU")
     ap.add_argument("--leaves", type=int, default=None, help="clusters in the synthetic search tree (c2/c5: 823, c3: 202)")
     ap.add_argument("--pairs", type=int, default=50_000_000, help="c3: read pairs of the sample (two .fq.gz files)")
-    ap.add_argument("--member-reads", type=int, default=800_000, help="c3: reads per gzip member of the generated files")
+    ap.add_argument("--member-reads", type=int, default=200_000, help="c3: reads per gzip member of the generated files")
     ap.add_argument("--gz-level", type=int, default=1, help="c3: deflate level of the generated files")
     ap.add_argument("--sweep", default="1,3,10,30,100,500", help="c5: total reads of every point, in millions")
     ap.add_argument("--sample-reads", type=int, default=3_000_000,

@@ -617,6 +617,7 @@ SS_HD int ssi_gz_parse_header(const uint8_t *p, const uint8_t *end, ssi_gz_heade
 // (zcat would only print a warning after the data is already in the pipe).
 struct ssi_gz_stream {
     const uint8_t *p, *end;     // next member header / end of the file
+    const uint8_t *stop_p;      // optional: standing between two members at or behind this byte, return SSI_OK
     ssi_stream s;
     ssi_tables t;
     int in_member;
@@ -625,7 +626,7 @@ struct ssi_gz_stream {
 };
 
 inline void ssi_gz_init(ssi_gz_stream &g, const uint8_t *data, size_t len) {
-    g.p = data; g.end = data + len; g.in_member = 0; g.n_members = 0; g.total_out = 0;
+    g.p = data; g.end = data + len; g.in_member = 0; g.n_members = 0; g.total_out = 0; g.stop_p = nullptr;
 }
 
 // Fill [*out_pos, out_end).  SSI_OK = the whole file is done, SSI_MORE_OUTPUT = window full (call again
@@ -634,6 +635,7 @@ inline int ssi_gz_read(ssi_gz_stream &g, uint8_t **out_pos, uint8_t *out_end) {
     while (true) {
         if (!g.in_member) {
             if (g.p >= g.end) return g.n_members ? SSI_OK : SSI_ERR_HEADER;
+            if (g.stop_p && g.n_members && g.p >= g.stop_p) return SSI_OK;      // the next member belongs to someone else
             ssi_gz_header h;
             int rc = ssi_gz_parse_header(g.p, g.end, &h);
             if (rc == SSI_ERR_HEADER && g.n_members) return SSI_OK;   // trailing garbage

@@ -173,6 +173,39 @@ int ss_text_source::plain_boundary(const file_map &f, size_t off, size_t *out) {
 
 static size_t bgzf_resync(const uint8_t *p, size_t size, size_t off);
 
+// ---- multi-member gzip: members found by their header ------------------------------------------------
+// Does a gzip member start at byte `at`?  Magic, method, reserved flag bits, a header that parses, and a first
+// deflate block whose header is valid (for a dynamic block: complete code-length code and both Huffman codes).
+static bool gz_member_at(const uint8_t *p, size_t size, size_t at, ssi_tables &t) {
+    if (at + 18 > size || p[at] != 0x1f || p[at + 1] != 0x8b || p[at + 2] != 8 || (p[at + 3] & 0xE0)) return false;
+    ssi_gz_header h;
+    if (ssi_gz_parse_header(p + at, p + size, &h) != SSI_OK) return false;
+    ssi_stream s;
+    pgz_seek(s, p, size, (uint64_t)(at + h.header_len) * 8u);
+    return pgz_block_header(s, t) >= 0;
+}
+
+// first member start in [from, limit), or `size` when there is none (a member needs 18 bytes: header + trailer)
+static size_t gz_next_member(const uint8_t *p, size_t size, size_t from, size_t limit, ssi_tables &t) {
+    limit = std::min(limit, size >= 18 ? size - 17 : 0);
+    for (size_t at = from; at < limit;) {
+        const uint8_t *q = (const uint8_t *)memchr(p + at, 0x1f, limit - at);
+        if (!q) return size;
+        at = (size_t)(q - p);
+        if (gz_member_at(p, size, at, t)) return at;
+        at++;
+    }
+    return size;
+}
+
+// fixed parts of a member-split gzip file: a function of the file size only, so every rank (whatever its thread
+// count) cuts the file the same way
+static size_t gz_split_parts(size_t size) {
+    size_t part = 32u << 20;
+    if (const char *e = getenv("SS_GZ_PART_BYTES")) { long long v = atoll(e); if (v >= (64 << 10)) part = (size_t)v; }
+    return std::max<size_t>(1, std::min<size_t>(4096, size / part));
+}
+
 int ss_text_source::start(const char *const *paths, int n_paths, int shard, int n_shards) {
     if (bufs_.empty()) { err_msg_ = "ingest: init() was not called"; return SS_ERR_ARG; }
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { err_msg_ = "reads: bad shard / n_shards"; return SS_ERR_ARG; }
@@ -204,6 +237,16 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
             ssi_gz_header h;
             f.bgzf = device_bgzf_ && ssi_gz_parse_header(f.map, f.map + f.size, &h) == SSI_OK && h.bgzf_bsize >= h.header_len + 8 &&
                      h.bgzf_bsize <= f.size;
+            // A file of many gzip members (lane files concatenated, block-wise compressors) is split at member
+            // starts: decided from the distance to the second member alone, i.e. identically on every rank.
+            int want_split = 1;
+            if (const char *e = getenv("SS_GZ_SPLIT")) want_split = atoi(e);
+            if (!f.bgzf && want_split && f.size >= (1u << 20)) {
+                ssi_tables *t = new ssi_tables;
+                const size_t m2 = gz_next_member(f.map, f.size, 1, 256u << 20, *t);
+                delete t;
+                f.split = m2 < f.size && (want_split == 2 || f.size / m2 >= 4 * (size_t)n_shards);
+            }
         }
         if (f.size) {   // dialect from the head of the text: FASTA and wrapped FASTQ are rewritten on the host (ss_fastx.h)
             std::vector<uint8_t> head(SS_INGEST_HIST + (64u << 10));
@@ -248,9 +291,11 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
         if (f.bgzf) {
             // members inflate independently: cut the file into parts at member starts (found by their
             // 16-byte BGZF header signature and confirmed by walking the chain), one producer per part
-            size_t part_min = 4 * chunk_bytes_;
+            // (part size is a constant, not a function of the thread count: with several ranks the batches are dealt
+            // by part and batch number, and every rank must cut the file the same way)
+            size_t part_min = 128u << 20;
             if (const char *e = getenv("SS_BGZF_PART_BYTES")) { long long v = atoll(e); if (v >= (256 << 10)) part_min = (size_t)v; }
-            int parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads_, f.size / (part_min + 1) + 1));
+            int parts = (int)std::max<size_t>(1, std::min<size_t>(4096, f.size / (part_min + 1) + 1));
             size_t prev = 0;
             for (int pi = 1; pi <= parts; pi++) {
                 size_t b = pi == parts ? f.size : bgzf_resync(f.map, f.size, (size_t)((unsigned __int128)f.size * pi / parts));
@@ -259,6 +304,20 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
                     jobs_.push_back(j);
                 }
                 prev = std::max(prev, b);
+            }
+            gz_bytes_ += f.size;
+            continue;
+        }
+        if (f.gz && f.split) {
+            // fixed parts; rank r owns the members that START in parts [P r / N, P (r + 1) / N)
+            const size_t P = gz_split_parts(f.size);
+            const size_t p_lo = P * (size_t)shard_ / (size_t)n_shards_, p_hi = P * ((size_t)shard_ + 1) / (size_t)n_shards_;
+            for (size_t pi = p_lo; pi < p_hi; pi++) {
+                job j; j.file = (int)fi;
+                j.lo = (size_t)((unsigned __int128)f.size * pi / P);
+                j.hi = pi + 1 == P ? f.size : (size_t)((unsigned __int128)f.size * (pi + 1) / P);
+                j.first_of_file = (pi == 0);
+                if (j.hi > j.lo) jobs_.push_back(j);
             }
             gz_bytes_ += f.size;
             continue;
@@ -366,6 +425,7 @@ void ss_text_source::worker() {
         const file_map &f = files_[(size_t)j.file];
         if (f.normalize) run_normalize(j);
         else if (f.bgzf) run_bgzf(j);
+        else if (f.gz && f.split) run_gz_members(j);
         else if (f.gz) {
             // an ordinary gzip stream: decoded by several threads per round when cores are to spare (ss_pgz.cuh)
             int t = std::max(1, n_threads_ / std::max(1, n_gz_jobs_));
@@ -444,53 +504,138 @@ void ss_text_source::run_plain(const job &j) {
     }
 }
 
+// One thread decodes the stream; the text goes through the same stream_writer as the parallel decoder's, so both
+// cut the stream into the SAME chunks (filled exactly to the chunk size, cut at the last record start): the
+// round-robin dealing of a stream that every rank decodes does not depend on which decoder a rank picked.
 void ss_text_source::run_gz(const job &j) {
     const file_map &f = files_[(size_t)j.file];
     ssi_gz_stream *g = new ssi_gz_stream;
     ssi_gz_init(*g, f.map, f.size);
-    ss_chunk *c = acquire();
-    if (!c) { delete g; return; }
-    size_t fill = 0;
-    uint64_t chunk_idx = 0;
-    bool first = true;
+    stream_writer w;
+    w.src = this; w.j = &j; w.fill_threads = 1;
+    const size_t win = 4u << 20;
+    std::vector<uint8_t> buf(SS_INGEST_HIST + win + 2 * SSI_OUT_SLACK);
+    uint8_t *text = buf.data() + SS_INGEST_HIST;
     while (true) {
-        uint8_t *pos = c->text + fill;
-        int rc = ssi_gz_read(*g, &pos, c->text + c->cap);
-        fill = (size_t)(pos - c->text);
+        uint8_t *pos = text;
+        int rc = ssi_gz_read(*g, &pos, text + win + 2 * SSI_OUT_SLACK);
+        const size_t got = (size_t)(pos - text);
         if (rc < 0) {
-            release(c);
+            w.abandon();
             const char *why = rc == SSI_ERR_TRUNC ? "unexpected end of file" : rc == SSI_ERR_HEADER ? "not in gzip format"
                               : rc == SSI_ERR_SIZE ? "length error" : "invalid compressed data";
             fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why);
             break;
         }
-        const bool last = rc == SSI_OK;
-        if (first) {
-            std::string m;
-            int hrc = check_head(c->text, ss_trim_tail((const char *)c->text, fill), f.path, m);
-            if (hrc) { release(c); fail(hrc, m); break; }
-            first = false;
+        if (got && !w.append(got, [text](uint8_t *dst, size_t off, size_t len) { memcpy(dst, text + off, len); })) break;
+        if (rc == SSI_OK) { w.finish(); break; }
+        // keep the last 32 KiB in front of the window for the matches of the next round
+        if (got >= SS_INGEST_HIST) memcpy(text - SS_INGEST_HIST, pos - SS_INGEST_HIST, SS_INGEST_HIST);
+        else { memmove(text - SS_INGEST_HIST, text - SS_INGEST_HIST + got, SS_INGEST_HIST - got); memcpy(text - got, text, got); }
+    }
+    delete g;
+}
+
+// Member-split mode: this job owns the gzip members that START in [j.lo, j.hi) of the file.  They are decoded one
+// after the other straight into the chunk buffers (32 KiB of history carried from chunk to chunk); all chunks are
+// this rank's.  Members need not hold whole records.  The same rule as for BGZF parts settles who owns what: the
+// text of a part's first member belongs to the PREVIOUS part up to the first record start behind the member's first
+// byte, so the owner of a part drops that head and, at the other end, decodes on into the next part's first member
+// until it has seen that record start (same search, same bytes: both owners agree without talking to each other).
+// Checked, loudly: the member the job stops in front of is what the next part's owner will find as its first.
+void ss_text_source::run_gz_members(const job &j) {
+    const file_map &f = files_[(size_t)j.file];
+    ssi_tables *tabs = new ssi_tables;
+    const size_t start = j.lo == 0 ? 0 : gz_next_member(f.map, f.size, j.lo, j.hi, *tabs);
+    if (start >= j.hi) { delete tabs; return; }                       // no member starts in this part
+    ssi_gz_stream *g = new ssi_gz_stream;
+    ssi_gz_init(*g, f.map + start, f.size - start);
+    g->stop_p = f.map + j.hi;
+    ss_chunk *c = acquire();
+    if (!c) { delete g; delete tabs; return; }
+    auto why = [](int rc) {
+        return rc == SSI_ERR_TRUNC ? "unexpected end of file" : rc == SSI_ERR_HEADER ? "not in gzip format"
+               : rc == SSI_ERR_SIZE ? "length error" : "invalid compressed data";
+    };
+    size_t fill = 0;
+    size_t drop = j.lo == 0 ? 0 : (size_t)-1;        // bytes of the first chunk that belong to the previous part (-1: not known yet)
+    size_t mark = (size_t)-1;                        // offset in the current chunk where the NEXT part's first member begins
+    bool file_end = false, done = false;
+    while (!done) {
+        // decode: up to the part boundary first (stop_p), then little by little into the next part's first member
+        uint8_t *pos = c->text + fill;
+        uint8_t *lim = mark == (size_t)-1 ? c->text + c->cap : std::min(c->text + c->cap, pos + (64u << 10) + 2 * SSI_OUT_SLACK);
+        int rc = ssi_gz_read(*g, &pos, lim);
+        fill = (size_t)(pos - c->text);
+        if (rc < 0) { release(c); fail(SS_ERR_IO, "inflate failed on " + f.path + ": " + why(rc)); break; }
+        size_t cut = 0;
+        bool emit_all = false;
+        if (rc == SSI_OK && mark == (size_t)-1) {
+            // the decoder stands between two members at or behind j.hi, at the file end, or in front of bytes that are
+            // no member (zcat: "trailing garbage ignored" -- the same thing here only if no member follows them)
+            const size_t end = (size_t)(g->p - f.map);
+            file_end = end >= f.size;
+            if (!file_end && !gz_member_at(f.map, f.size, end, *tabs)) {
+                if (gz_next_member(f.map, f.size, end + 1, f.size, *tabs) < f.size) {
+                    release(c); fail(SS_ERR_IO, f.path + ": bytes that are no gzip member are followed by more members; set SS_GZ_SPLIT=0"); break;
+                }
+                file_end = true;
+            }
+            if (!file_end && (end < j.hi || gz_next_member(f.map, f.size, j.hi, end + 1, *tabs) != end)) {
+                release(c); fail(SS_ERR_IO, f.path + ": gzip member boundaries are ambiguous (a member header pattern inside compressed data); set SS_GZ_SPLIT=0"); break;
+            }
+            if (file_end) { emit_all = true; }
+            else { mark = fill; g->stop_p = nullptr; continue; }      // go on into the next part's first member
         }
-        size_t cut = cut_chunk(c, fill, last);
+        if (mark != (size_t)-1 && !emit_all) {
+            // looking for the first record start behind the first byte of the next part's first member
+            size_t r = ss_find_record_start((const char *)c->text, fill, mark + 1);
+            if (r < fill) { cut = r; done = true; }
+            else if (rc == SSI_OK) { file_end = true; emit_all = true; }             // the file ends before another record starts
+            else if (fill + (64u << 10) + 4 * SSI_OUT_SLACK <= c->cap) continue;      // decode some more into this chunk
+        }
+        if (emit_all) {
+            cut = ss_trim_tail((const char *)c->text, fill);
+            if (cut) c->text[cut++] = '\n';
+            done = true;
+        }
         ss_chunk *c2 = nullptr;
-        if (!last) {
-            if (cut == 0) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); break; }
+        if (!done) {                                                   // chunk full: cut at the last record start, carry the tail
+            cut = cut_chunk(c, fill, false);
+            if (cut == 0) {
+                release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); break;
+            }
             c2 = acquire();
             if (!c2) { release(c); break; }
-            // carry the tail (the bytes after the cut) and keep 32 KiB of history in front of the point
-            // where decoding continues
             size_t tail = fill - cut, h = std::min(fill, tail + (size_t)SS_INGEST_HIST);
             memcpy(c2->text + tail - h, c->text + fill - h, h);
+            if (mark != (size_t)-1) {
+                if (mark >= cut) mark -= cut;                          // the boundary member begins in the carried tail
+                else { release(c); release(c2); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
+            }
             fill = tail;
         }
-        // gzip streams cannot be range-split: every rank decodes the whole stream and keeps its chunks
-        if ((chunk_idx + (uint64_t)j.file) % (uint64_t)n_shards_ == (uint64_t)shard_) { c->len = cut; emit(c); }
-        else release(c);
-        chunk_idx++;
-        if (last) break;
+        // the head of the job's first chunk belongs to the previous part
+        size_t off = 0;
+        if (j.lo == 0 && drop == 0) {                                  // the file's first chunk: is this FASTQ at all?
+            std::string m;
+            int hrc = check_head(c->text, ss_trim_tail((const char *)c->text, cut), f.path, m);
+            if (hrc) { release(c); if (c2) release(c2); fail(hrc, m); break; }
+            drop = 1;                                                  // checked
+        }
+        if (drop == (size_t)-1) {
+            off = ss_find_record_start((const char *)c->text, cut, 1);
+            if (off >= cut && !done) { release(c); if (c2) release(c2); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
+            off = std::min(off, cut);
+            drop = off;
+        }
+        if (off) memmove(c->text, c->text + off, cut - off);
+        c->len = cut - off;
+        emit(c);
         c = c2;
     }
     delete g;
+    delete tabs;
 }
 
 // ---------------------------------------------------------------------------------------------

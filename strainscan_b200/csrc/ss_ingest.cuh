@@ -69,8 +69,9 @@ public:
     int init(size_t chunk_bytes, int n_buffers, int n_threads, bool pinned = true, bool device_bgzf = false,
              size_t bgzf_out_cap = 0);
     // Start producing shard `shard` of `n_shards` of the given files.  Plain files are split into
-    // record-aligned byte ranges (one range per rank and producer); gzip streams are decoded whole by
-    // every rank and their chunks are dealt round-robin.
+    // record-aligned byte ranges (one range per rank and producer); multi-member gzip files are split at
+    // member starts (fixed file parts, every member decoded by exactly one rank); a single gzip stream is
+    // decoded whole by every rank and its chunks (always cut the same way) are dealt round-robin.
     int start(const char *const *paths, int n_paths, int shard, int n_shards);
     ss_chunk *next();              // blocks; nullptr when everything was delivered or on error
     void release(ss_chunk *c);     // the buffer may be refilled (call once the H2D copy has completed)
@@ -83,12 +84,13 @@ public:
     bool ready() const { return !bufs_.empty(); }
 
 private:
-    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false, bgzf = false, normalize = false; };
+    struct file_map { int fd = -1; const uint8_t *map = nullptr; size_t size = 0; std::string path; bool gz = false, bgzf = false, normalize = false, split = false; };
     struct job { int file = 0; size_t lo = 0, hi = 0; bool first_of_file = false; };
 
     void worker();
     void run_plain(const job &j);
     void run_gz(const job &j);
+    void run_gz_members(const job &j);
     void run_gz_parallel(const job &j, int threads, size_t span);
     void run_bgzf(const job &j);
     void run_normalize(const job &j);

@@ -385,3 +385,81 @@ def test_long_records_cut_with_a_widening_window(tmp_path):
     with pytest.raises(_lib.StrainScanB200Error) as ei:
         ingest([str(p)], chunk=1 << 18, threads=2)
     assert ei.value.code == 4 and "record boundary" in str(ei.value)
+
+
+def _members(fq, sizes, level=6):
+    out, i = [], 0
+    for n in sizes:
+        out.append(gzip.compress(fq[i:i + n], level))
+        i += n
+    assert i >= len(fq)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+@pytest.mark.parametrize("n_shards", [1, 2, 3, 8])
+def test_multi_member_gzip_is_split_at_member_starts(tmp_path, monkeypatch, aligned, n_shards):
+    """A file of many gzip members (what `cat lane*.fq.gz` or a block-wise compressor writes) is cut into fixed parts and
+    every member is decoded by exactly one shard; members need not hold whole records (a record that straddles a part
+    boundary goes to the earlier part, as for BGZF).  SS_GZ_SPLIT=2 forces the mode on this small file."""
+    rng = np.random.default_rng(31 + n_shards)
+    g = util.rand_genome(rng, 60_000)
+    fq = util.make_reads(rng, g, 24_000, read_len=150, var_len=True)          # ~7 MB
+    if aligned:                                                                 # members = whole records
+        starts = [m.start() for m in __import__("re").finditer(rb"(?m)^@read", fq)]
+        cuts = [starts[i] for i in range(0, len(starts), 700)] + [len(fq)]
+        sizes = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+    else:                                                                       # arbitrary byte boundaries, some tiny members
+        sizes, left = [], len(fq)
+        while left > 0:
+            n = int(rng.choice([17, 300, 40_000, 130_001, 260_000]))
+            sizes.append(min(n, left)); left -= sizes[-1]
+    p = str(tmp_path / "mm.fq.gz")
+    open(p, "wb").write(_members(fq, sizes, level=int(rng.choice([1, 6]))))
+    monkeypatch.setenv("SS_GZ_SPLIT", "2")
+    monkeypatch.setenv("SS_GZ_PART_BYTES", str(256 << 10))                      # ~12 parts
+    for threads in (1, 4):                                                      # the cut does not depend on the thread count
+        parts = [ingest([p], s, n_shards, threads=threads)[0] for s in range(n_shards)]
+        assert sum(len(x) for x in parts) == len(fq)
+        assert records(b"".join(parts)) == records(fq)
+        if n_shards in (2, 3):
+            assert sum(1 for x in parts if x) == n_shards
+        if threads == 1:
+            first = parts
+        else:
+            assert [records(x) for x in parts] == [records(x) for x in first]
+    monkeypatch.setenv("SS_GZ_SPLIT", "0")                                      # the whole-stream decoder gives the same reads
+    assert records(b"".join(ingest([p], s, n_shards)[0] for s in range(n_shards))) == records(fq)
+
+
+def test_multi_member_gzip_odd_shapes(tmp_path, monkeypatch):
+    """Empty members, trailing garbage, a missing final newline, a lone huge member among small ones, and a header-like
+    byte pattern inside the text of a stored block."""
+    rng = np.random.default_rng(5)
+    g = util.rand_genome(rng, 30_000)
+    fq = util.make_reads(rng, g, 9000, read_len=150)
+    monkeypatch.setenv("SS_GZ_SPLIT", "2")
+    monkeypatch.setenv("SS_GZ_PART_BYTES", str(128 << 10))
+    n = len(fq)
+    third = fq.index(b"\n@read", n // 3) + 1
+    blobs = {
+        "empties": gzip.compress(fq[:third]) + gzip.compress(b"") + gzip.compress(b"") + gzip.compress(fq[third:]),
+        "garbage": gzip.compress(fq[:third]) + gzip.compress(fq[third:]) + b"\0\0\0\0not a member at all",
+        "no_final_newline": gzip.compress(fq[:third]) + gzip.compress(fq[third:-1]),
+        "one_big_member": gzip.compress(fq[:2000]) + gzip.compress(fq[2000:n - 3000], 1) + gzip.compress(fq[n - 3000:]),
+        # stored blocks keep the text verbatim: a gzip magic inside it must not be taken for a member
+        "magic_in_stored": gzip.compress(fq[:third], 0) + gzip.compress(fq[third:], 0),
+    }
+    want = records(fq)
+    for name, blob in blobs.items():
+        p = str(tmp_path / (name + ".fq.gz"))
+        open(p, "wb").write(blob)
+        for n_shards in (1, 3):
+            got = b"".join(ingest([p], s, n_shards)[0] for s in range(n_shards))
+            assert records(got) == want, name
+    bad = gzip.compress(fq[:third]) + b"junk junk junk junk junk" + gzip.compress(fq[third:])
+    p = str(tmp_path / "junk_between.fq.gz")
+    open(p, "wb").write(bad)
+    with pytest.raises(_lib.StrainScanB200Error):
+        for s in range(3):
+            ingest([p], s, 3)
