@@ -132,6 +132,15 @@ int ss_fastq_shard_range(const char *buf, size_t len, int shard, int n_shards, s
  * into `out` (chunk order is arbitrary; every chunk holds whole records).  out may be NULL to size. */
 int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n_shards, size_t chunk_bytes,
                          int n_threads, char *out, size_t out_cap, size_t *out_len, uint32_t *n_chunks);
+/* Host-only helper (no GPU needed): the pipeline that inflates ORDINARY gzip streams on the device (block starts found
+ * for pieces of `piece_bytes` compressed bytes, each piece decoded with an unknown window into marker symbols, pieces
+ * stitched by exact block-boundary match, windows resolved in order; strainscan_b200/csrc/ss_dgz.cuh) run on the CPU with
+ * the same source, for tests against zlib.  Decodes the members that start in [first_member, stop_member_at) of the
+ * compressed bytes.  stats4 (may be NULL): pieces found, pieces used, batches, members.  Replaces the `zcat` of
+ * identify.py:82 like ss_ingest_files_host does. */
+int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
+                        uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, char *out, size_t out_cap,
+                        size_t *out_len, size_t *stopped_at, uint64_t *stats4);
 /* Same from in-memory FASTQ text (each buffer = one file's uncompressed contents). */
 int ss_reads_from_host(ss_ctx *ctx, const char *const *bufs, const size_t *lens, int n_bufs,
                        ss_reads **reads);

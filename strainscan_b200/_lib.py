@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstrainscan_b200.so")
+# SS_LIB_PATH: another build of the SAME library (tools/build_variant.sh, A/B runs of compile-time knobs); never a fallback
+LIB_PATH = os.environ.get("SS_LIB_PATH") or os.path.join(_HERE, "libstrainscan_b200.so")
 
 SS_OK = 0
 SS_ERR_NO_DEVICE, SS_ERR_CUDA, SS_ERR_IO, SS_ERR_FORMAT, SS_ERR_ARG, SS_ERR_NOMEM, SS_ERR_UNSUPPORTED = range(1, 8)
@@ -71,6 +72,8 @@ SIGNATURES = {
     "ss_fastq_shard_range": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_int, _SIZES, _SIZES]),
     "ss_ingest_files_host": (C.c_int, [_CSTRS, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, C.c_size_t, _SIZES,
                                        C.POINTER(C.c_uint32)]),
+    "ss_dgz_inflate_host": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, _P,
+                                      C.c_size_t, _SIZES, _SIZES, C.POINTER(C.c_uint64)]),
     "ss_reads_from_host": (C.c_int, [_P, _CSTRS, _SIZES, C.c_int, _PP]),
     "ss_reads_from_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _PP]),
     "ss_reads_device_capacity": (C.c_size_t, [C.c_size_t]),

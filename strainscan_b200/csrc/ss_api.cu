@@ -4,6 +4,8 @@
 // Replaces the process/file protocol around library/jellyfish-linux at
 //   library/identify.py:73-103, library/identify_low_mem.py:67-90, library/identify_low_depth.py:46-74,
 //   library/Vote_Strain_L2_Lasso_new_sp.py:354-403.
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -24,6 +26,7 @@
 #include "ss_synth.cuh"
 #include "ss_inflate.cuh"
 #include "ss_fastx.h"
+#include "ss_dgz_host.h"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -451,8 +454,12 @@ static int build_from_parsed(ss_ctx *c, int k, parsed_set &ps, ss_kmerset **out)
     }
     SS_TRY(ss_launch_insert(d_keys, d_ok, n, (unsigned long long *)s->d_buckets, s->n_buckets, s->d_slot_of, d_last,
                             d_nd, c->stream));
-    {   // L2-resident prefilter for tables that cannot live in L2 themselves ("filter")
-        double bits_per_key = 16.0, max_mb = 48.0, min_table_mb = 32.0;
+    {   // L2-resident prefilter.  First built only for tables that cannot live in L2 themselves; but a k-mer that is
+        // not in the set is also cheaper to turn away with one 4-byte filter load than with a 32-byte bucket load and
+        // four 64-bit compares when the table does sit in L2 (11 MB cluster set, 1.6 % hits: 7.6 ms without, DESIGN.md
+        // section 4), so every set of more than a few thousand k-mers gets one
+        double bits_per_key = 16.0, max_mb = 48.0, min_table_mb = 0.25;
+        if (const char *e = getenv("SS_FILTER_MIN_TABLE_MB")) { double v = atof(e); if (v >= 0) min_table_mb = v; }
         int force = -1;
         if (const char *e = getenv("SS_FILTER")) force = atoi(e);
         if (const char *e = getenv("SS_FILTER_BITS")) { double v = atof(e); if (v >= 4 && v <= 64) bits_per_key = v; }
@@ -761,7 +768,8 @@ static int ensure_source(ss_ctx *c) {
     unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     int threads = (int)std::min(12u, std::max(2u, hw > 4 ? hw - 4 : 2u));   // measured: 8 -> 21-30, 12 -> 35 GB/s of plain text
     if (const char *e = getenv("SS_INGEST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) threads = v; }
-    int rc = c->src->init(c->chunk_bytes, threads + 3, threads, true, c->device_bgzf, c->bgzf_out_cap);
+    // one buffer per producer, the copies the consumer may have in flight (released as they complete), and slack
+    int rc = c->src->init(c->chunk_bytes, threads + 3 + SS_NPEND, threads, true, c->device_bgzf, c->bgzf_out_cap);
     if (rc) return fail(rc, c->src->error());
     return SS_OK;
 }
@@ -774,6 +782,8 @@ struct pending_ring {
     explicit pending_ring(ss_ctx *ctx) : c(ctx) {}
     // call right after the copy of `ch` was issued on `st`
     cudaError_t push(ss_chunk *ch, cudaStream_t st) {
+        for (int i = 0; i < SS_NPEND; i++)              // hand back every buffer whose copy has completed by now
+            if (chunk[i] && i != at && cudaEventQuery(c->ev_pend[i]) == cudaSuccess) { c->src->release(chunk[i]); chunk[i] = nullptr; }
         if (chunk[at]) {
             cudaError_t e = cudaEventSynchronize(c->ev_pend[at]);
             if (e != cudaSuccess) return e;
@@ -840,6 +850,246 @@ static int gz_check(ss_ctx *c, const char *what) {
     return SS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ordinary gzip read files inflated on the device (ss_dgz.cu)
+// ---------------------------------------------------------------------------------------------
+// A .gz read file that is not blocked gzip: the compressed bytes are uploaded as they are (3-4x fewer than the text
+// cross PCIe) and inflated by thousands of decoders at once (block starts found per 128 KiB piece, marker symbols for
+// the unknown window, exact stitching).  Replaces the `zcat a b |` of identify.py:82 / Vote_...:359,367, which the host
+// threads of ss_ingest.cu otherwise stand in for.  With several ranks a file of many members is split at member
+// starts exactly as ss_ingest.cu splits it (same parts, same ownership of the record that straddles a boundary);
+// a single-member file is left to the host path (every rank decodes it, chunks dealt round-robin).
+struct dgz_file {
+    std::string path;
+    int fd = -1;
+    const uint8_t *map = nullptr;
+    size_t size = 0;
+    size_t lo = 0, hi = 0;            // members that START in [lo, hi) are mine
+    size_t first_member = 0;          // the first of them (== size: none)
+    size_t up_hi = 0;                 // compressed bytes [first_member, up_hi) are uploaded
+    void close_map() {
+        if (map) munmap((void *)map, size);
+        if (fd >= 0) close(fd);
+        map = nullptr; fd = -1;
+    }
+};
+
+static bool dgz_enabled() {
+    const char *e = getenv("SS_DGZ");
+    return !e || atoi(e) != 0;
+}
+
+// Does `path` take the device gzip path for this shard?  On true the file stays mapped in `df`.
+static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, dgz_file &df) {
+    if (!dgz_enabled() || !c->device_bgzf) return false;
+    df = dgz_file();
+    df.path = path;
+    df.fd = open(path, O_RDONLY);
+    if (df.fd < 0) return false;                                   // the text source reports the error
+    struct stat st;
+    if (fstat(df.fd, &st) != 0) { df.close_map(); return false; }
+    df.size = (size_t)st.st_size;
+    size_t min_bytes = 8u << 20;
+    if (const char *e = getenv("SS_DGZ_MIN_BYTES")) { long long v = atoll(e); if (v >= 0) min_bytes = (size_t)v; }
+    if (df.size < 64 || df.size < min_bytes) { df.close_map(); return false; }
+    void *m = mmap(nullptr, df.size, PROT_READ, MAP_PRIVATE, df.fd, 0);
+    if (m == MAP_FAILED) { df.map = nullptr; df.close_map(); return false; }
+    df.map = (const uint8_t *)m;
+    ssi_gz_header h;
+    const char *dot = strrchr(path, '.');
+    const bool gz = (dot && strcmp(dot + 1, "gz") == 0) || (df.map[0] == 0x1f && df.map[1] == 0x8b);
+    if (!gz || ssi_gz_parse_header(df.map, df.map + df.size, &h) != SSI_OK || h.bgzf_bsize) { df.close_map(); return false; }
+    {   // 4-line FASTQ?  (FASTA / wrapped FASTQ are rewritten on the host)
+        std::vector<uint8_t> head(SS_INGEST_HIST + (64u << 10));
+        ssi_gz_stream *g = new ssi_gz_stream;
+        ssi_gz_init(*g, df.map, df.size);
+        uint8_t *pos = head.data() + SS_INGEST_HIST;
+        int rc = ssi_gz_read(*g, &pos, head.data() + head.size());
+        delete g;
+        const size_t hn = (size_t)(pos - (head.data() + SS_INGEST_HIST));
+        if (rc < 0 || hn == 0 || ss_fastx_kind((const char *)head.data() + SS_INGEST_HIST, hn, rc == SSI_OK) != 0) { df.close_map(); return false; }
+    }
+    df.lo = 0; df.hi = df.size;
+    if (n_shards > 1) {
+        if (!ss_gz_is_member_split(df.map, df.size, n_shards)) { df.close_map(); return false; }
+        const size_t P = ss_gz_split_parts(df.size);
+        const size_t p_lo = P * (size_t)shard / (size_t)n_shards, p_hi = P * ((size_t)shard + 1) / (size_t)n_shards;
+        df.lo = (size_t)((unsigned __int128)df.size * p_lo / P);
+        df.hi = p_hi >= P ? df.size : (size_t)((unsigned __int128)df.size * p_hi / P);
+    }
+    df.first_member = df.lo == 0 ? 0 : (df.hi > df.lo ? ss_gz_next_member_start(df.map, df.size, df.lo, df.hi) : df.size);
+    if (df.first_member >= df.hi) df.first_member = df.size;      // no member of mine: nothing to do, but the file is handled
+    // everything up to the end of the member that straddles `hi`
+    df.up_hi = df.hi >= df.size ? df.size : ss_gz_next_member_start(df.map, df.size, df.hi, df.size);
+    if (df.up_hi < df.size) df.up_hi = std::min(df.size, df.up_hi + 64);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < (df.up_hi - std::min(df.up_hi, df.first_member)) + (14ull << 30)) {
+        df.close_map();
+        return false;                                                // not enough room beside the read cache: host threads
+    }
+    return true;
+}
+
+// Inflate one file on the device and hand its text out in pieces of whole FASTQ records:
+// sink(const uint8_t *d_text, size_t n) -> SS_* code.  `d_text` stays valid until the sink returns.
+template <typename Sink>
+static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
+    if (df.first_member >= df.size) return SS_OK;
+    int rc = ensure_source(c);
+    if (rc) return rc;
+    const size_t base_off = df.first_member, n_up = df.up_hi - base_off;
+    uint8_t *d_alloc = nullptr, *d_scratch = nullptr, *d_carry = nullptr;
+    size_t carry_cap = 0;
+    size_t scratch_cap = 2048ull << 20;
+    if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) scratch_cap = (size_t)v << 20; }
+    uint32_t piece = 128u << 10, max_pieces = 4096;
+    if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) piece = (uint32_t)v; }
+    if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= 8192) max_pieces = (uint32_t)v; }
+    auto cleanup = [&]() { cudaFree(d_alloc); cudaFree(d_scratch); cudaFree(d_carry); };
+#define DGZ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
+    DGZ_TRY(cudaMalloc(&d_alloc, n_up + 128));
+    DGZ_TRY(cudaMalloc(&d_scratch, scratch_cap + SS_TEXT_PAD + SS_TILE));
+    uint8_t *d_comp = d_alloc + 64;
+    DGZ_TRY(cudaMemsetAsync(d_alloc, 0, 64, c->copy_stream));
+    DGZ_TRY(cudaMemsetAsync(d_comp + n_up, 0, 64, c->copy_stream));
+    // ---- upload the compressed bytes (several readers, pinned chunks, any order)
+    rc = c->src->start_raw(df.path.c_str(), base_off, df.up_hi);
+    if (rc) { cleanup(); return fail(rc, c->src->error()); }
+    {
+        pending_ring pend(c);
+        cudaError_t ce = cudaSuccess;
+        while (ss_chunk *ch = c->src->next()) {
+            ce = cudaMemcpyAsync(d_comp + (ch->file_off - base_off), ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
+            if (ce != cudaSuccess) { c->src->release(ch); break; }
+            ce = pend.push(ch, c->copy_stream);
+            if (ce != cudaSuccess) break;
+        }
+        pend.drain();
+        int src_rc = c->src->finish();
+        cudaStreamSynchronize(c->copy_stream);
+        if (ce != cudaSuccess) { cleanup(); return ss_cuda_fail(ce, "H2D compressed reads", __FILE__, __LINE__); }
+        if (src_rc) { cleanup(); return fail(src_rc, c->src->error()); }
+    }
+    // ---- inflate, batch by batch
+    ss_dgz dz;
+    rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, max_pieces, piece);
+    if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
+    std::vector<char> h_win(1u << 20);
+    size_t carry = 0;
+    bool first = true, done = false;
+    const std::string no_boundary = df.path + ": no FASTQ record boundary within a batch of the device inflate";
+    while (!done) {
+        size_t n = 0;
+        rc = dz.next(d_scratch + carry, scratch_cap - carry, &n, &done);
+        if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
+        size_t len = carry + n, start = 0;
+        if (first) {
+            const size_t w = std::min(len, h_win.size());
+            DGZ_TRY(cudaMemcpy(h_win.data(), d_scratch, w, cudaMemcpyDeviceToHost));
+            if (df.lo == 0) {
+                rc = check_fastq_head(h_win.data(), w, df.path.c_str());
+                if (rc) { cleanup(); return rc; }
+            } else {                                                 // the head belongs to the previous part's owner
+                start = ss_find_record_start(h_win.data(), w, 1);
+                if (start >= w) {
+                    if (!done || w < len) { cleanup(); return fail(SS_ERR_FORMAT, no_boundary); }
+                    start = len;
+                }
+            }
+            first = false;
+        }
+        size_t cut = len;
+        if (!done) {
+            // the last record start of the batch: searched in a window at its end that widens
+            cut = 0;
+            for (size_t win = 256u << 10; cut == 0; win *= 4) {
+                const size_t w = std::min(win, len - start);
+                if (w > h_win.size()) h_win.resize(w);
+                DGZ_TRY(cudaMemcpy(h_win.data(), d_scratch + len - w, w, cudaMemcpyDeviceToHost));
+                const size_t r = ss_find_cut(h_win.data(), 0, w);
+                if (r) cut = len - w + r;
+                else if (w == len - start) break;
+            }
+            if (cut == 0) {
+                if (len - start + (scratch_cap >> 2) > scratch_cap) { cleanup(); return fail(SS_ERR_FORMAT, no_boundary); }
+                cut = start;                                         // nothing whole yet: keep everything, decode on
+            }
+        } else {
+            // the end of my members.  Another part follows: its owner drops the head of its first member up to the
+            // first record start behind the member's first byte, so that head is mine (decoded here, on the host).
+            const size_t at = dz.stopped_at();
+            if (df.hi < df.size && at < df.size && at >= df.hi) {
+                std::vector<uint8_t> head(SS_INGEST_HIST + (256u << 10));
+                bool found = false;
+                while (!found) {
+                    ssi_gz_stream *g = new ssi_gz_stream;
+                    ssi_gz_init(*g, df.map + at, df.size - at);
+                    uint8_t *pos = head.data() + SS_INGEST_HIST;
+                    int irc = ssi_gz_read(*g, &pos, head.data() + head.size());
+                    delete g;
+                    const size_t hn = (size_t)(pos - (head.data() + SS_INGEST_HIST));
+                    if (irc < 0 && irc != SSI_ERR_HEADER) { cleanup(); return fail(SS_ERR_IO, "inflate failed on " + df.path + ": invalid compressed data"); }
+                    size_t r = ss_find_record_start((const char *)head.data() + SS_INGEST_HIST, hn, 1);
+                    if (r < hn || irc == SSI_OK) {
+                        if (r > hn) r = hn;
+                        if (len + r > scratch_cap) { cleanup(); return fail(SS_ERR_FORMAT, no_boundary); }
+                        DGZ_TRY(cudaMemcpy(d_scratch + len, head.data() + SS_INGEST_HIST, r, cudaMemcpyHostToDevice));
+                        len += r;
+                        found = true;
+                    } else if (head.size() > (256u << 20)) { cleanup(); return fail(SS_ERR_FORMAT, no_boundary); }
+                    else head.resize(SS_INGEST_HIST + (head.size() - SS_INGEST_HIST) * 4);
+                }
+                cut = len;
+            } else {
+                // the file ends here: blank tail lines go, the last line is closed (as the host producers do)
+                const size_t w = std::min<size_t>(len - start, 4096);
+                DGZ_TRY(cudaMemcpy(h_win.data(), d_scratch + len - w, w, cudaMemcpyDeviceToHost));
+                size_t keep = ss_trim_tail(h_win.data(), w);
+                if (keep == 0 && w < len - start) {                  // 4 KiB of blank lines: look at everything (rare)
+                    std::vector<char> all(len - start);
+                    DGZ_TRY(cudaMemcpy(all.data(), d_scratch + start, len - start, cudaMemcpyDeviceToHost));
+                    keep = ss_trim_tail(all.data(), len - start);
+                    len = start + keep;
+                } else len = len - w + keep;
+                if (len > start) { DGZ_TRY(cudaMemsetAsync(d_scratch + len, '\n', 1, c->stream)); len++; }
+                cut = len;
+            }
+        }
+        // the partial record behind the cut is set aside (the sink may pad behind its text), then moved to the front
+        carry = len - cut;
+        if (carry) {
+            if (carry > carry_cap) {
+                cudaFree(d_carry); d_carry = nullptr;
+                carry_cap = std::max<size_t>(carry, 1u << 20);
+                DGZ_TRY(cudaMalloc(&d_carry, carry_cap));
+            }
+            DGZ_TRY(cudaMemcpyAsync(d_carry, d_scratch + cut, carry, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (cut > start) {
+            const uint8_t *text = d_scratch + start;
+            uint8_t *moved = nullptr;
+            if (start & 255u) {                                      // (first batch of a later part only) the kernels want an aligned text
+                DGZ_TRY(cudaMalloc(&moved, cut - start));
+                DGZ_TRY(cudaMemcpyAsync(moved, text, cut - start, cudaMemcpyDeviceToDevice, c->stream));
+                DGZ_TRY(cudaMemcpyAsync(d_scratch, moved, cut - start, cudaMemcpyDeviceToDevice, c->stream));
+                DGZ_TRY(cudaStreamSynchronize(c->stream));
+                cudaFree(moved);
+                text = d_scratch;
+            }
+            rc = sink(text, cut - start);
+            if (rc) { cleanup(); return rc; }
+        }
+        if (carry) DGZ_TRY(cudaMemcpyAsync(d_scratch, d_carry, carry, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (getenv("SS_DEBUG_TIMING"))
+        fprintf(stderr, "[ss dgz] %s: %llu batches, %llu/%llu pieces used, %llu members\n", df.path.c_str(), (unsigned long long)dz.batches(),
+                (unsigned long long)dz.pieces_used(), (unsigned long long)(dz.pieces_found() + dz.batches()), (unsigned long long)dz.members());
+#undef DGZ_TRY
+    cudaStreamSynchronize(c->stream);
+    cleanup();
+    return SS_OK;
+}
+
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
@@ -849,10 +1099,31 @@ extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_pa
     int rc = ensure_source(c);
     if (rc) return rc;
     ss_text_source &src = *c->src;
-    rc = src.start(paths, n_paths, shard, n_shards);
-    if (rc) return fail(rc, src.error());
     ss_reads *r = new ss_reads();
     r->ctx = c;
+    // ordinary gzip files big enough to pay off are inflated on the device, one after the other (ss_dgz.cu)
+    std::vector<const char *> rest;
+    for (int i = 0; i < n_paths; i++) {
+        dgz_file df;
+        if (!dgz_eligible(c, paths[i], shard, n_shards, df)) { rest.push_back(paths[i]); continue; }
+        rc = dgz_inflate_file(c, df, [&](const uint8_t *d_text, size_t n) {
+            if (r->seg.empty() || r->seg.back().len + n + SSI_OUT_SLACK > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
+                r->seg.emplace_back();
+                int arc = alloc_segment(r->seg.back(), std::max<uint64_t>(c->seg_bytes, n + SSI_OUT_SLACK));
+                if (arc) { r->seg.pop_back(); return arc; }
+            }
+            ss_segment &g = r->seg.back();
+            SS_CUDA(cudaMemcpyAsync(g.d_text + g.len, d_text, n, cudaMemcpyDeviceToDevice, c->stream));
+            SS_CUDA(cudaStreamSynchronize(c->stream));
+            g.len += n; r->len += n;
+            return (int)SS_OK;
+        });
+        df.close_map();
+        if (rc) { ss_reads_free(r); return rc; }
+    }
+    paths = rest.data(); n_paths = (int)rest.size();
+    rc = src.start(paths, n_paths, shard, n_shards);
+    if (rc) { ss_reads_free(r); return fail(rc, src.error()); }
     // plain inputs have a known size (one segment); gzip streams grow segment by segment
     const uint64_t known = src.plain_bytes() + 64 * (uint64_t)n_paths + 4096;
     const uint64_t seg_default = src.gz_bytes() ? std::max<uint64_t>(c->seg_bytes, c->chunk_bytes) : known;
@@ -969,6 +1240,24 @@ extern "C" int ss_ingest_files_host(const char *const *paths, int n_paths, int s
     *out_len = total;
     if (n_chunks) *n_chunks = n;
     if (overflow) return fail(SS_ERR_ARG, "ss_ingest_files_host: output buffer too small");
+    return SS_OK;
+}
+
+// host-only: the device gzip inflate pipeline (piece search, marker decode, chain, windows, resolve) on the CPU
+extern "C" int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
+                                   uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, char *out, size_t out_cap,
+                                   size_t *out_len, size_t *stopped_at, uint64_t *stats4) {
+    if ((!comp && comp_size) || !out_len) return fail(SS_ERR_ARG, "ss_dgz_inflate_host: NULL argument");
+    std::vector<uint8_t> text;
+    std::string err;
+    int rc = ss_dgz_host_inflate((const uint8_t *)comp, comp_size, first_member, stop_member_at, max_pieces, piece_bytes,
+                                 sym_per_byte ? sym_per_byte : 5u, text, stopped_at, stats4, err);
+    if (rc) return fail(rc, "device gzip inflate (host emulation): " + err);
+    *out_len = text.size();
+    if (out) {
+        if (text.size() > out_cap) return fail(SS_ERR_ARG, "ss_dgz_inflate_host: output buffer too small");
+        if (!text.empty()) memcpy(out, text.data(), text.size());
+    }
     return SS_OK;
 }
 
@@ -1392,12 +1681,41 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
     rc = ensure_source(c);
     if (rc) return rc;
     ss_text_source &src = *c->src;
-    rc = src.start(paths, n_paths, shard, n_shards);
-    if (rc) return fail(rc, src.error());
     rc = reset_pass(c, s);
-    if (rc) { src.finish(); return rc; }
+    if (rc) return rc;
     SS_CUDA(cudaEventRecord(c->ev_a, c->stream));
     stream_state ss;
+    // ordinary gzip files big enough to pay off are inflated on the device, batch after batch, each batch scanned
+    // where it was inflated (ss_dgz.cu)
+    std::vector<const char *> rest;
+    {
+        uint32_t *d_line = nullptr;
+        size_t line_words = 0;
+        for (int i = 0; i < n_paths && !rc; i++) {
+            dgz_file df;
+            if (!dgz_eligible(c, paths[i], shard, n_shards, df)) { rest.push_back(paths[i]); continue; }
+            rc = dgz_inflate_file(c, df, [&](const uint8_t *d_text, size_t n) {
+                const uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
+                if (ss_index_words(tiles) > line_words) {
+                    cudaFree(d_line); d_line = nullptr;
+                    line_words = ss_index_words(tiles) + (1u << 16);
+                    SS_CUDA(cudaMalloc(&d_line, line_words * sizeof(uint32_t)));
+                }
+                SS_CUDA(cudaMemsetAsync((uint8_t *)d_text + n, '\n', ss_reads_device_capacity(n) - n, c->stream));
+                SS_CUDA(ss_launch_index(d_text, tiles, d_line, 0, c->n_sm, c->stream));
+                SS_CUDA(ss_launch_probe(d_text, n, tiles, d_line, s->view(), c->d_stats, c->d_stats + 4, c->n_sm, c->stream));
+                SS_CUDA(cudaStreamSynchronize(c->stream));
+                ss.probe_launches++; ss.total_launches += 2; ss.bytes += n;
+                return (int)SS_OK;
+            });
+            df.close_map();
+        }
+        cudaFree(d_line);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    paths = rest.data(); n_paths = (int)rest.size();
+    rc = src.start(paths, n_paths, shard, n_shards);
+    if (rc) return fail(rc, src.error());
     pending_ring pend(c);
     bool any_gz = false;
     rc = gz_begin(c);

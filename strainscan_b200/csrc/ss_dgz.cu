@@ -1,0 +1,276 @@
+// ss_dgz.cu -- kernels K7..K10 and the host driver of the device inflate of ordinary gzip streams (ss_dgz.cuh).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ss_common.cuh"
+#include "ss_dgz.cuh"
+#include "ss_dgz_host.h"
+
+// ---------------------------------------------------------------------------------------------
+// K7: find a block start for every piece but the first.  One warp per piece: the lanes try 32 consecutive bit
+// positions with the cheap test, the (rare) survivors are put through the full header test one after the other.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) ss_dgz_find_kernel(const uint8_t *__restrict__ comp, size_t comp_size, dgz_piece *pieces,
+                                                          uint32_t n_pieces, uint64_t first_byte, uint64_t limit_bit, uint32_t piece) {
+    __shared__ ssi_tables s_tab;
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t j = blockIdx.x + 1; j < n_pieces; j += gridDim.x) {
+        const uint64_t from = (first_byte + (uint64_t)j * piece) * 8u;
+        uint64_t to = from + (uint64_t)piece * 8u;
+        if (to > limit_bit) to = limit_bit;
+        uint64_t found = ~0ull;
+        for (uint64_t base = from; base < to && found == ~0ull; base += 32u) {
+            const uint64_t p = base + lane;
+            const bool ok = p < to && dgz_quick_test(comp, comp_size, p);
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                int good = 0;
+                if ((int)lane == l) good = dgz_full_test(comp, comp_size, p, s_tab) ? 1 : 0;
+                good = __shfl_sync(0xFFFFFFFFu, good, l);
+                if (good) { found = base + (uint64_t)l; break; }
+                m &= m - 1;
+            }
+        }
+        if (lane == 0) pieces[j].start_bit = found;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: marker-mode decode, one decoder (lane 0 of a one-warp CTA, tables in shared memory) per piece, pieces handed
+// out dynamically.  Huffman decoding is a serial bit chain: parallelism = pieces in flight.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 24) ss_dgz_decode_kernel(const uint8_t *__restrict__ comp, size_t comp_size, dgz_piece *pieces,
+                                                                uint32_t n_pieces, uint64_t limit_bit, uint64_t stop_byte,
+                                                                uint16_t *__restrict__ sym_pool, uint32_t cap,
+                                                                unsigned int *__restrict__ next) {
+    __shared__ ssi_tables s_tab;
+    if (threadIdx.x != 0) return;
+    while (true) {
+        const uint32_t j = atomicAdd(next, 1u);
+        if (j >= n_pieces) break;
+        dgz_decode_piece(comp, comp_size, pieces, n_pieces, j, limit_bit, stop_byte, sym_pool + (uint64_t)j * cap, cap, s_tab);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: the window in front of every accepted piece, in stream order (one CTA; every step is a 32 KiB gather).
+// windows[k] = the 32 KiB in front of accepted piece k (right-aligned; win_len bytes valid); windows[0] is given.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ss_dgz_window_kernel(const uint32_t *__restrict__ order, uint32_t n_acc,
+                                                              const dgz_piece *__restrict__ pieces,
+                                                              const uint16_t *__restrict__ sym_pool, uint32_t cap,
+                                                              uint8_t *__restrict__ windows, uint32_t win_len0,
+                                                              unsigned int *__restrict__ err) {
+    uint32_t win_len = win_len0;
+    const uint32_t per = SS_DGZ_WINDOW / 1024u;
+    for (uint32_t k = 0; k < n_acc; k++) {
+        const dgz_piece &pc = pieces[order[k]];
+        const uint8_t *w = windows + (uint64_t)k * SS_DGZ_WINDOW;
+        uint8_t *wn = windows + (uint64_t)(k + 1) * SS_DGZ_WINDOW;
+        const bool ok = dgz_next_window_part(w, win_len, sym_pool + (uint64_t)order[k] * cap, pc.n_sym, wn, threadIdx.x * per,
+                                             (threadIdx.x + 1) * per);
+        if (!ok) atomicMin(err, k);
+        win_len = min(SS_DGZ_WINDOW, win_len + pc.n_sym);
+        __syncthreads();
+    }
+}
+
+// K10: symbols -> bytes at their place in the text.  grid.y = accepted piece, grid.x strides over its symbols.
+__global__ void __launch_bounds__(256) ss_dgz_resolve_kernel(const uint32_t *__restrict__ order, const uint64_t *__restrict__ text_off,
+                                                              const dgz_piece *__restrict__ pieces,
+                                                              const uint16_t *__restrict__ sym_pool, uint32_t cap,
+                                                              const uint8_t *__restrict__ windows, uint8_t *__restrict__ out) {
+    const uint32_t k = blockIdx.y;
+    const uint32_t n = pieces[order[k]].n_sym;
+    const uint16_t *sym = sym_pool + (uint64_t)order[k] * cap;
+    const uint8_t *w = windows + (uint64_t)k * SS_DGZ_WINDOW;
+    uint8_t *o = out + text_off[k];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) o[i] = dgz_resolve1(sym[i], w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+#define DGZ_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err_ = std::string("CUDA error in the device gzip inflate: ") + cudaGetErrorString(e_) + " (" #x ")"; return SS_ERR_CUDA; } } while (0)
+
+ss_dgz::~ss_dgz() { close(); }
+
+void ss_dgz::close() {
+    cudaFree(d_pieces_); cudaFree(d_sym_); cudaFree(d_windows_); cudaFree(d_order_); cudaFree(d_off_); cudaFree(d_ctr_);
+    d_pieces_ = nullptr; d_sym_ = nullptr; d_windows_ = nullptr; d_order_ = nullptr; d_off_ = nullptr; d_ctr_ = nullptr;
+}
+
+int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
+                 size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes) {
+    close();
+    n_sm_ = n_sm; st_ = st; d_comp_ = d_comp; h_comp_ = h_comp; size_ = comp_size; stop_at_ = std::min(stop_member_at, comp_size);
+    max_pieces_ = std::max(2u, std::min(max_pieces, 8192u));
+    piece_ = std::max(4096u, piece_bytes);
+    uint32_t expand = SS_DGZ_EXPAND_DEFAULT;
+    if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) expand = (uint32_t)v; }
+    cap_ = piece_ * expand;
+    done_ = false; win_len_ = 0; members_ = 0; pieces_used_ = pieces_found_ = batches_ = 0;
+    ssi_gz_header h;
+    if (first_member >= comp_size || ssi_gz_parse_header(h_comp + first_member, h_comp + comp_size, &h) != SSI_OK) {
+        err_ = "device gzip inflate: no gzip member at the start of the range";
+        return SS_ERR_IO;
+    }
+    cur_bit_ = (uint64_t)(first_member + h.header_len) * 8u;
+    DGZ_CUDA(cudaMalloc(&d_pieces_, (size_t)max_pieces_ * sizeof(dgz_piece)));
+    DGZ_CUDA(cudaMalloc(&d_sym_, (size_t)max_pieces_ * cap_ * sizeof(uint16_t)));
+    DGZ_CUDA(cudaMalloc(&d_windows_, ((size_t)max_pieces_ + 1) * SS_DGZ_WINDOW));
+    DGZ_CUDA(cudaMalloc(&d_order_, (size_t)max_pieces_ * sizeof(uint32_t)));
+    DGZ_CUDA(cudaMalloc(&d_off_, (size_t)max_pieces_ * sizeof(uint64_t)));
+    DGZ_CUDA(cudaMalloc(&d_ctr_, 2 * sizeof(unsigned int)));
+    DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));
+    h_pieces_.resize(max_pieces_);
+    return SS_OK;
+}
+
+size_t ss_dgz::batch_text_capacity() const { return (size_t)max_pieces_ * cap_; }
+
+// Inflate the next batch into d_out (out_cap bytes of room; any size of at least one piece's worth works: a batch is
+// sized to what the stream has been inflating to, and pieces that do not fit are decoded again next time).  *n_out bytes
+// were produced; *done: the stream (or this range's members) is finished.  The text continues the previous batch's.
+int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
+    *n_out = 0; *done = done_;
+    if (done_) return SS_OK;
+    if (out_cap < cap_) { err_ = "device gzip inflate: output buffer smaller than one piece's text"; return SS_ERR_ARG; }
+    const uint64_t first_byte = cur_bit_ >> 3;
+    uint64_t span = size_ - first_byte;
+    uint32_t P = (uint32_t)std::min<uint64_t>(max_pieces_, (span + piece_ - 1) / piece_);
+    P = (uint32_t)std::min<double>((double)P, (double)out_cap / ((double)piece_ * ratio_ * 1.15));
+    if (P == 0) P = 1;
+    const uint64_t limit_bit = std::min<uint64_t>((uint64_t)size_ * 8u, (first_byte + (uint64_t)P * piece_) * 8u);
+    for (uint32_t j = 0; j < P; j++) { h_pieces_[j] = dgz_piece(); h_pieces_[j].start_bit = j == 0 ? cur_bit_ : ~0ull; }
+    DGZ_CUDA(cudaMemcpyAsync(d_pieces_, h_pieces_.data(), (size_t)P * sizeof(dgz_piece), cudaMemcpyHostToDevice, st_));
+    DGZ_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(unsigned int), st_));
+    DGZ_CUDA(cudaMemsetAsync(d_ctr_ + 1, 0xFF, sizeof(unsigned int), st_));
+    if (P > 1) ss_dgz_find_kernel<<<std::min<uint32_t>(P - 1, (uint32_t)n_sm_ * 32u), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, first_byte, limit_bit, piece_);
+    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * 24u), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
+                                                                                    d_sym_, cap_, d_ctr_);
+    DGZ_CUDA(cudaGetLastError());
+    DGZ_CUDA(cudaMemcpyAsync(h_pieces_.data(), d_pieces_, (size_t)P * sizeof(dgz_piece), cudaMemcpyDeviceToHost, st_));
+    DGZ_CUDA(cudaStreamSynchronize(st_));
+    batches_++;
+    // ---- the chain: a piece counts only if the accepted piece before it ended exactly on its start
+    std::vector<uint32_t> order;
+    std::vector<uint64_t> off;
+    uint64_t total = 0;
+    uint32_t cur = 0;
+    bool stream_end = false;
+    for (uint32_t j = 1; j < P; j++) pieces_found_ += h_pieces_[j].start_bit != ~0ull;
+    while (true) {
+        const dgz_piece &pc = h_pieces_[cur];
+        if (pc.status == SS_DGZ_ERROR || pc.status == SS_DGZ_NOSTART) {
+            err_ = "invalid compressed data";
+            return SS_ERR_IO;
+        }
+        if (pc.status == SS_DGZ_FULL && pc.n_sym == 0) {
+            err_ = "a single deflate block inflates to more than the device decoder's piece buffer";
+            return SS_ERR_UNSUPPORTED;
+        }
+        if (total + pc.n_sym > out_cap) {                           // does not fit: the next batch starts here
+            if (order.empty()) { err_ = "device gzip inflate: output buffer smaller than one piece's text"; return SS_ERR_ARG; }
+            break;
+        }
+        order.push_back(cur); off.push_back(total);
+        total += pc.n_sym;
+        members_ += pc.members;
+        cur_bit_ = pc.end_bit;
+        if (pc.status == SS_DGZ_END) { stream_end = true; break; }
+        if (pc.status == SS_DGZ_FULL || pc.next >= P) break;
+        cur = pc.next;
+    }
+    pieces_used_ += order.size();
+    const uint32_t n_acc = (uint32_t)order.size();
+    DGZ_CUDA(cudaMemcpyAsync(d_order_, order.data(), n_acc * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
+    DGZ_CUDA(cudaMemcpyAsync(d_off_, off.data(), n_acc * sizeof(uint64_t), cudaMemcpyHostToDevice, st_));
+    ss_dgz_window_kernel<<<1, 1024, 0, st_>>>(d_order_, n_acc, d_pieces_, d_sym_, cap_, d_windows_, win_len_, d_ctr_ + 1);
+    ss_dgz_resolve_kernel<<<dim3(32, n_acc), 256, 0, st_>>>(d_order_, d_off_, d_pieces_, d_sym_, cap_, d_windows_, d_out);
+    // the last window becomes the first one of the next batch
+    DGZ_CUDA(cudaMemcpyAsync(d_windows_, d_windows_ + (size_t)n_acc * SS_DGZ_WINDOW, SS_DGZ_WINDOW, cudaMemcpyDeviceToDevice, st_));
+    unsigned int bad = 0xFFFFFFFFu;
+    DGZ_CUDA(cudaMemcpyAsync(&bad, d_ctr_ + 1, sizeof bad, cudaMemcpyDeviceToHost, st_));
+    DGZ_CUDA(cudaStreamSynchronize(st_));
+    if (bad != 0xFFFFFFFFu) { err_ = "invalid compressed data (a match reaches in front of the stream start)"; return SS_ERR_IO; }
+    win_len_ = (uint32_t)std::min<uint64_t>(SS_DGZ_WINDOW, (uint64_t)win_len_ + total);
+    {   // what a compressed byte has been inflating to (sizes the next batch)
+        const double consumed = (double)((cur_bit_ >> 3) - first_byte);
+        if (consumed > 65536.0) ratio_ = std::max(1.0, 0.5 * ratio_ + 0.5 * (double)total / consumed);
+    }
+    *n_out = (size_t)total;
+    if (stream_end) { done_ = true; }
+    *done = done_;
+    return SS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the same pipeline on the host (no GPU): tests of the algorithms against zlib
+// ---------------------------------------------------------------------------------------------
+int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
+                        uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, std::vector<uint8_t> &out,
+                        size_t *stopped_at, uint64_t *stats4, std::string &err) {
+    out.clear();
+    const uint32_t piece = std::max(4096u, piece_bytes), cap = piece * std::max(1u, sym_per_byte);
+    max_pieces = std::max(2u, max_pieces);
+    const uint64_t stop_byte = std::min(stop_member_at, comp_size);
+    ssi_gz_header h;
+    if (first_member >= comp_size || ssi_gz_parse_header(comp + first_member, comp + comp_size, &h) != SSI_OK) { err = "no gzip member at the start of the range"; return SS_ERR_IO; }
+    // the device buffers are padded by 16 readable bytes; so is this copy
+    std::vector<uint8_t> padded(comp_size + 32, 0);
+    memcpy(padded.data(), comp, comp_size);
+    comp = padded.data();
+    uint64_t cur_bit = (uint64_t)(first_member + h.header_len) * 8u;
+    std::vector<uint8_t> win(SS_DGZ_WINDOW, 0), win2(SS_DGZ_WINDOW, 0);
+    uint32_t win_len = 0;
+    std::vector<dgz_piece> pieces(max_pieces);
+    std::vector<uint16_t> sym((size_t)max_pieces * cap);
+    ssi_tables *tab = new ssi_tables;
+    uint64_t found = 0, used = 0, batches = 0, members = 0;
+    int rc = SS_OK;
+    while (true) {
+        const uint64_t first_byte = cur_bit >> 3;
+        uint32_t P = (uint32_t)std::min<uint64_t>(max_pieces, (comp_size - first_byte + piece - 1) / piece);
+        if (P == 0) P = 1;
+        const uint64_t limit_bit = std::min<uint64_t>((uint64_t)comp_size * 8u, (first_byte + (uint64_t)P * piece) * 8u);
+        for (uint32_t j = 0; j < P; j++) { pieces[j] = dgz_piece(); pieces[j].start_bit = ~0ull; }
+        pieces[0].start_bit = cur_bit;
+        for (uint32_t j = 1; j < P; j++) {
+            const uint64_t from = (first_byte + (uint64_t)j * piece) * 8u, to = std::min<uint64_t>(from + (uint64_t)piece * 8u, limit_bit);
+            for (uint64_t p = from; p < to; p++)
+                if (dgz_quick_test(comp, comp_size, p) && dgz_full_test(comp, comp_size, p, *tab)) { pieces[j].start_bit = p; found++; break; }
+        }
+        for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
+        batches++;
+        uint32_t cur = 0;
+        bool end = false;
+        while (true) {
+            const dgz_piece &pc = pieces[cur];
+            if (pc.status == SS_DGZ_ERROR || pc.status == SS_DGZ_NOSTART) { err = "invalid compressed data"; rc = SS_ERR_IO; break; }
+            if (pc.status == SS_DGZ_FULL && pc.n_sym == 0) { err = "a single deflate block inflates to more than the decoder's piece buffer"; rc = SS_ERR_UNSUPPORTED; break; }
+            const uint16_t *ps = sym.data() + (size_t)cur * cap;
+            if (!dgz_next_window_part(win.data(), win_len, ps, pc.n_sym, win2.data(), 0, SS_DGZ_WINDOW)) { err = "invalid compressed data (a match reaches in front of the stream start)"; rc = SS_ERR_IO; break; }
+            const size_t o = out.size();
+            out.resize(o + pc.n_sym);
+            for (uint32_t i = 0; i < pc.n_sym; i++) out[o + i] = dgz_resolve1(ps[i], win.data());
+            win.swap(win2);
+            win_len = (uint32_t)std::min<uint64_t>(SS_DGZ_WINDOW, (uint64_t)win_len + pc.n_sym);
+            used++; members += pc.members;
+            cur_bit = pc.end_bit;
+            if (pc.status == SS_DGZ_END) { end = true; break; }
+            if (pc.status == SS_DGZ_FULL || pc.next >= P) break;
+            cur = pc.next;
+        }
+        if (rc || end) break;
+    }
+    delete tab;
+    if (stopped_at) *stopped_at = (size_t)(cur_bit >> 3);
+    if (stats4) { stats4[0] = found; stats4[1] = used; stats4[2] = batches; stats4[3] = members; }
+    return rc;
+}

@@ -1,0 +1,57 @@
+// ss_dgz_host.h -- host driver of the device inflate of ordinary gzip streams (ss_dgz.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ss_dgz.cuh"
+
+// One gzip file (or the members of one file part) inflated batch by batch on the device.  The compressed bytes
+// [0, comp_size) sit in device memory (d_comp, padded by 16 readable bytes) and in host memory (h_comp: headers are
+// parsed there).  Text comes out in stream order, cut anywhere (the caller carries partial records over).
+class ss_dgz {
+public:
+    ss_dgz() = default;
+    ~ss_dgz();
+    ss_dgz(const ss_dgz &) = delete;
+    ss_dgz &operator=(const ss_dgz &) = delete;
+    // first_member: byte offset of a member header; members that start at or behind stop_member_at are not decoded
+    int open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
+             size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes);
+    size_t batch_text_capacity() const;
+    int next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done);
+    void close();
+    const std::string &error() const { return err_; }
+    size_t stopped_at() const { return (size_t)(cur_bit_ >> 3); }     // after `done`: the byte the decoder stands on
+    uint64_t members() const { return members_; }
+    uint64_t pieces_found() const { return pieces_found_; }
+    uint64_t pieces_used() const { return pieces_used_; }
+    uint64_t batches() const { return batches_; }
+
+private:
+    int n_sm_ = 0;
+    cudaStream_t st_ = nullptr;
+    const uint8_t *d_comp_ = nullptr, *h_comp_ = nullptr;
+    size_t size_ = 0, stop_at_ = 0;
+    uint32_t max_pieces_ = 0, cap_ = 0, piece_ = 0;
+    uint64_t cur_bit_ = 0;
+    uint32_t win_len_ = 0;
+    double ratio_ = 4.0;              // text bytes per compressed byte seen so far
+    bool done_ = false;
+    uint64_t members_ = 0, pieces_found_ = 0, pieces_used_ = 0, batches_ = 0;
+    dgz_piece *d_pieces_ = nullptr;
+    uint16_t *d_sym_ = nullptr;
+    uint8_t *d_windows_ = nullptr;
+    uint32_t *d_order_ = nullptr;
+    uint64_t *d_off_ = nullptr;
+    unsigned int *d_ctr_ = nullptr;
+    std::vector<dgz_piece> h_pieces_;
+    std::string err_;
+};
+
+// the same pipeline on host threads (tests: the algorithms against zlib without a GPU); out is resized to the text
+int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
+                        uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, std::vector<uint8_t> &out,
+                        size_t *stopped_at, uint64_t *stats4, std::string &err);

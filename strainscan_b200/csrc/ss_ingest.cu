@@ -174,15 +174,30 @@ int ss_text_source::plain_boundary(const file_map &f, size_t off, size_t *out) {
 static size_t bgzf_resync(const uint8_t *p, size_t size, size_t off);
 
 // ---- multi-member gzip: members found by their header ------------------------------------------------
-// Does a gzip member start at byte `at`?  Magic, method, reserved flag bits, a header that parses, and a first
-// deflate block whose header is valid (for a dynamic block: complete code-length code and both Huffman codes).
+// Does a gzip member start at byte `at`?  Magic, method, reserved flag bits, a header that parses -- and a deflate
+// stream behind it that decodes: the first 64 KiB of text (or the whole member, if shorter) are inflated with an EMPTY
+// history, so in bytes that merely look like a header the first match that reaches back before the "member start",
+// the first unused code or the first broken block header ends the trial; a stream that ends inside the trial must be
+// followed by its own length (ISIZE).  (A header check alone is not enough: a
+// fixed-Huffman block "header" is valid whatever follows, and the 3-byte magic turns up every 2^27 bytes of
+// compressed data.)
 static bool gz_member_at(const uint8_t *p, size_t size, size_t at, ssi_tables &t) {
     if (at + 18 > size || p[at] != 0x1f || p[at + 1] != 0x8b || p[at + 2] != 8 || (p[at + 3] & 0xE0)) return false;
     ssi_gz_header h;
     if (ssi_gz_parse_header(p + at, p + size, &h) != SSI_OK) return false;
     ssi_stream s;
-    pgz_seek(s, p, size, (uint64_t)(at + h.header_len) * 8u);
-    return pgz_block_header(s, t) >= 0;
+    ssi_stream_init(s, p + at + h.header_len, p + size);
+    std::vector<uint8_t> buf((64u << 10) + 4 * SSI_OUT_SLACK);
+    uint8_t *pos = buf.data();
+    const int rc = ssi_inflate(s, t, &pos, buf.data() + buf.size());
+    if (rc == SSI_MORE_OUTPUT) return true;
+    if (rc != SSI_OK) return false;
+    // a member that ends inside the trial: its trailer must carry the length just produced
+    ssi_drop(s.bits, s.bits.cnt & 7u);
+    const uint8_t *q = ssi_in_pos(s.bits);
+    if (p + size - q < 8) return false;
+    const uint32_t isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
+    return isize == (uint32_t)s.out_total;
 }
 
 // first member start in [from, limit), or `size` when there is none (a member needs 18 bytes: header + trailer)
@@ -198,9 +213,26 @@ static size_t gz_next_member(const uint8_t *p, size_t size, size_t from, size_t 
     return size;
 }
 
+size_t ss_gz_next_member_start(const uint8_t *map, size_t size, size_t from, size_t limit) {
+    ssi_tables *t = new ssi_tables;
+    const size_t r = gz_next_member(map, size, from, limit, *t);
+    delete t;
+    return r;
+}
+
+bool ss_gz_is_member_split(const uint8_t *map, size_t size, int n_shards) {
+    int want_split = 1;
+    if (const char *e = getenv("SS_GZ_SPLIT")) want_split = atoi(e);
+    if (!want_split || size < (1u << 20)) return false;
+    const size_t m2 = ss_gz_next_member_start(map, size, 1, 256u << 20);
+    return m2 < size && (want_split == 2 || size / m2 >= 4 * (size_t)std::max(1, n_shards));
+}
+
+size_t ss_gz_split_parts(size_t size);
+
 // fixed parts of a member-split gzip file: a function of the file size only, so every rank (whatever its thread
 // count) cuts the file the same way
-static size_t gz_split_parts(size_t size) {
+size_t ss_gz_split_parts(size_t size) {
     size_t part = 32u << 20;
     if (const char *e = getenv("SS_GZ_PART_BYTES")) { long long v = atoll(e); if (v >= (64 << 10)) part = (size_t)v; }
     return std::max<size_t>(1, std::min<size_t>(4096, size / part));
@@ -212,6 +244,7 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
     finish();
     err_code_ = 0; err_msg_.clear(); stop_ = false;
     shard_ = shard; n_shards_ = n_shards;
+    raw_mode_ = false;
     plain_bytes_ = gz_bytes_ = 0;
     n_gz_jobs_ = 0;
     files_.clear(); jobs_.clear(); next_job_ = 0;
@@ -239,14 +272,7 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
                      h.bgzf_bsize <= f.size;
             // A file of many gzip members (lane files concatenated, block-wise compressors) is split at member
             // starts: decided from the distance to the second member alone, i.e. identically on every rank.
-            int want_split = 1;
-            if (const char *e = getenv("SS_GZ_SPLIT")) want_split = atoi(e);
-            if (!f.bgzf && want_split && f.size >= (1u << 20)) {
-                ssi_tables *t = new ssi_tables;
-                const size_t m2 = gz_next_member(f.map, f.size, 1, 256u << 20, *t);
-                delete t;
-                f.split = m2 < f.size && (want_split == 2 || f.size / m2 >= 4 * (size_t)n_shards);
-            }
+            if (!f.bgzf) f.split = ss_gz_is_member_split(f.map, f.size, n_shards);
         }
         if (f.size) {   // dialect from the head of the text: FASTA and wrapped FASTQ are rewritten on the host (ss_fastx.h)
             std::vector<uint8_t> head(SS_INGEST_HIST + (64u << 10));
@@ -310,7 +336,7 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
         }
         if (f.gz && f.split) {
             // fixed parts; rank r owns the members that START in parts [P r / N, P (r + 1) / N)
-            const size_t P = gz_split_parts(f.size);
+            const size_t P = ss_gz_split_parts(f.size);
             const size_t p_lo = P * (size_t)shard_ / (size_t)n_shards_, p_hi = P * ((size_t)shard_ + 1) / (size_t)n_shards_;
             for (size_t pi = p_lo; pi < p_hi; pi++) {
                 job j; j.file = (int)fi;
@@ -356,6 +382,52 @@ int ss_text_source::start(const char *const *paths, int n_paths, int shard, int 
     active_ = nt;
     for (int t = 0; t < nt; t++) threads_.emplace_back([this]() { worker(); });
     return SS_OK;
+}
+
+int ss_text_source::start_raw(const char *path, size_t lo, size_t hi) {
+    if (bufs_.empty()) { err_msg_ = "ingest: init() was not called"; return SS_ERR_ARG; }
+    finish();
+    err_code_ = 0; err_msg_.clear(); stop_ = false;
+    shard_ = 0; n_shards_ = 1; plain_bytes_ = gz_bytes_ = 0; n_gz_jobs_ = 0;
+    files_.clear(); jobs_.clear(); next_job_ = 0;
+    free_.clear(); ready_.clear();
+    for (auto &b : bufs_) free_.push_back(&b);
+    file_map f;
+    f.path = path;
+    f.fd = open(path, O_RDONLY);
+    if (f.fd < 0) { err_msg_ = std::string("cannot open ") + path; return SS_ERR_IO; }
+    struct stat st;
+    if (fstat(f.fd, &st) != 0) { err_msg_ = std::string("cannot stat ") + path; close(f.fd); return SS_ERR_IO; }
+    f.size = (size_t)st.st_size;
+    files_.push_back(f);
+    hi = std::min(hi, f.size);
+    for (size_t at = lo; at < hi; at += chunk_bytes_) {
+        job j; j.file = 0; j.lo = at; j.hi = std::min(hi, at + chunk_bytes_);
+        jobs_.push_back(j);
+    }
+    raw_mode_ = true;
+    int nt = (int)std::min<size_t>((size_t)n_threads_, jobs_.size());
+    nt = std::min(nt, std::max(1, (int)bufs_.size() - 2));
+    active_ = nt;
+    for (int t = 0; t < nt; t++) threads_.emplace_back([this]() { worker(); });
+    return SS_OK;
+}
+
+void ss_text_source::run_raw(const job &j) {
+    const file_map &f = files_[(size_t)j.file];
+    ss_chunk *c = acquire();
+    if (!c) return;
+    const size_t want = j.hi - j.lo;
+    for (size_t have = 0; have < want;) {
+        ssize_t got = pread(f.fd, c->text + have, want - have, (off_t)(j.lo + have));
+        if (got <= 0) { release(c); fail(SS_ERR_IO, "short read on " + f.path); return; }
+        have += (size_t)got;
+    }
+    c->kind = SS_CHUNK_RAW;
+    c->file_off = j.lo;
+    c->len = want;
+    c->inflated_len = want;                      // text_len() of a non-TEXT chunk: pre + inflated + post
+    emit(c);
 }
 
 int ss_text_source::finish() {
@@ -423,7 +495,8 @@ void ss_text_source::worker() {
             j = jobs_[next_job_++];
         }
         const file_map &f = files_[(size_t)j.file];
-        if (f.normalize) run_normalize(j);
+        if (raw_mode_) run_raw(j);
+        else if (f.normalize) run_normalize(j);
         else if (f.bgzf) run_bgzf(j);
         else if (f.gz && f.split) run_gz_members(j);
         else if (f.gz) {
@@ -557,6 +630,7 @@ void ss_text_source::run_gz_members(const job &j) {
         return rc == SSI_ERR_TRUNC ? "unexpected end of file" : rc == SSI_ERR_HEADER ? "not in gzip format"
                : rc == SSI_ERR_SIZE ? "length error" : "invalid compressed data";
     };
+    std::vector<uint8_t> carry;
     size_t fill = 0;
     size_t drop = j.lo == 0 ? 0 : (size_t)-1;        // bytes of the first chunk that belong to the previous part (-1: not known yet)
     size_t mark = (size_t)-1;                        // offset in the current chunk where the NEXT part's first member begins
@@ -581,7 +655,9 @@ void ss_text_source::run_gz_members(const job &j) {
                 }
                 file_end = true;
             }
-            if (!file_end && (end < j.hi || gz_next_member(f.map, f.size, j.hi, end + 1, *tabs) != end)) {
+            // (at the file end: nobody may find a member start inside the bytes I decoded as part of my last member)
+            if (file_end ? (j.hi < f.size && gz_next_member(f.map, f.size, j.hi, f.size, *tabs) < f.size)
+                         : (end < j.hi || gz_next_member(f.map, f.size, j.hi, end + 1, *tabs) != end)) {
                 release(c); fail(SS_ERR_IO, f.path + ": gzip member boundaries are ambiguous (a member header pattern inside compressed data); set SS_GZ_SPLIT=0"); break;
             }
             if (file_end) { emit_all = true; }
@@ -599,40 +675,45 @@ void ss_text_source::run_gz_members(const job &j) {
             if (cut) c->text[cut++] = '\n';
             done = true;
         }
-        ss_chunk *c2 = nullptr;
+        size_t tail = 0, hist = 0;
         if (!done) {                                                   // chunk full: cut at the last record start, carry the tail
             cut = cut_chunk(c, fill, false);
             if (cut == 0) {
                 release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record boundary within a chunk (a record longer than SS_CHUNK_BYTES?)"); break;
             }
-            c2 = acquire();
-            if (!c2) { release(c); break; }
-            size_t tail = fill - cut, h = std::min(fill, tail + (size_t)SS_INGEST_HIST);
-            memcpy(c2->text + tail - h, c->text + fill - h, h);
+            // the tail and the 32 KiB of history the decoder needs go through a private buffer: this thread must not
+            // sit on its full chunk while it waits for an empty one (all producers doing that at once would starve
+            // the consumer, which hands buffers back only as its copies complete)
+            tail = fill - cut; hist = std::min(fill, tail + (size_t)SS_INGEST_HIST);
+            carry.assign(c->text + fill - hist, c->text + fill);
             if (mark != (size_t)-1) {
                 if (mark >= cut) mark -= cut;                          // the boundary member begins in the carried tail
-                else { release(c); release(c2); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
+                else { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
             }
-            fill = tail;
         }
         // the head of the job's first chunk belongs to the previous part
         size_t off = 0;
         if (j.lo == 0 && drop == 0) {                                  // the file's first chunk: is this FASTQ at all?
             std::string m;
             int hrc = check_head(c->text, ss_trim_tail((const char *)c->text, cut), f.path, m);
-            if (hrc) { release(c); if (c2) release(c2); fail(hrc, m); break; }
+            if (hrc) { release(c); fail(hrc, m); break; }
             drop = 1;                                                  // checked
         }
         if (drop == (size_t)-1) {
             off = ss_find_record_start((const char *)c->text, cut, 1);
-            if (off >= cut && !done) { release(c); if (c2) release(c2); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
+            if (off >= cut && !done) { release(c); fail(SS_ERR_FORMAT, f.path + ": no FASTQ record start within a chunk behind a gzip member start"); break; }
             off = std::min(off, cut);
             drop = off;
         }
         if (off) memmove(c->text, c->text + off, cut - off);
         c->len = cut - off;
         emit(c);
-        c = c2;
+        c = nullptr;
+        if (done) break;
+        c = acquire();
+        if (!c) break;
+        memcpy(c->text + tail - hist, carry.data(), hist);            // history in front of the text area, tail at its start
+        fill = tail;
     }
     delete g;
     delete tabs;

@@ -33,7 +33,7 @@ struct ss_member {
 // with the compressed members in text[0, len), the two host-decoded text pieces behind them (the
 // boundary member of every batch is inflated by the producer so that batches begin and end on record
 // boundaries) and the member table in `members`.
-enum { SS_CHUNK_TEXT = 0, SS_CHUNK_BGZF = 1 };
+enum { SS_CHUNK_TEXT = 0, SS_CHUNK_BGZF = 1, SS_CHUNK_RAW = 2 };
 struct ss_chunk {
     uint8_t *base = nullptr;   // pinned allocation: [SS_INGEST_HIST history][cap text bytes][slack][member table]
     uint8_t *text = nullptr;   // TEXT: whole FASTQ records ending with '\n'; BGZF: compressed members
@@ -42,6 +42,7 @@ struct ss_chunk {
     int kind = SS_CHUNK_TEXT;
     ss_member *members = nullptr;      // SS_BGZF_MAX_MEMBERS entries (pinned)
     uint32_t n_members = 0;
+    uint64_t file_off = 0;             // RAW: bytes [file_off, file_off + len) of the file, verbatim (start_raw)
     const uint8_t *pre_text = nullptr, *post_text = nullptr;   // inside this buffer, behind the compressed bytes
     size_t pre_len = 0, post_len = 0, inflated_len = 0;
     size_t text_len() const { return kind == SS_CHUNK_TEXT ? len : pre_len + inflated_len + post_len; }
@@ -53,6 +54,11 @@ int ss_read_whole_file(const char *path, std::vector<char> &out, std::string &er
 size_t ss_trim_tail(const char *buf, size_t len);
 size_t ss_find_record_start(const char *buf, size_t len, size_t from);
 size_t ss_find_cut(const char *buf, size_t lo, size_t hi);
+// multi-member gzip files (ss_ingest.cu): is the file one (decided from the distance to its second member, the same on
+// every rank), its fixed parts, and the first member start in [from, limit) (`size` = none)
+bool ss_gz_is_member_split(const uint8_t *map, size_t size, int n_shards);
+size_t ss_gz_split_parts(size_t size);
+size_t ss_gz_next_member_start(const uint8_t *map, size_t size, size_t from, size_t limit);
 
 class ss_text_source {
 public:
@@ -73,6 +79,9 @@ public:
     // member starts (fixed file parts, every member decoded by exactly one rank); a single gzip stream is
     // decoded whole by every rank and its chunks (always cut the same way) are dealt round-robin.
     int start(const char *const *paths, int n_paths, int shard, int n_shards);
+    // Deliver bytes [lo, hi) of ONE file verbatim as SS_CHUNK_RAW chunks (any order, several readers): the upload of a
+    // compressed file that the device inflates.
+    int start_raw(const char *path, size_t lo, size_t hi);
     ss_chunk *next();              // blocks; nullptr when everything was delivered or on error
     void release(ss_chunk *c);     // the buffer may be refilled (call once the H2D copy has completed)
     int finish();                  // joins the producers; returns the SS_ERR_* code of the first failure
@@ -94,6 +103,8 @@ private:
     void run_gz_parallel(const job &j, int threads, size_t span);
     void run_bgzf(const job &j);
     void run_normalize(const job &j);
+    void run_raw(const job &j);
+    bool raw_mode_ = false;
     // in-order byte stream of one file -> record-aligned chunks (used by the parallel gzip decoder)
     struct stream_writer {
         ss_text_source *src = nullptr;

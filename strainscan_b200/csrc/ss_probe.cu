@@ -83,23 +83,44 @@ __device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
 // ---------------------------------------------------------------------------------------------
 // SWAR byte classification of one 32-bit word (4 text bytes)
 // ---------------------------------------------------------------------------------------------
-// 0x80 in every byte of (w ^ pat) that is NON-zero (exact, no cross-byte carries)
+// 0x80 in every byte of (w ^ pat) that is NON-zero (exact, no cross-byte carries); used by the line index kernel
 __device__ __forceinline__ uint32_t nz7(uint32_t w, uint32_t pat) {
     uint32_t v = w ^ pat;
     return ((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v;
 }
-// bits 7,15,23,31 -> bits 0..3
-__device__ __forceinline__ uint32_t pack4(uint32_t m7) {
-    return (((m7 >> 7) & 0x01010101u) * 0x00204081u >> 21) & 0xFu;
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
 }
-// nl4: byte == '\n';  ok4: byte in {A,C,G,T,a,c,g,t};  c8: 2-bit codes (A0 C1 G2 T3), byte i at bits 2i
+// truth-table bytes of lop3 for inputs a = 0xF0, b = 0xCC, c = 0xAA
+#define SS_LA 0xF0
+#define SS_LB 0xCC
+#define SS_LC 0xAA
+// Classification by bit planes.  s_i = w >> i carries bit i of every byte at that byte's bit 0 (what spills in from
+// the neighbouring byte lands in the higher bits of the lane, which the final 0x01010101 mask drops), and each
+// property is a Boolean function of the planes, three inputs per LOP3:
+//   newline 0x0A = 00001010b                                   -> ~s7 ~s6 ~s5 ~s4 s3 ~s2 s1 ~s0
+//   A 0x41, C 0x43, G 0x47, T 0x54 with bit 5 (case) ignored   -> ~s7 s6 ~s3 and (s4, s2, s1, s0) in {0001, 0011, 0111, 1100}
+//   2-bit code A0 C1 G2 T3 = bits 1..2 xor bits 2..3           -> (s1 ^ s2) & 3 per byte
+// The four results of a word are gathered with one multiply each (the wanted bits land in the top nibble / byte).
+// 26 instructions per word against 45 for the compare-with-four-patterns form this replaces.
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t &nl4, uint32_t &ok4, uint32_t &c8) {
-    nl4 = pack4(~nz7(w, 0x0A0A0A0Au));
-    uint32_t u = w & 0xDFDFDFDFu;   // fold case
-    uint32_t bad = nz7(u, 0x41414141u) & nz7(u, 0x43434343u) & nz7(u, 0x47474747u) & nz7(u, 0x54545454u);
-    ok4 = pack4(~bad);
-    uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
-    c8 = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xFFu;
+    const uint32_t s0 = w, s1 = w >> 1, s2 = w >> 2, s3 = w >> 3, s4 = w >> 4, s5 = w >> 5, s6 = w >> 6, s7 = w >> 7;
+    const uint32_t hi0 = lop3<(~SS_LA & ~SS_LB & ~SS_LC) & 0xFF>(s7, s6, s5);              // ~s7 & ~s6 & ~s5
+    const uint32_t mid = lop3<(~SS_LA & SS_LB & ~SS_LC) & 0xFF>(s4, s3, s2);               // ~s4 & s3 & ~s2
+    const uint32_t low = lop3<(SS_LA & ~SS_LB & SS_LC) & 0xFF>(s1, s0, hi0);               // s1 & ~s0 & hi0
+    const uint32_t nl = lop3<(SS_LA & SS_LB & SS_LC) & 0xFF>(mid, low, 0x01010101u);
+    const uint32_t acg = lop3<(SS_LA & (SS_LB | ~SS_LC)) & 0xFF>(s0, s1, s2);              // s0 & (s1 | ~s2): A, C, G
+    const uint32_t t = lop3<(SS_LA & ~SS_LB & ~SS_LC) & 0xFF>(s2, s1, s0);                 // s2 & ~s1 & ~s0: T
+    const uint32_t f = lop3<((SS_LA & SS_LB) | (~SS_LA & SS_LC)) & 0xFF>(s4, t, acg);      // s4 ? t : acg
+    const uint32_t g = lop3<(SS_LA & ~SS_LB & ~SS_LC) & 0xFF>(s6, s7, s3);                 // s6 & ~s7 & ~s3
+    const uint32_t ok = lop3<(SS_LA & SS_LB & SS_LC) & 0xFF>(f, g, 0x01010101u);
+    const uint32_t c = lop3<((SS_LA ^ SS_LB) & SS_LC) & 0xFF>(s1, s2, 0x03030303u);        // (s1 ^ s2) & 3
+    nl4 = (nl * 0x10204080u) >> 28;      // byte i's bit 0 -> bit 28 + i
+    ok4 = (ok * 0x10204080u) >> 28;
+    c8 = (c * 0x01041040u) >> 24;        // byte i's two bits -> bits 24 + 2i
 }
 
 struct run_bits { uint32_t nl, ok; uint64_t codes; };
@@ -285,8 +306,7 @@ struct __align__(16) ss_warp_smem {
     uint32_t codes[2 * SS_WRUNS + 4];            // 2-bit codes of my 32 runs, 2 words per run (+ zero pad)
     uint32_t valid[SS_WRUNS + 2];                // valid bits of my 32 runs (+ zero pad)
     uint64_t q_key[SS_QCAP];                     // deferred table probes: the k-mers that passed the filter
-    uint32_t g_mask[32 + 8];                     // window masks of the non-empty groups of the unit
-    uint32_t g_off[32 + 8];                      // their word offsets into codes
+    uint2 g_ent[32 + 8];                         // non-empty groups of the unit: {window mask, byte offset of its codes}
     uint64_t full[SS_STAGES];                    // my mbarriers
     uint32_t qn, pad_;                           // queued survivors
 };
@@ -395,8 +415,8 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
 
     uint32_t n_kmers = 0, n_hits = 0, n_second = 0, n_reads = 0, n_table = 0, n_ones = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t half = lane >> 4;                    // which 32-bit word my window starts in
-    const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside it
+    const uint32_t fsh = (2u * lane) & 31u;             // funnel shift inside the 32-bit word my window starts in
+    const char *const codes_lane = reinterpret_cast<const char *>(ws.codes) + 4u * (lane >> 4);   // ... which is word lane / 16 of the group
     const uint32_t khi_mask = (uint32_t)(tv.kmask >> 32), klo_mask = (uint32_t)tv.kmask;
     const uint32_t phi_mask = (uint32_t)(tv.kmask >> 34), plo_mask = (uint32_t)(tv.kmask >> 2);   // the first k-1 bases
 
@@ -443,12 +463,8 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
             }
             uint32_t nonempty = __ballot_sync(0xFFFFFFFFu, my_w != 0u);
             n_groups = __popc(nonempty);
-            if (my_w) {
-                uint32_t r = __popc(nonempty & lt_mask);
-                ws.g_mask[r] = my_w;
-                ws.g_off[r] = 2u * lane;              // word offset of the group's codes
-            }
-            if (lane < UNROLL) { ws.g_mask[n_groups + lane] = 0; ws.g_off[n_groups + lane] = 0; }
+            if (my_w) ws.g_ent[__popc(nonempty & lt_mask)] = make_uint2(my_w, 8u * lane);
+            if (lane < UNROLL) ws.g_ent[n_groups + lane] = make_uint2(0u, 0u);
             __syncwarp();
         }
         for (uint32_t g = 0; g < n_groups; g += UNROLL) {
@@ -456,9 +472,10 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
             bool ok[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                ok[u] = (ws.g_mask[g + u] >> lane) & 1u;
+                const uint2 ge = ws.g_ent[g + u];
+                ok[u] = (ge.x >> lane) & 1u;
                 // my window = 2k bits starting at bit 2*lane of the group's codes: three 32-bit words
-                const uint32_t *cw = ws.codes + ws.g_off[g + u] + half;
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(codes_lane + ge.y);
                 uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2];
                 k0[u] = __funnelshift_r(w0, w1, fsh) & klo_mask;
                 k1[u] = __funnelshift_r(w1, w2, fsh) & khi_mask;
@@ -492,8 +509,10 @@ ss_probe_kernel(const uint8_t *__restrict__ text, uint64_t text_len, uint32_t un
                 bool pass[UNROLL], any = false;
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    const ss_fword m = s_pat[hl[u] & (SS_NPAT - 1)];
-                    bool hit = need[u] && (fw[u] & m) == m;
+                    // looked up by every lane, wanted or not: a pattern is never 0, so fw == 0 (no load) cannot pass
+                    const ss_fword m = *reinterpret_cast<const ss_fword *>(
+                        reinterpret_cast<const char *>(s_pat) + (hh[u] & ((SS_NPAT - 1u) * (uint32_t)sizeof(ss_fword))));
+                    bool hit = (fw[u] & m) == m;
                     if (SS_FILTER_PAIRS) {
                         const bool next = __shfl_down_sync(0xFFFFFFFFu, hit, 1);
                         hit = ((lane & 1u) && lane != 31u) ? next : hit;
@@ -701,12 +720,12 @@ __global__ void ss_filter_build_kernel(const uint64_t *__restrict__ keys, const 
 #if SS_FILTER_PAIRS
     const uint64_t pre = keys[i] & (kmask >> 2), suf = keys[i] >> 2;      // first / last k-1 bases
     ss_hash2((uint32_t)pre, (uint32_t)(pre >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(ss_pat_index(hh)));
     ss_hash2((uint32_t)suf, (uint32_t)(suf >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(ss_pat_index(hh)));
 #else
     ss_hash2((uint32_t)keys[i], (uint32_t)(keys[i] >> 32), hh, hl);
-    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(hl & (SS_NPAT - 1)));
+    atomicOr(filter + __umulhi(hl, n_words), ss_filter_pattern(ss_pat_index(hh)));
 #endif
 }
 

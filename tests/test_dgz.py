@@ -1,0 +1,125 @@
+"""The device inflate of ORDINARY gzip streams (strainscan_b200/csrc/ss_dgz.cuh: block starts found per piece, marker-symbol
+decode with an unknown window, exact stitching, window chain, resolve) run on the CPU with the same source
+(ss_dgz_inflate_host) against Python's zlib/gzip -- the stand-in for the `zcat` of library/identify.py:82.  The GPU form
+of the same pipeline is checked in tests/test_gpu_parity.py."""
+import ctypes as C
+import gzip
+import io
+import zlib
+
+import numpy as np
+import pytest
+
+from strainscan_b200 import _lib
+from tests import util
+
+
+def dgz(blob, first=0, stop=None, max_pieces=64, piece=8192, sym_per_byte=64, cap=None):
+    lib = _lib.load()
+    cap = cap or (len(blob) * 40 + (1 << 20))
+    out = C.create_string_buffer(cap)
+    n, stopped = C.c_size_t(), C.c_size_t()
+    stats = (C.c_uint64 * 4)()
+    rc = lib.ss_dgz_inflate_host(blob, len(blob), first, len(blob) if stop is None else stop, max_pieces, piece, sym_per_byte,
+                                 out, cap, C.byref(n), C.byref(stopped), stats)
+    if rc:
+        raise _lib.StrainScanB200Error(rc, lib.ss_last_error().decode())
+    return out.raw[:n.value], stopped.value, list(stats)
+
+
+@pytest.fixture(scope="module")
+def fastq():
+    rng = np.random.default_rng(11)
+    g = util.rand_genome(rng, 80_000)
+    return util.make_reads(rng, g, 9000, read_len=150, var_len=True)      # ~3 MB
+
+
+def test_single_stream_levels_and_piece_sizes(fastq):
+    for level in (1, 6, 9):
+        blob = gzip.compress(fastq, level)
+        for piece, max_pieces in ((4096, 1000), (16384, 7), (65536, 3), (1 << 20, 2)):
+            text, stopped, st = dgz(blob, max_pieces=max_pieces, piece=piece)
+            assert text == fastq, (level, piece)
+            assert stopped == len(blob) and st[3] == 1
+        # most pieces really start in the middle of the stream (found block starts), and their text went through markers
+        _, _, st = dgz(blob, max_pieces=1000, piece=16384)
+        assert st[1] > 5 and st[1] <= st[0] + st[2]
+
+
+def test_stream_shapes(fastq):
+    shapes = {}
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, zlib.Z_FIXED)
+    shapes["fixed_huffman"] = co.compress(fastq) + co.flush()               # no dynamic header to find: one piece runs through
+    shapes["stored"] = gzip.compress(fastq, 0)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31, 1)
+    shapes["memlevel1"] = co.compress(fastq) + co.flush()                   # a new block every ~100 symbols
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = []
+    for i in range(0, len(fastq), 9973):
+        parts += [co.compress(fastq[i:i + 9973]), co.flush(zlib.Z_SYNC_FLUSH)]
+    shapes["sync_flush"] = b"".join(parts) + co.flush()
+    b = io.BytesIO()
+    with gzip.GzipFile(filename="reads_R1.fastq", mode="wb", fileobj=b, mtime=1) as gz:
+        gz.write(fastq)
+    shapes["fname_header"] = b.getvalue()
+    shapes["trailing_garbage"] = gzip.compress(fastq) + b"\0\0\0not a member"
+    shapes["multi_member"] = b"".join(gzip.compress(fastq[i:i + 70_001], 6) for i in range(0, len(fastq), 70_001))
+    shapes["empty_members"] = gzip.compress(b"") + gzip.compress(fastq[:50_000]) + gzip.compress(b"") + gzip.compress(fastq[50_000:])
+    low = b"A" * 300_000 + fastq[:10_000] + b"\n".join([b"ACGT" * 30] * 4000)      # very high compression ratio
+    for name, blob in shapes.items():
+        text, _, st = dgz(blob, max_pieces=50, piece=8192, sym_per_byte=512 if name in ("fixed_huffman", "stored") else 64)
+        assert text == fastq, name
+    text, _, st = dgz(gzip.compress(low, 9), max_pieces=16, piece=4096, sym_per_byte=256)
+    assert text == low
+    # a block that inflates to more than a piece's whole buffer is refused loudly, never mis-decoded
+    with pytest.raises(_lib.StrainScanB200Error):
+        dgz(gzip.compress(b"A" * 3_000_000, 9), max_pieces=4, piece=4096, sym_per_byte=2)
+
+
+def test_member_ranges(fastq):
+    """Member-split files: a decoder owns the members that start in [first, stop) and says where it stopped."""
+    chunks = [fastq[i:i + 200_003] for i in range(0, len(fastq), 200_003)]
+    blobs = [gzip.compress(c, 6) for c in chunks]
+    starts = np.cumsum([0] + [len(b) for b in blobs]).tolist()
+    blob = b"".join(blobs)
+    text, stopped, st = dgz(blob, first=starts[2], stop=starts[5], piece=4096, max_pieces=33)
+    assert text == b"".join(chunks[2:5]) and stopped == starts[5] and st[3] == 3
+    text, stopped, _ = dgz(blob, first=starts[1], stop=starts[1] + 1, piece=4096, max_pieces=9)
+    assert text == chunks[1] and stopped == starts[2]
+    text, stopped, _ = dgz(blob, first=starts[-2], piece=4096)
+    assert text == chunks[-1] and stopped == len(blob)
+
+
+def test_corrupt_streams_fail(fastq):
+    blob = bytearray(gzip.compress(fastq, 6))
+    for at in (len(blob) // 3, len(blob) // 2, len(blob) - 20):
+        bad = bytearray(blob)
+        bad[at] ^= 0x5A
+        try:
+            text, _, _ = dgz(bytes(bad), piece=8192)
+        except _lib.StrainScanB200Error:
+            continue
+        # a flipped bit that still decodes (literal changed) must at least not be silently "repaired"
+        assert text != fastq
+    with pytest.raises(_lib.StrainScanB200Error):
+        dgz(bytes(blob[:len(blob) // 2]), piece=8192)                        # truncated
+    with pytest.raises(_lib.StrainScanB200Error):
+        dgz(b"hello, not gzip at all" * 100)
+
+
+def test_random_binary_streams_roundtrip():
+    rng = np.random.default_rng(3)
+    for trial in range(12):
+        n = int(rng.integers(1, 400_000))
+        kind = trial % 3
+        if kind == 0:
+            data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()                      # incompressible
+        elif kind == 1:
+            data = bytes(rng.integers(0, 4, n, dtype=np.uint8) + 65)                      # 2 bits per byte
+        else:
+            words = [bytes(rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(50)]
+            data = b" ".join(words[int(i)] for i in rng.integers(0, 50, n // 6 + 1))      # long matches
+        level = int(rng.choice([1, 4, 6, 9]))
+        blob = gzip.compress(data, level)
+        text, _, _ = dgz(blob, piece=int(rng.choice([4096, 8192, 32768])), max_pieces=int(rng.integers(2, 40)), sym_per_byte=64)
+        assert text == data, (trial, level)

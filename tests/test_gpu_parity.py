@@ -563,3 +563,65 @@ def test_host_generator_equals_device_generator(eng):
     buf = torch.empty(n * rec, dtype=torch.uint8, device="cuda")
     eng.synth_reads_device(p, buf.data_ptr(), n, first)
     assert np.array_equal(buf.cpu().numpy(), synth_host.reads(p, n, first, threads=3))
+
+
+@pytest.mark.parametrize("shape", ["single", "members", "level9_small_batches"])
+def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape):
+    """ss_dgz.cu: ordinary (non-blocked) gzip read files inflated on the device -- block starts found per piece, marker
+    symbols, exact stitching, window chain -- through ss_count_files and ss_reads_from_files, against the oracle.  Small
+    pieces / batches force many pieces, several batches and records carried from batch to batch; sharded runs split a
+    multi-member file at member starts."""
+    rng = np.random.default_rng({"single": 1, "members": 2, "level9_small_batches": 3}[shape])
+    G = util.rand_genome(rng, 150_000)
+    fa = util.make_db(rng, G, 31, 20_000, both_strands=True)
+    fq1 = util.make_reads(rng, G, 20_000, 150, var_len=True)                 # ~6 MB each
+    fq2 = util.make_reads(rng, G, 18_000, 120, var_len=True, crlf=False)
+    monkeypatch.setenv("SS_DGZ_MIN_BYTES", "0")
+    monkeypatch.setenv("SS_DGZ_PIECE_BYTES", "16384")
+    monkeypatch.setenv("SS_DGZ_SYM_PER_BYTE", "32")
+    monkeypatch.setenv("SS_DGZ_BATCH_MB", "8")
+    p1, p2 = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq.gz")
+    if shape == "single":
+        open(p1, "wb").write(gzip.compress(fq1, 6))
+        open(p2, "wb").write(gzip.compress(fq2[:-1], 1))                       # no final newline
+    elif shape == "members":
+        step = 700_001                                                          # members cut records apart
+        open(p1, "wb").write(b"".join(gzip.compress(fq1[i:i + step], 6) for i in range(0, len(fq1), step)))
+        open(p2, "wb").write(b"".join(gzip.compress(fq2[i:i + step], 1) for i in range(0, len(fq2), step)) + b"\0\0trailing garbage")
+    else:
+        monkeypatch.setenv("SS_DGZ_MAX_PIECES", "16")
+        open(p1, "wb").write(gzip.compress(fq1 + b"\n\n", 9))                  # blank tail lines
+        open(p2, "wb").write(gzip.compress(fq2, 9))
+    ks = eng.kmerset_from_text(fa, 31)
+    o = adapters.count_dense(fa, 31, [fq1, fq2])
+    got, st = eng.count_files(ks, [p1, p2])
+    assert np.array_equal(got.astype(np.uint64), o.cnt) and st.n_reads == 38_000
+    reads = eng.reads_from_files([p1, p2])
+    got2, st2 = eng.count(ks, reads)
+    assert np.array_equal(got2, got) and st2.n_reads == 38_000
+    # the host decoders give the same vector (SS_DGZ=0)
+    monkeypatch.setenv("SS_DGZ", "0")
+    got3, _ = eng.count_files(ks, [p1, p2])
+    assert np.array_equal(got3, got)
+    monkeypatch.setenv("SS_DGZ", "1")
+    if shape == "members":                                                      # shards: every member decoded by exactly one
+        monkeypatch.setenv("SS_GZ_SPLIT", "2")
+        monkeypatch.setenv("SS_GZ_PART_BYTES", str(256 << 10))
+        for n_shards in (2, 5):
+            acc = np.zeros_like(got, dtype=np.uint64)
+            n_reads = 0
+            for s in range(n_shards):
+                part, stp = eng.count_files(ks, [p1, p2], s, n_shards)
+                acc += part
+                n_reads += stp.n_reads
+            assert np.array_equal(acc, o.cnt) and n_reads == 38_000, n_shards
+            # mixed: one shard on the device path, the others on the host threads -- the same partition of the reads
+            monkeypatch.setenv("SS_DGZ", "0")
+            acc2 = np.zeros_like(acc)
+            for s in range(n_shards):
+                if s == 1:
+                    monkeypatch.setenv("SS_DGZ", "1")
+                acc2 += eng.count_files(ks, [p1, p2], s, n_shards)[0]
+                monkeypatch.setenv("SS_DGZ", "0")
+            monkeypatch.setenv("SS_DGZ", "1")
+            assert np.array_equal(acc2, o.cnt), n_shards

@@ -463,3 +463,32 @@ def test_multi_member_gzip_odd_shapes(tmp_path, monkeypatch):
     with pytest.raises(_lib.StrainScanB200Error):
         for s in range(3):
             ingest([p], s, 3)
+    # Header look-alikes inside the data.  (1) the gzip magic + a fixed-Huffman "block" of text bytes, in a quality line
+    # of a STORED member: the trial decode of the member finder rejects it, the file splits as usual.  (2) a complete,
+    # valid empty gzip member spelled out inside stored text: no finder can tell it from a real member, so the split
+    # mode must fail loudly (and SS_GZ_SPLIT=0 must still read the file like zcat).
+    lines = fq.split(b"\n")
+    q = len(lines) // 2 // 4 * 4 + 3
+    fake = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + b"\x4b\x4c\x4a" * 40
+    look = lines[:]
+    look[q] = (fake + look[q])[:len(look[q])] if len(look[q]) > 60 else look[q]
+    look[q - 2] = b"N" * len(look[q])
+    text1 = b"\n".join(look)
+    half = text1.index(b"\n@read", len(text1) // 5) + 1
+    p = str(tmp_path / "lookalike.fq.gz")
+    open(p, "wb").write(gzip.compress(text1[:half], 0) + gzip.compress(text1[half:], 0))
+    for n_shards in (1, 4):
+        assert records(b"".join(ingest([p], s, n_shards)[0] for s in range(n_shards))) == records(text1)
+    empty_member = gzip.compress(b"", mtime=0)
+    evil = lines[:]
+    evil[q] = empty_member + b"I" * 200
+    evil[q - 2] = b"A" * len(evil[q])
+    text2 = b"\n".join(evil)
+    p = str(tmp_path / "evil.fq.gz")
+    open(p, "wb").write(gzip.compress(text2[:half], 0) + gzip.compress(text2[half:], 0))
+    with pytest.raises(_lib.StrainScanB200Error) as ei:
+        for s in range(4):
+            ingest([p], s, 4)
+    assert "SS_GZ_SPLIT=0" in str(ei.value)
+    monkeypatch.setenv("SS_GZ_SPLIT", "0")
+    assert records(ingest([p])[0]) == records(text2)
