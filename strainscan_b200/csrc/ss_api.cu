@@ -942,7 +942,7 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
     size_t carry_cap = 0;
     size_t scratch_cap = 2048ull << 20;
     if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) scratch_cap = (size_t)v << 20; }
-    uint32_t piece = 128u << 10, max_pieces = 4096;
+    uint32_t piece = 128u << 10, max_pieces = 7104;                 // two waves of 148 x 24 decoders
     if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) piece = (uint32_t)v; }
     if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= 8192) max_pieces = (uint32_t)v; }
     auto cleanup = [&]() { cudaFree(d_alloc); cudaFree(d_scratch); cudaFree(d_carry); };
@@ -953,6 +953,8 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
     DGZ_TRY(cudaMemsetAsync(d_alloc, 0, 64, c->copy_stream));
     DGZ_TRY(cudaMemsetAsync(d_comp + n_up, 0, 64, c->copy_stream));
     // ---- upload the compressed bytes (several readers, pinned chunks, any order)
+    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
+    double t_up = now_ms(), t_inflate = 0, t_cut = 0, t_sink = 0;
     rc = c->src->start_raw(df.path.c_str(), base_off, df.up_hi);
     if (rc) { cleanup(); return fail(rc, c->src->error()); }
     {
@@ -970,6 +972,7 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
         if (ce != cudaSuccess) { cleanup(); return ss_cuda_fail(ce, "H2D compressed reads", __FILE__, __LINE__); }
         if (src_rc) { cleanup(); return fail(src_rc, c->src->error()); }
     }
+    t_up = now_ms() - t_up;
     // ---- inflate, batch by batch
     ss_dgz dz;
     rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, max_pieces, piece);
@@ -980,8 +983,10 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
     const std::string no_boundary = df.path + ": no FASTQ record boundary within a batch of the device inflate";
     while (!done) {
         size_t n = 0;
+        double t0 = now_ms();
         rc = dz.next(d_scratch + carry, scratch_cap - carry, &n, &done);
         if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
+        t_inflate += now_ms() - t0; t0 = now_ms();
         size_t len = carry + n, start = 0;
         if (first) {
             const size_t w = std::min(len, h_win.size());
@@ -1076,14 +1081,18 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
                 cudaFree(moved);
                 text = d_scratch;
             }
+            t_cut += now_ms() - t0; t0 = now_ms();
             rc = sink(text, cut - start);
             if (rc) { cleanup(); return rc; }
+            t_sink += now_ms() - t0;
         }
         if (carry) DGZ_TRY(cudaMemcpyAsync(d_scratch, d_carry, carry, cudaMemcpyDeviceToDevice, c->stream));
     }
-    if (getenv("SS_DEBUG_TIMING"))
-        fprintf(stderr, "[ss dgz] %s: %llu batches, %llu/%llu pieces used, %llu members\n", df.path.c_str(), (unsigned long long)dz.batches(),
-                (unsigned long long)dz.pieces_used(), (unsigned long long)(dz.pieces_found() + dz.batches()), (unsigned long long)dz.members());
+    if (dbg)
+        fprintf(stderr, "[ss dgz] %s: %llu batches, %llu/%llu pieces used, %llu members; upload %.1f ms (%.1f MB), inflate %.1f ms "
+                "(find+decode %.1f, windows+resolve %.1f), cuts %.1f ms, sink %.1f ms\n", df.path.c_str(), (unsigned long long)dz.batches(),
+                (unsigned long long)dz.pieces_used(), (unsigned long long)(dz.pieces_found() + dz.batches()), (unsigned long long)dz.members(),
+                t_up, n_up / 1e6, t_inflate, dz.ms_decode(), dz.ms_resolve(), t_cut, t_sink);
 #undef DGZ_TRY
     cudaStreamSynchronize(c->stream);
     cleanup();

@@ -1,5 +1,6 @@
 // ss_dgz.cu -- kernels K7..K10 and the host driver of the device inflate of ordinary gzip streams (ss_dgz.cuh).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -8,6 +9,10 @@
 #include "ss_common.cuh"
 #include "ss_dgz.cuh"
 #include "ss_dgz_host.h"
+
+#ifndef SS_DGZ_DECODERS_PER_SM
+#define SS_DGZ_DECODERS_PER_SM 24u       // one-lane decoders resident per SM (80 registers each; 7 KB of tables)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K7: find a block start for every piece but the first.  One warp per piece: the lanes try 32 consecutive bit
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(32) ss_dgz_find_kernel(const uint8_t *__restri
 // K8: marker-mode decode, one decoder (lane 0 of a one-warp CTA, tables in shared memory) per piece, pieces handed
 // out dynamically.  Huffman decoding is a serial bit chain: parallelism = pieces in flight.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, 24) ss_dgz_decode_kernel(const uint8_t *__restrict__ comp, size_t comp_size, dgz_piece *pieces,
+__global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kernel(const uint8_t *__restrict__ comp, size_t comp_size, dgz_piece *pieces,
                                                                 uint32_t n_pieces, uint64_t limit_bit, uint64_t stop_byte,
                                                                 uint16_t *__restrict__ sym_pool, uint32_t cap,
                                                                 unsigned int *__restrict__ next) {
@@ -66,16 +71,47 @@ __global__ void __launch_bounds__(1024) ss_dgz_window_kernel(const uint32_t *__r
                                                               const uint16_t *__restrict__ sym_pool, uint32_t cap,
                                                               uint8_t *__restrict__ windows, uint32_t win_len0,
                                                               unsigned int *__restrict__ err) {
+    // Every step is latency, not bandwidth: 32 KiB gathered through two dependent loads.  So a thread first issues the
+    // loads of all its 32 symbols, then all its 32 window lookups, then stores 32 bytes -- the loads of one kind are in
+    // flight together (the first form walked its 32 positions one dependent pair at a time: 24 us per piece).
+    // Positions that still lie in the OLD window are written as markers pointing at themselves shifted, so both kinds
+    // take the same path.
+    constexpr uint32_t PER = SS_DGZ_WINDOW / 1024u;     // 32
     uint32_t win_len = win_len0;
-    const uint32_t per = SS_DGZ_WINDOW / 1024u;
+    const uint32_t p0 = threadIdx.x * PER;
     for (uint32_t k = 0; k < n_acc; k++) {
-        const dgz_piece &pc = pieces[order[k]];
-        const uint8_t *w = windows + (uint64_t)k * SS_DGZ_WINDOW;
-        uint8_t *wn = windows + (uint64_t)(k + 1) * SS_DGZ_WINDOW;
-        const bool ok = dgz_next_window_part(w, win_len, sym_pool + (uint64_t)order[k] * cap, pc.n_sym, wn, threadIdx.x * per,
-                                             (threadIdx.x + 1) * per);
+        const uint32_t pi = order[k];
+        const uint32_t n = pieces[pi].n_sym;
+        const uint16_t *__restrict__ ps = sym_pool + (uint64_t)pi * cap;
+        const uint8_t *__restrict__ w = windows + (uint64_t)k * SS_DGZ_WINDOW;
+        uint8_t *__restrict__ wn = windows + (uint64_t)(k + 1) * SS_DGZ_WINDOW;
+        uint16_t x[PER];
+#pragma unroll
+        for (uint32_t j = 0; j < PER; j++) {
+            const int64_t e = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)(p0 + j);
+            x[j] = e >= 0 ? ps[e] : (uint16_t)(256 + (int64_t)SS_DGZ_WINDOW + e);
+        }
+        uint32_t v[PER / 4];
+        bool ok = true;
+#pragma unroll
+        for (uint32_t j = 0; j < PER; j++) {
+            uint32_t b;
+            if (x[j] < 256) b = x[j];
+            else {
+                const uint32_t off = (uint32_t)x[j] - 256u;
+                const int64_t e = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)(p0 + j);
+                // a marker into the part of the old window that lies in front of the stream start is an error -- unless
+                // the position itself is old-window filler (e < 0), which nothing can reference either
+                if (off + win_len < SS_DGZ_WINDOW) { b = 0; if (e >= 0) ok = false; }
+                else b = w[off];
+            }
+            if ((j & 3u) == 0) v[j >> 2] = b; else v[j >> 2] |= b << (8u * (j & 3u));
+        }
+        uint4 *o4 = reinterpret_cast<uint4 *>(wn + p0);
+        o4[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        o4[1] = make_uint4(v[4], v[5], v[6], v[7]);
         if (!ok) atomicMin(err, k);
-        win_len = min(SS_DGZ_WINDOW, win_len + pc.n_sym);
+        win_len = min(SS_DGZ_WINDOW, win_len + n);
         __syncthreads();
     }
 }
@@ -96,6 +132,10 @@ __global__ void __launch_bounds__(256) ss_dgz_resolve_kernel(const uint32_t *__r
 // ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
+static double dgz_now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 #define DGZ_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err_ = std::string("CUDA error in the device gzip inflate: ") + cudaGetErrorString(e_) + " (" #x ")"; return SS_ERR_CUDA; } } while (0)
 
 ss_dgz::~ss_dgz() { close(); }
@@ -141,10 +181,15 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     *n_out = 0; *done = done_;
     if (done_) return SS_OK;
     if (out_cap < cap_) { err_ = "device gzip inflate: output buffer smaller than one piece's text"; return SS_ERR_ARG; }
+    double t0 = dgz_now_ms();
     const uint64_t first_byte = cur_bit_ >> 3;
     uint64_t span = size_ - first_byte;
     uint32_t P = (uint32_t)std::min<uint64_t>(max_pieces_, (span + piece_ - 1) / piece_);
     P = (uint32_t)std::min<double>((double)P, (double)out_cap / ((double)piece_ * ratio_ * 1.15));
+    {   // whole waves of decoders: a last wave with a few pieces costs as much as a full one
+        const uint32_t wave = (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM;
+        if (P > wave && P < (uint32_t)std::min<uint64_t>(max_pieces_, (span + piece_ - 1) / piece_)) P -= P % wave;
+    }
     if (P == 0) P = 1;
     const uint64_t limit_bit = std::min<uint64_t>((uint64_t)size_ * 8u, (first_byte + (uint64_t)P * piece_) * 8u);
     for (uint32_t j = 0; j < P; j++) { h_pieces_[j] = dgz_piece(); h_pieces_[j].start_bit = j == 0 ? cur_bit_ : ~0ull; }
@@ -152,12 +197,13 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     DGZ_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(unsigned int), st_));
     DGZ_CUDA(cudaMemsetAsync(d_ctr_ + 1, 0xFF, sizeof(unsigned int), st_));
     if (P > 1) ss_dgz_find_kernel<<<std::min<uint32_t>(P - 1, (uint32_t)n_sm_ * 32u), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, first_byte, limit_bit, piece_);
-    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * 24u), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
+    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
                                                                                     d_sym_, cap_, d_ctr_);
     DGZ_CUDA(cudaGetLastError());
     DGZ_CUDA(cudaMemcpyAsync(h_pieces_.data(), d_pieces_, (size_t)P * sizeof(dgz_piece), cudaMemcpyDeviceToHost, st_));
     DGZ_CUDA(cudaStreamSynchronize(st_));
     batches_++;
+    ms_decode_ += dgz_now_ms() - t0; t0 = dgz_now_ms();
     // ---- the chain: a piece counts only if the accepted piece before it ended exactly on its start
     std::vector<uint32_t> order;
     std::vector<uint64_t> off;
@@ -199,6 +245,7 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     DGZ_CUDA(cudaMemcpyAsync(&bad, d_ctr_ + 1, sizeof bad, cudaMemcpyDeviceToHost, st_));
     DGZ_CUDA(cudaStreamSynchronize(st_));
     if (bad != 0xFFFFFFFFu) { err_ = "invalid compressed data (a match reaches in front of the stream start)"; return SS_ERR_IO; }
+    ms_resolve_ += dgz_now_ms() - t0;
     win_len_ = (uint32_t)std::min<uint64_t>(SS_DGZ_WINDOW, (uint64_t)win_len_ + total);
     {   // what a compressed byte has been inflating to (sizes the next batch)
         const double consumed = (double)((cur_bit_ >> 3) - first_byte);

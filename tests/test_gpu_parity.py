@@ -122,6 +122,8 @@ def test_random_vs_oracle(eng, k, filt, monkeypatch):
     if filt:
         monkeypatch.setenv("SS_FILTER", "1")
         monkeypatch.setenv("SS_FILTER_BITS", filt)
+    else:
+        monkeypatch.setenv("SS_FILTER", "0")          # the path without a filter: every k-mer probes the table
     rng = np.random.default_rng(1000 + k)
     G = util.rand_genome(rng, 200_000)
     fa = util.make_db(rng, G, k, 20_000, both_strands=True, lower_frac=0.02, junk=40)
