@@ -1090,9 +1090,9 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
     }
     if (dbg)
         fprintf(stderr, "[ss dgz] %s: %llu batches, %llu/%llu pieces used, %llu members; upload %.1f ms (%.1f MB), inflate %.1f ms "
-                "(find+decode %.1f, windows+resolve %.1f), cuts %.1f ms, sink %.1f ms\n", df.path.c_str(), (unsigned long long)dz.batches(),
+                "(find+decode %.1f, windows+resolve %.1f of which windows %.1f), cuts %.1f ms, sink %.1f ms\n", df.path.c_str(), (unsigned long long)dz.batches(),
                 (unsigned long long)dz.pieces_used(), (unsigned long long)(dz.pieces_found() + dz.batches()), (unsigned long long)dz.members(),
-                t_up, n_up / 1e6, t_inflate, dz.ms_decode(), dz.ms_resolve(), t_cut, t_sink);
+                t_up, n_up / 1e6, t_inflate, dz.ms_decode(), dz.ms_resolve(), dz.ms_windows(), t_cut, t_sink);
 #undef DGZ_TRY
     cudaStreamSynchronize(c->stream);
     cleanup();

@@ -76,57 +76,70 @@ __global__ void __launch_bounds__(1024) ss_dgz_window_kernel(const uint32_t *__r
     // flight together (the first form walked its 32 positions one dependent pair at a time: 24 us per piece).
     // Positions that still lie in the OLD window are written as markers pointing at themselves shifted, so both kinds
     // take the same path.
-    constexpr uint32_t PER = SS_DGZ_WINDOW / 1024u;     // 32
+    constexpr uint32_t PER = SS_DGZ_WINDOW / 1024u;     // 32 positions per thread: tid, tid + 1024, ... (coalesced)
     uint32_t win_len = win_len0;
-    const uint32_t p0 = threadIdx.x * PER;
     for (uint32_t k = 0; k < n_acc; k++) {
         const uint32_t pi = order[k];
         const uint32_t n = pieces[pi].n_sym;
         const uint16_t *__restrict__ ps = sym_pool + (uint64_t)pi * cap;
         const uint8_t *__restrict__ w = windows + (uint64_t)k * SS_DGZ_WINDOW;
         uint8_t *__restrict__ wn = windows + (uint64_t)(k + 1) * SS_DGZ_WINDOW;
+        const int64_t e0 = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)threadIdx.x;
         uint16_t x[PER];
 #pragma unroll
         for (uint32_t j = 0; j < PER; j++) {
-            const int64_t e = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)(p0 + j);
+            const int64_t e = e0 + (int64_t)(j * 1024u);
             x[j] = e >= 0 ? ps[e] : (uint16_t)(256 + (int64_t)SS_DGZ_WINDOW + e);
         }
-        uint32_t v[PER / 4];
+        uint8_t v[PER];
         bool ok = true;
 #pragma unroll
         for (uint32_t j = 0; j < PER; j++) {
-            uint32_t b;
-            if (x[j] < 256) b = x[j];
+            if (x[j] < 256) v[j] = (uint8_t)x[j];
             else {
                 const uint32_t off = (uint32_t)x[j] - 256u;
-                const int64_t e = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)(p0 + j);
                 // a marker into the part of the old window that lies in front of the stream start is an error -- unless
                 // the position itself is old-window filler (e < 0), which nothing can reference either
-                if (off + win_len < SS_DGZ_WINDOW) { b = 0; if (e >= 0) ok = false; }
-                else b = w[off];
+                if (off + win_len < SS_DGZ_WINDOW) { v[j] = 0; if (e0 + (int64_t)(j * 1024u) >= 0) ok = false; }
+                else v[j] = w[off];
             }
-            if ((j & 3u) == 0) v[j >> 2] = b; else v[j >> 2] |= b << (8u * (j & 3u));
         }
-        uint4 *o4 = reinterpret_cast<uint4 *>(wn + p0);
-        o4[0] = make_uint4(v[0], v[1], v[2], v[3]);
-        o4[1] = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (uint32_t j = 0; j < PER; j++) wn[j * 1024u + threadIdx.x] = v[j];
         if (!ok) atomicMin(err, k);
         win_len = min(SS_DGZ_WINDOW, win_len + n);
         __syncthreads();
     }
 }
 
-// K10: symbols -> bytes at their place in the text.  grid.y = accepted piece, grid.x strides over its symbols.
+// K10: symbols -> bytes at their place in the text.  grid.y = accepted piece, grid.x strides over its symbols; a
+// thread resolves the 8 symbols behind an 8-byte aligned OUTPUT address and writes them with one store.
 __global__ void __launch_bounds__(256) ss_dgz_resolve_kernel(const uint32_t *__restrict__ order, const uint64_t *__restrict__ text_off,
                                                               const dgz_piece *__restrict__ pieces,
                                                               const uint16_t *__restrict__ sym_pool, uint32_t cap,
                                                               const uint8_t *__restrict__ windows, uint8_t *__restrict__ out) {
     const uint32_t k = blockIdx.y;
     const uint32_t n = pieces[order[k]].n_sym;
-    const uint16_t *sym = sym_pool + (uint64_t)order[k] * cap;
-    const uint8_t *w = windows + (uint64_t)k * SS_DGZ_WINDOW;
+    const uint16_t *__restrict__ sym = sym_pool + (uint64_t)order[k] * cap;
+    const uint8_t *__restrict__ w = windows + (uint64_t)k * SS_DGZ_WINDOW;
     uint8_t *o = out + text_off[k];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) o[i] = dgz_resolve1(sym[i], w);
+    const uint32_t head = min(n, (uint32_t)((8u - (uint32_t)((uintptr_t)o & 7u)) & 7u));      // bytes in front of the first aligned address
+    if (blockIdx.x == 0 && threadIdx.x < head) o[threadIdx.x] = dgz_resolve1(sym[threadIdx.x], w);
+    const uint32_t n8 = (n - head) >> 3;                                                      // whole aligned groups of 8
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += gridDim.x * blockDim.x) {
+        const uint16_t *ps = sym + head + 8u * g;
+        uint16_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = ps[j];
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) lo |= (uint32_t)dgz_resolve1(x[j], w) << (8 * j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) hi |= (uint32_t)dgz_resolve1(x[4 + j], w) << (8 * j);
+        *reinterpret_cast<uint2 *>(o + head + 8u * g) = make_uint2(lo, hi);
+    }
+    const uint32_t tail0 = head + 8u * n8;
+    if (blockIdx.x == 0 && tail0 + threadIdx.x < n && threadIdx.x < 8) o[tail0 + threadIdx.x] = dgz_resolve1(sym[tail0 + threadIdx.x], w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,7 +251,8 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     DGZ_CUDA(cudaMemcpyAsync(d_order_, order.data(), n_acc * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
     DGZ_CUDA(cudaMemcpyAsync(d_off_, off.data(), n_acc * sizeof(uint64_t), cudaMemcpyHostToDevice, st_));
     ss_dgz_window_kernel<<<1, 1024, 0, st_>>>(d_order_, n_acc, d_pieces_, d_sym_, cap_, d_windows_, win_len_, d_ctr_ + 1);
-    ss_dgz_resolve_kernel<<<dim3(32, n_acc), 256, 0, st_>>>(d_order_, d_off_, d_pieces_, d_sym_, cap_, d_windows_, d_out);
+    if (getenv("SS_DEBUG_TIMING")) { cudaStreamSynchronize(st_); ms_windows_ += dgz_now_ms() - t0; }
+    ss_dgz_resolve_kernel<<<dim3(16, n_acc), 256, 0, st_>>>(d_order_, d_off_, d_pieces_, d_sym_, cap_, d_windows_, d_out);
     // the last window becomes the first one of the next batch
     DGZ_CUDA(cudaMemcpyAsync(d_windows_, d_windows_ + (size_t)n_acc * SS_DGZ_WINDOW, SS_DGZ_WINDOW, cudaMemcpyDeviceToDevice, st_));
     unsigned int bad = 0xFFFFFFFFu;

@@ -78,10 +78,108 @@ SS_HD bool dgz_full_test(const uint8_t *base, size_t size, uint64_t p, ssi_table
     return ssi_dynamic_tables(s.bits, t) == SSI_OK && !ssi_truncated(s.bits);
 }
 
+#ifdef __CUDA_ARCH__
+// DEVICE fast path of the Huffman loop in marker mode (the shape of ssi_huff_fast's device loop: one lane walks the
+// stream, so the loop is written for instruction count -- bit buffer, a 32-bit word index into the 4-byte aligned
+// input and one prefetched word in registers; decode tables through 32-bit shared addresses; the literal run is its own
+// inner loop and everything rarer is reached through its exits; bounds are checked once per burst of symbols).
+// Returns 1 at the end of the block, 0 when the careful loop has to go on (input or room nearly used up), < 0 on bad data.
+__device__ __forceinline__ int dgz_huff_fast_dev(ssi_stream &s, ssi_tables &t, uint16_t *sym, uint32_t &n_io, uint32_t cap,
+                                                 uint32_t fresh, bool unknown) {
+    ssi_bits &b = s.bits;
+    if (b.overrun || b.in_end - b.in < 64 || cap - n_io < 2u * 260u) return 0;
+    uint32_t cnt = b.cnt & 7u;
+    const uint8_t *in = b.in - (b.cnt >> 3);
+    uint64_t buf = b.buf & ((1ull << cnt) - 1ull);
+    while ((uintptr_t)in & 3u) { buf |= (uint64_t)(*in++) << cnt; cnt += 8u; }
+    const uint32_t *const words = reinterpret_cast<const uint32_t *>(in);
+    const uint32_t n_words = (uint32_t)((b.in_end - in) >> 2);
+    uint32_t wi = 0, n = n_io;
+    const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(t.lit), dist_sa = (uint32_t)__cvta_generic_to_shared(t.dist);
+    const uint32_t LM4 = ((1u << SSI_LIT_BITS) - 1u) << 2, DM4 = ((1u << SSI_DIST_BITS) - 1u) << 2;
+    uint32_t nextw = words[0];
+    int ret = 0;
+#define DGZ_LDS(v, addr) asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr))
+#define DGZ_REFILL() do { if (cnt < 32u) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; } } while (0)
+    uint32_t burst = 0;
+    while (ret == 0) {
+        if (burst == 0) {
+            const uint32_t words_left = n_words > wi + 8u ? n_words - wi - 8u : 0u;
+            burst = words_left >> 1;
+            if (cap - n < 2u * 260u) break;
+            const uint32_t by_out = (cap - n - 2u * 260u) / 258u + 1u;
+            if (by_out < burst) burst = by_out;
+            if (burst == 0) break;
+            if (burst > 4096u) burst = 4096u;
+        }
+        DGZ_REFILL();
+        uint32_t e;
+        bool more = true;
+        do {                                                          // literal run
+            DGZ_LDS(e, lit_sa + (((uint32_t)buf << 2) & LM4));
+            if (SSI_KIND(e) != SSI_LIT) break;
+            buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
+            sym[n++] = (uint16_t)SSI_VAL(e);
+            more = --burst != 0 && cnt >= 32u;
+        } while (more);
+        if (!more) continue;
+        burst--;
+        if (SSI_KIND(e) == SSI_SUB) {
+            buf >>= SSI_LIT_BITS; cnt -= SSI_LIT_BITS;
+            DGZ_LDS(e, lit_sa + ((SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u))) << 2));
+        }
+        buf >>= SSI_LEN(e); cnt -= SSI_LEN(e);
+        if (SSI_KIND(e) == SSI_LIT) { sym[n++] = (uint16_t)SSI_VAL(e); continue; }
+        if (SSI_KIND(e) != SSI_BASE) { ret = SSI_KIND(e) == SSI_EOB ? 1 : SSI_ERR_DATA; break; }
+        const uint32_t len = SSI_VAL(e) + ((uint32_t)buf & ((1u << SSI_EXTRA(e)) - 1u));
+        buf >>= SSI_EXTRA(e); cnt -= SSI_EXTRA(e);
+        DGZ_REFILL();
+        uint32_t d;
+        DGZ_LDS(d, dist_sa + (((uint32_t)buf << 2) & DM4));
+        if (SSI_KIND(d) == SSI_SUB) {
+            buf >>= SSI_DIST_BITS; cnt -= SSI_DIST_BITS;
+            DGZ_LDS(d, dist_sa + ((SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u))) << 2));
+        }
+        buf >>= SSI_LEN(d); cnt -= SSI_LEN(d);
+        if (SSI_KIND(d) != SSI_BASE) { ret = SSI_ERR_DATA; break; }
+        const uint32_t dist = SSI_VAL(d) + ((uint32_t)buf & ((1u << SSI_EXTRA(d)) - 1u));
+        buf >>= SSI_EXTRA(d); cnt -= SSI_EXTRA(d);
+        if (dist > SS_DGZ_WINDOW) { ret = SSI_ERR_DATA; break; }
+        uint16_t *dst = sym + n;
+        if (dist <= n - fresh) {
+            const uint16_t *src = dst - dist;
+            if (dist >= len) {                                        // no overlap: the loads do not wait for the stores
+                uint32_t i = 0;
+                for (; i + 4 <= len; i += 4) {
+                    const uint16_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
+                    dst[i] = a0; dst[i + 1] = a1; dst[i + 2] = a2; dst[i + 3] = a3;
+                }
+                for (; i < len; i++) dst[i] = src[i];
+            } else {
+                for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+            }
+        } else {
+            if (fresh != 0 || !unknown) { ret = SSI_ERR_DATA; break; }
+            for (uint32_t i = 0; i < len; i++) {
+                const int32_t idx = (int32_t)(n + i) - (int32_t)dist;
+                dst[i] = idx >= 0 ? sym[idx] : (uint16_t)(256 + (int32_t)SS_DGZ_WINDOW + idx);
+            }
+        }
+        n += len;
+    }
+#undef DGZ_REFILL
+#undef DGZ_LDS
+    b.in = reinterpret_cast<const uint8_t *>(words + wi); b.buf = buf; b.cnt = cnt;
+    n_io = n;
+    return ret;
+}
+#endif
+
 // One deflate block in marker mode.  sym[0, n) are the symbols this piece has produced so far, `fresh` the index of
 // the first symbol behind a member start (references may not reach in front of it; 0 with unknown = true means the
 // window in front of sym[0] is unknown and reaches 32 KiB back).  Returns 0 (block done), 1 (out of room: nothing
 // of this block counts, the caller stops at the block's start) or an SSI_ERR_* code.
+template <bool DGZ_TABLES_IN_SHARED = true>
 SS_HD int dgz_block(ssi_stream &s, ssi_tables &t, uint16_t *sym, uint32_t &n_io, uint32_t cap, uint32_t fresh, bool unknown) {
     ssi_bits &b = s.bits;
     ssi_refill(b);
@@ -105,7 +203,15 @@ SS_HD int dgz_block(ssi_stream &s, ssi_tables &t, uint16_t *sym, uint32_t &n_io,
     if (type == 1) { if (ssi_fixed_tables(t)) return SSI_ERR_DATA; }
     else if (type == 2) { int rc = ssi_dynamic_tables(b, t); if (rc) return rc; }
     else return ssi_truncated(b) ? SSI_ERR_TRUNC : SSI_ERR_DATA;
-    while (true) {
+    bool eob = false;
+#ifdef __CUDA_ARCH__
+    if (DGZ_TABLES_IN_SHARED) {
+        const int fr = dgz_huff_fast_dev(s, t, sym, n, cap, fresh, unknown);
+        if (fr < 0) return fr;
+        eob = fr == 1;
+    }
+#endif
+    while (!eob) {
         if (cap - n < 260u) return 1;
         ssi_refill(b);
         uint32_t e = t.lit[ssi_peek(b, SSI_LIT_BITS)];

@@ -31,6 +31,7 @@ public:
     uint64_t batches() const { return batches_; }
     double ms_decode() const { return ms_decode_; }
     double ms_resolve() const { return ms_resolve_; }
+    double ms_windows() const { return ms_windows_; }     // part of ms_resolve, SS_DEBUG_TIMING only
 
 private:
     int n_sm_ = 0;
@@ -40,7 +41,7 @@ private:
     uint32_t max_pieces_ = 0, cap_ = 0, piece_ = 0;
     uint64_t cur_bit_ = 0;
     uint32_t win_len_ = 0;
-    double ms_decode_ = 0, ms_resolve_ = 0;
+    double ms_decode_ = 0, ms_resolve_ = 0, ms_windows_ = 0;
     double ratio_ = 4.0;              // text bytes per compressed byte seen so far
     bool done_ = false;
     uint64_t members_ = 0, pieces_found_ = 0, pieces_used_ = 0, batches_ = 0;

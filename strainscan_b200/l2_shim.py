@@ -71,15 +71,24 @@ class StrainMatrix:
     With `engine` (or at first use on the GPU) the CSC arrays are uploaded once into a persistent device handle
     (ss_strain_matrix_create), so that the ~45 reductions Pre_Scan asks for per cluster move only y and the mask."""
 
-    def __init__(self, X, engine=None):
-        import scipy.sparse as sp
-        X = sp.csc_matrix(X)
-        X.eliminate_zeros()
-        X.sort_indices()
-        self.n_rows, self.n_strains = X.shape
+    def __init__(self, X, engine=None, _csc=None):
+        if _csc is not None:
+            self.n_rows, self.n_strains, self.col_ptr, self.rows = _csc
+        elif isinstance(X, np.ndarray):
+            # the dense rows x strains array detect_strains builds (pX = X.A): one pass to a strains x rows bool array,
+            # then the row indices strain by strain (scipy's dense -> CSC conversion is several times slower)
+            if X.ndim != 2:
+                raise ValueError("StrainMatrix: a 2-D matrix is expected, got shape %r" % (X.shape,))
+            self.n_rows, self.n_strains, self.col_ptr, self.rows = _csc_of_strains_by_rows(np.ascontiguousarray(X.T != 0))
+        else:
+            import scipy.sparse as sp
+            X = sp.csc_matrix(X)
+            X.eliminate_zeros()
+            X.sort_indices()
+            self.n_rows, self.n_strains = X.shape
+            self.col_ptr = X.indptr.astype(np.uint64)
+            self.rows = X.indices.astype(np.uint32)
         self.shape = (self.n_rows, self.n_strains)
-        self.col_ptr = X.indptr.astype(np.uint64)
-        self.rows = X.indices.astype(np.uint32)
         self._dev = None
         self._eng = engine
 
@@ -110,6 +119,17 @@ class StrainMatrix:
             self.free()
         except Exception:
             pass
+
+
+def _csc_of_strains_by_rows(Xt):
+    """(n_rows, n_strains, col_ptr, rows) of a dense STRAINS x ROWS array (any dtype): np.flatnonzero row by row."""
+    S, R = Xt.shape
+    parts = [np.flatnonzero(Xt[j]).astype(np.uint32) for j in range(S)]
+    col_ptr = np.zeros(S + 1, dtype=np.uint64)
+    if S:
+        col_ptr[1:] = np.cumsum([p.size for p in parts])
+    rows = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
+    return R, S, col_ptr, rows
 
 
 class _StrainsByRows:
@@ -146,8 +166,11 @@ def _strains_by_rows(X, y_len, what):
     else:
         if getattr(X, "ndim", 2) != 2 or X.shape[1] != y_len:
             raise ValueError("%s: matrix is %s but y has %d entries: expected strains x rows" % (what, getattr(X, "shape", None), y_len))
-        import scipy.sparse as sp
-        m = StrainMatrix(sp.csr_matrix(X).T)          # CSR of strains x rows = CSC of rows x strains
+        if isinstance(X, np.ndarray):
+            m = StrainMatrix(None, _csc=_csc_of_strains_by_rows(X))     # strains x rows, row by row
+        else:
+            import scipy.sparse as sp
+            m = StrainMatrix(sp.csr_matrix(X).T)      # CSR of strains x rows = CSC of rows x strains
     if m.n_rows != y_len:
         raise ValueError("%s: matrix has %d rows but y has %d entries" % (what, m.n_rows, y_len))
     return m
