@@ -380,7 +380,7 @@ class Ctx:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.eng = Engine(self.local_rank)
-        self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.eng.follow_torch_stream()          # kernels and NCCL collectives ordered on one stream
         self.params = synth.default_params(n_leaves=args.leaves, seed=args.seed)
         self.sizes = synth.node_sizes(self.params, seed=args.seed)
         t0 = time.perf_counter()
@@ -468,6 +468,8 @@ class Ctx:
                         "(`traffic`, ncu, per launch) is ~4x smaller than the algorithmic bytes and `frac` is NOT a statement about "
                         "DRAM saturation: what binds the kernel is issue slots and the latency of the L2 filter loads (DESIGN.md "
                         "section 3); `frac_of_random_gather` compares the k-mer rate with the measured random-sector ceiling",
+                "dram_traffic_gbps": (traffic / (probe_ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac": (traffic / (probe_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "random_sector_gather_gbps": rand_gbps,
                 "frac_of_random_gather": (st.n_kmers * 32.0 * (1 + p2) / (probe_ms * 1e-3) / 1e9 / rand_gbps)
                 if rand_gbps else None}, h, p2
@@ -817,7 +819,11 @@ def run_c5(args):
         ms, wall, sts = cx.timed(step, min(args.warmup, 3), steps)
         st = sts[-1]
         tk, th, _, tr, _ = cx.sum_stats(st)
-        assert tr == total and cx.valid_sum(counts) == th
+        vs = cx.valid_sum(counts)
+        if rank == 0:
+            sys.stderr.write("[c5] %d reads: %.3f ms/step, reads seen %d, hits %d, sum of counts %d\n" % (total, ms, tr, th, vs))
+        assert tr == total, "ranks scanned %d reads, the point has %d" % (tr, total)
+        assert vs == th, "sum of valid-record counts %d != hits %d at %d reads" % (vs, th, total)
         points.append({"reads": total, "reads_per_gpu": per, "kmers": tk, "ms_per_step": ms, "wall_ms_per_step": wall,
                        "kmers_per_s": tk / (ms * 1e-3), "reads_per_s": total / (ms * 1e-3),
                        "rank0_ms": {"index": sum(s.ms_index for s in sts) / len(sts),

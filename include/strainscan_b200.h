@@ -84,7 +84,9 @@ int ss_init(int device, ss_ctx **ctx);
 int ss_shutdown(ss_ctx *ctx);
 const char *ss_last_error(void);
 /* Run the kernels on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) so the
- * caller can order its own work (NCCL all-reduce, CUDA events) after them; NULL = the context's own. */
+ * caller can order its own work (NCCL all-reduce, CUDA events) after them AND the next pass after that work;
+ * NULL = the context's own non-blocking stream.  To name the default stream pass cudaStreamLegacy
+ * ((cudaStream_t)0x1), not 0 -- strainscan_b200.Engine.follow_torch_stream() does. */
 int ss_set_stream(ss_ctx *ctx, void *stream);
 /* name (<= name_cap bytes), SM count, total memory */
 int ss_device_info(const ss_ctx *ctx, char *name, size_t name_cap, int *n_sm, uint64_t *mem_bytes);

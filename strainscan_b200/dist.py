@@ -68,7 +68,7 @@ def count_sharded(engine, kset, fq_paths, group=None):
     reads = cached_reads(engine, fq_paths, rank, n)
     dev = torch.device("cuda", engine.device)
     out = torch.zeros(max(kset.n_records, 1), dtype=torch.int32, device=dev)
-    engine.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    engine.follow_torch_stream(dev)          # the all-reduce below and the next pass are ordered after these kernels
     st = engine.count_device(kset, reads, out.data_ptr())
     allreduce_counts(out, group)
     return out[:kset.n_records], st

@@ -45,9 +45,21 @@ class Engine:
         except Exception:
             pass
 
+    CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the handle that NAMES the default stream (0 means "the context's own")
+
     def set_stream(self, cuda_stream_ptr):
-        """Launch on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own."""
+        """Launch on the caller's stream (a cudaStream_t handle); 0 = the context's own non-blocking stream."""
         check(self.lib.ss_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) or None)))
+
+    def follow_torch_stream(self, device=None):
+        """Launch on torch's CURRENT stream, so that torch work issued next (an NCCL all-reduce of the count vector,
+        a reduction, an event) is ordered after the kernels AND the next pass is ordered after that work.  torch's
+        default stream has handle 0, which ss_set_stream reads as "own stream": it is passed as cudaStreamLegacy.
+        (With the own stream a pass started right after an all-reduce would overwrite the vector while NCCL still
+        reads it -- seen at 8 GPUs with sub-millisecond passes.)"""
+        import torch
+        h = int(torch.cuda.current_stream(device if device is not None else self.device).cuda_stream)
+        self.set_stream(h if h else self.CUDA_STREAM_LEGACY)
 
     def device_info(self):
         name = C.create_string_buffer(256)
