@@ -92,6 +92,11 @@ struct ss_ctx {
     unsigned long long *h_bin = nullptr;         // pinned: [0..5] the round's scan statistics, then the uint32 d_bin_n mirror
     uint64_t bin_pool_chunks = 0, bin_pool_want = 0;
     ss_text_source *src = nullptr;               // file ingest: producer threads + pinned chunk pool (lazy)
+    // device inflate of ordinary gzip (ss_dgz.cu): decoder buffers and the text batch buffer, kept from file to file and
+    // call to call (allocating ~11 GB per file cost more than a tenth of an 8-GPU config-3 pass); freed by ss_shutdown
+    ss_dgz *dgz = nullptr;
+    uint8_t *d_dgz_scratch = nullptr;
+    size_t dgz_scratch_cap = 0;
     cudaEvent_t ev_pend[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -208,6 +213,8 @@ extern "C" int ss_shutdown(ss_ctx *c) {
         cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]);
     }
     delete c->src;
+    delete c->dgz;
+    cudaFree(c->d_dgz_scratch);
     for (int i = 0; i < SS_NGZ; i++) {
         cudaFree(c->d_comp[i]); cudaFree(c->d_members[i]);
         cudaEventDestroy(c->ev_gz_done[i]); cudaEventDestroy(c->ev_gz_copied[i]);
@@ -932,49 +939,84 @@ static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, d
 
 // Inflate one file on the device and hand its text out in pieces of whole FASTQ records:
 // sink(const uint8_t *d_text, size_t n) -> SS_* code.  `d_text` stays valid until the sink returns.
-template <typename Sink>
-static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
-    if (df.first_member >= df.size) return SS_OK;
-    int rc = ensure_source(c);
-    if (rc) return rc;
+// the compressed bytes of one file (range) on the device
+struct dgz_upload {
+    uint8_t *d_alloc = nullptr;       // 64 bytes of zero padding, the bytes, 64 bytes of zero padding
+    double ms = 0;
+    int rc = SS_OK;
+    std::string msg;
+};
+
+// Upload [first_member, up_hi) of the file: several readers, pinned chunks, any order, H2D on the copy stream.
+// Runs beside the inflate of the PREVIOUS file (its own thread): touches the text source and the copy stream only.
+static void dgz_upload_file(ss_ctx *c, const dgz_file &df, dgz_upload &up) {
+    up = dgz_upload();
+    if (df.first_member >= df.size) return;
+    cudaSetDevice(c->device);
+    const double t0 = now_ms();
     const size_t base_off = df.first_member, n_up = df.up_hi - base_off;
-    uint8_t *d_alloc = nullptr, *d_scratch = nullptr, *d_carry = nullptr;
+    auto cuda_fail = [&](cudaError_t e, const char *what) {
+        up.rc = SS_ERR_CUDA; up.msg = std::string("CUDA error (") + cudaGetErrorString(e) + ") in the upload of " + df.path + ": " + what;
+        cudaFree(up.d_alloc); up.d_alloc = nullptr;
+    };
+    cudaError_t ce = cudaMalloc(&up.d_alloc, n_up + 128);
+    if (ce != cudaSuccess) { cuda_fail(ce, "cudaMalloc"); return; }
+    uint8_t *d_comp = up.d_alloc + 64;
+    cudaMemsetAsync(up.d_alloc, 0, 64, c->copy_stream);
+    cudaMemsetAsync(d_comp + n_up, 0, 64, c->copy_stream);
+    int rc = c->src->start_raw(df.path.c_str(), base_off, df.up_hi);
+    if (rc) { up.rc = rc; up.msg = c->src->error(); cudaFree(up.d_alloc); up.d_alloc = nullptr; return; }
+    pending_ring pend(c);
+    while (ss_chunk *ch = c->src->next()) {
+        ce = cudaMemcpyAsync(d_comp + (ch->file_off - base_off), ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
+        if (ce != cudaSuccess) { c->src->release(ch); break; }
+        ce = pend.push(ch, c->copy_stream);
+        if (ce != cudaSuccess) break;
+    }
+    pend.drain();
+    int src_rc = c->src->finish();
+    cudaStreamSynchronize(c->copy_stream);
+    if (ce != cudaSuccess) { cuda_fail(ce, "H2D of compressed reads"); return; }
+    if (src_rc) { up.rc = src_rc; up.msg = c->src->error(); cudaFree(up.d_alloc); up.d_alloc = nullptr; return; }
+    up.ms = now_ms() - t0;
+}
+
+// Inflate one uploaded file on the device and hand its text out in pieces of whole FASTQ records:
+// sink(const uint8_t *d_text, size_t n) -> SS_* code.  `d_text` stays valid until the sink returns.
+template <typename Sink>
+static int dgz_inflate_file(ss_ctx *c, dgz_file &df, const dgz_upload &up, Sink &&sink) {
+    if (df.first_member >= df.size) return SS_OK;
+    int rc = SS_OK;
+    const size_t base_off = df.first_member, n_up = df.up_hi - base_off;
+    uint8_t *d_scratch = nullptr, *d_carry = nullptr;
     size_t carry_cap = 0;
     size_t scratch_cap = 2048ull << 20;
     if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) scratch_cap = (size_t)v << 20; }
-    uint32_t piece = 128u << 10, max_pieces = 7104;                 // two waves of 148 x 24 decoders
+    // Pieces of ~128 KiB, sized so that the file is a whole number of WAVES of decoders (148 SMs x 24): a last wave with
+    // a few pieces takes as long as a full one (an eighth of a config-3 file is 2.5 waves of 128 KiB pieces).
+    const uint32_t wave = (uint32_t)c->n_sm * 24u;
+    uint32_t piece = 128u << 10, max_pieces = 2 * wave;
+    {
+        const double waves = std::max(1.0, std::floor((double)n_up / ((double)wave * piece) + 0.5));
+        const double fit = std::ceil((double)n_up / (waves * wave) / 4096.0) * 4096.0;
+        if (fit >= (64u << 10) && fit <= (256u << 10)) piece = (uint32_t)fit;
+    }
     if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) piece = (uint32_t)v; }
     if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= 8192) max_pieces = (uint32_t)v; }
-    auto cleanup = [&]() { cudaFree(d_alloc); cudaFree(d_scratch); cudaFree(d_carry); };
+    auto cleanup = [&]() { cudaFree(d_carry); };
 #define DGZ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
-    DGZ_TRY(cudaMalloc(&d_alloc, n_up + 128));
-    DGZ_TRY(cudaMalloc(&d_scratch, scratch_cap + SS_TEXT_PAD + SS_TILE));
-    uint8_t *d_comp = d_alloc + 64;
-    DGZ_TRY(cudaMemsetAsync(d_alloc, 0, 64, c->copy_stream));
-    DGZ_TRY(cudaMemsetAsync(d_comp + n_up, 0, 64, c->copy_stream));
-    // ---- upload the compressed bytes (several readers, pinned chunks, any order)
-    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
-    double t_up = now_ms(), t_inflate = 0, t_cut = 0, t_sink = 0;
-    rc = c->src->start_raw(df.path.c_str(), base_off, df.up_hi);
-    if (rc) { cleanup(); return fail(rc, c->src->error()); }
-    {
-        pending_ring pend(c);
-        cudaError_t ce = cudaSuccess;
-        while (ss_chunk *ch = c->src->next()) {
-            ce = cudaMemcpyAsync(d_comp + (ch->file_off - base_off), ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
-            if (ce != cudaSuccess) { c->src->release(ch); break; }
-            ce = pend.push(ch, c->copy_stream);
-            if (ce != cudaSuccess) break;
-        }
-        pend.drain();
-        int src_rc = c->src->finish();
-        cudaStreamSynchronize(c->copy_stream);
-        if (ce != cudaSuccess) { cleanup(); return ss_cuda_fail(ce, "H2D compressed reads", __FILE__, __LINE__); }
-        if (src_rc) { cleanup(); return fail(src_rc, c->src->error()); }
+    if (c->dgz_scratch_cap != scratch_cap) {
+        cudaFree(c->d_dgz_scratch); c->d_dgz_scratch = nullptr; c->dgz_scratch_cap = 0;
+        DGZ_TRY(cudaMalloc(&c->d_dgz_scratch, scratch_cap + SS_TEXT_PAD + SS_TILE));
+        c->dgz_scratch_cap = scratch_cap;
     }
-    t_up = now_ms() - t_up;
+    d_scratch = c->d_dgz_scratch;
+    uint8_t *d_comp = up.d_alloc + 64;
+    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
+    double t_up = up.ms, t_inflate = 0, t_cut = 0, t_sink = 0;
     // ---- inflate, batch by batch
-    ss_dgz dz;
+    if (!c->dgz) c->dgz = new ss_dgz();
+    ss_dgz &dz = *c->dgz;
     rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, max_pieces, piece);
     if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
     std::vector<char> h_win(1u << 20);
@@ -1099,6 +1141,27 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, Sink &&sink) {
     return SS_OK;
 }
 
+// All device-gzip files of a call: the upload of file i + 1 runs beside the inflate of file i.
+template <typename Sink>
+static int dgz_run_files(ss_ctx *c, std::vector<dgz_file> &files, Sink &&sink) {
+    if (files.empty()) return SS_OK;
+    int rc = ensure_source(c);
+    if (rc) { for (auto &f : files) f.close_map(); return rc; }
+    dgz_upload cur, nxt;
+    dgz_upload_file(c, files[0], cur);
+    for (size_t i = 0; i < files.size() && !rc; i++) {
+        std::thread th;
+        if (i + 1 < files.size()) th = std::thread([&, i]() { dgz_upload_file(c, files[i + 1], nxt); });
+        rc = cur.rc ? fail(cur.rc, cur.msg) : dgz_inflate_file(c, files[i], cur, sink);
+        if (th.joinable()) th.join();
+        cudaFree(cur.d_alloc);
+        cur = nxt; nxt = dgz_upload();
+    }
+    cudaFree(cur.d_alloc);
+    for (auto &f : files) f.close_map();
+    return rc;
+}
+
 extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_paths, int shard, int n_shards,
                                    ss_reads **out) {
     if (!c || !out || (n_paths > 0 && !paths)) return fail(SS_ERR_ARG, "ss_reads_from_files: NULL argument");
@@ -1112,24 +1175,25 @@ extern "C" int ss_reads_from_files(ss_ctx *c, const char *const *paths, int n_pa
     r->ctx = c;
     // ordinary gzip files big enough to pay off are inflated on the device, one after the other (ss_dgz.cu)
     std::vector<const char *> rest;
+    std::vector<dgz_file> dgz_files;
     for (int i = 0; i < n_paths; i++) {
         dgz_file df;
-        if (!dgz_eligible(c, paths[i], shard, n_shards, df)) { rest.push_back(paths[i]); continue; }
-        rc = dgz_inflate_file(c, df, [&](const uint8_t *d_text, size_t n) {
-            if (r->seg.empty() || r->seg.back().len + n + SSI_OUT_SLACK > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
-                r->seg.emplace_back();
-                int arc = alloc_segment(r->seg.back(), std::max<uint64_t>(c->seg_bytes, n + SSI_OUT_SLACK));
-                if (arc) { r->seg.pop_back(); return arc; }
-            }
-            ss_segment &g = r->seg.back();
-            SS_CUDA(cudaMemcpyAsync(g.d_text + g.len, d_text, n, cudaMemcpyDeviceToDevice, c->stream));
-            SS_CUDA(cudaStreamSynchronize(c->stream));
-            g.len += n; r->len += n;
-            return (int)SS_OK;
-        });
-        df.close_map();
-        if (rc) { ss_reads_free(r); return rc; }
+        if (dgz_eligible(c, paths[i], shard, n_shards, df)) dgz_files.push_back(df);
+        else rest.push_back(paths[i]);
     }
+    rc = dgz_run_files(c, dgz_files, [&](const uint8_t *d_text, size_t n) {
+        if (r->seg.empty() || r->seg.back().len + n + SSI_OUT_SLACK > r->seg.back().cap - SS_TEXT_PAD - SS_TILE) {
+            r->seg.emplace_back();
+            int arc = alloc_segment(r->seg.back(), std::max<uint64_t>(c->seg_bytes, n + SSI_OUT_SLACK));
+            if (arc) { r->seg.pop_back(); return arc; }
+        }
+        ss_segment &g = r->seg.back();
+        SS_CUDA(cudaMemcpyAsync(g.d_text + g.len, d_text, n, cudaMemcpyDeviceToDevice, c->stream));
+        SS_CUDA(cudaStreamSynchronize(c->stream));
+        g.len += n; r->len += n;
+        return (int)SS_OK;
+    });
+    if (rc) { ss_reads_free(r); return rc; }
     paths = rest.data(); n_paths = (int)rest.size();
     rc = src.start(paths, n_paths, shard, n_shards);
     if (rc) { ss_reads_free(r); return fail(rc, src.error()); }
@@ -1700,25 +1764,26 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
     {
         uint32_t *d_line = nullptr;
         size_t line_words = 0;
-        for (int i = 0; i < n_paths && !rc; i++) {
+        std::vector<dgz_file> dgz_files;
+        for (int i = 0; i < n_paths; i++) {
             dgz_file df;
-            if (!dgz_eligible(c, paths[i], shard, n_shards, df)) { rest.push_back(paths[i]); continue; }
-            rc = dgz_inflate_file(c, df, [&](const uint8_t *d_text, size_t n) {
-                const uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
-                if (ss_index_words(tiles) > line_words) {
-                    cudaFree(d_line); d_line = nullptr;
-                    line_words = ss_index_words(tiles) + (1u << 16);
-                    SS_CUDA(cudaMalloc(&d_line, line_words * sizeof(uint32_t)));
-                }
-                SS_CUDA(cudaMemsetAsync((uint8_t *)d_text + n, '\n', ss_reads_device_capacity(n) - n, c->stream));
-                SS_CUDA(ss_launch_index(d_text, tiles, d_line, 0, c->n_sm, c->stream));
-                SS_CUDA(ss_launch_probe(d_text, n, tiles, d_line, s->view(), c->d_stats, c->d_stats + 4, c->n_sm, c->stream));
-                SS_CUDA(cudaStreamSynchronize(c->stream));
-                ss.probe_launches++; ss.total_launches += 2; ss.bytes += n;
-                return (int)SS_OK;
-            });
-            df.close_map();
+            if (dgz_eligible(c, paths[i], shard, n_shards, df)) dgz_files.push_back(df);
+            else rest.push_back(paths[i]);
         }
+        rc = dgz_run_files(c, dgz_files, [&](const uint8_t *d_text, size_t n) {
+            const uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
+            if (ss_index_words(tiles) > line_words) {
+                cudaFree(d_line); d_line = nullptr;
+                line_words = ss_index_words(tiles) + (1u << 16);
+                SS_CUDA(cudaMalloc(&d_line, line_words * sizeof(uint32_t)));
+            }
+            SS_CUDA(cudaMemsetAsync((uint8_t *)d_text + n, '\n', ss_reads_device_capacity(n) - n, c->stream));
+            SS_CUDA(ss_launch_index(d_text, tiles, d_line, 0, c->n_sm, c->stream));
+            SS_CUDA(ss_launch_probe(d_text, n, tiles, d_line, s->view(), c->d_stats, c->d_stats + 4, c->n_sm, c->stream));
+            SS_CUDA(cudaStreamSynchronize(c->stream));
+            ss.probe_launches++; ss.total_launches += 2; ss.bytes += n;
+            return (int)SS_OK;
+        });
         cudaFree(d_line);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     }

@@ -160,7 +160,7 @@ void ss_dgz::close() {
 
 int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
                  size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes) {
-    close();
+    const uint32_t old_pieces = max_pieces_, old_cap = cap_;
     n_sm_ = n_sm; st_ = st; d_comp_ = d_comp; h_comp_ = h_comp; size_ = comp_size; stop_at_ = std::min(stop_member_at, comp_size);
     max_pieces_ = std::max(2u, std::min(max_pieces, 8192u));
     piece_ = std::max(4096u, piece_bytes);
@@ -174,6 +174,13 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
         return SS_ERR_IO;
     }
     cur_bit_ = (uint64_t)(first_member + h.header_len) * 8u;
+    ratio_ = 4.0; ms_decode_ = ms_resolve_ = ms_windows_ = 0;
+    if (d_pieces_ && old_pieces == max_pieces_ && old_cap == cap_) {      // the buffers of an earlier stream fit: keep them
+        DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));
+        h_pieces_.resize(max_pieces_);
+        return SS_OK;
+    }
+    close();
     DGZ_CUDA(cudaMalloc(&d_pieces_, (size_t)max_pieces_ * sizeof(dgz_piece)));
     DGZ_CUDA(cudaMalloc(&d_sym_, (size_t)max_pieces_ * cap_ * sizeof(uint16_t)));
     DGZ_CUDA(cudaMalloc(&d_windows_, ((size_t)max_pieces_ + 1) * SS_DGZ_WINDOW));

@@ -149,12 +149,19 @@ __device__ __forceinline__ int dgz_huff_fast_dev(ssi_stream &s, ssi_tables &t, u
         if (dist <= n - fresh) {
             const uint16_t *src = dst - dist;
             if (dist >= len) {                                        // no overlap: the loads do not wait for the stores
-                uint32_t i = 0;
-                for (; i + 4 <= len; i += 4) {
-                    const uint16_t a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3];
-                    dst[i] = a0; dst[i + 1] = a1; dst[i + 2] = a2; dst[i + 3] = a3;
+                // four symbols per round, the last round predicated (DNA text at low compression levels is mostly
+                // matches of 3-6 symbols: a separate tail loop cost more than the copies themselves)
+                for (uint32_t i = 0; i < len; i += 4) {
+                    const uint32_t left = len - i;
+                    const uint16_t a0 = src[i];
+                    const uint16_t a1 = left > 1 ? src[i + 1] : (uint16_t)0;
+                    const uint16_t a2 = left > 2 ? src[i + 2] : (uint16_t)0;
+                    const uint16_t a3 = left > 3 ? src[i + 3] : (uint16_t)0;
+                    dst[i] = a0;
+                    if (left > 1) dst[i + 1] = a1;
+                    if (left > 2) dst[i + 2] = a2;
+                    if (left > 3) dst[i + 3] = a3;
                 }
-                for (; i < len; i++) dst[i] = src[i];
             } else {
                 for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
             }
