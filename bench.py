@@ -397,6 +397,14 @@ class Ctx:
         self.counts = torch.zeros(self.kset.n_records, dtype=torch.int32, device=self.dev)
         self.valid_dev = torch.from_numpy(self.kset.valid).to(self.dev)
         self.sampler = ClockSampler(self.local_rank)
+        # cores every rank may run on (the ingest of config 3 is host work: pread / inflate threads per rank)
+        n_cpu = torch.tensor([len(os.sched_getaffinity(0))], dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            all_cpu = [torch.zeros_like(n_cpu) for _ in range(self.world)]
+            dist.all_gather(all_cpu, n_cpu)
+            self.cpus_per_rank = [int(x) for x in all_cpu]
+        else:
+            self.cpus_per_rank = [int(n_cpu)]
 
     def barrier(self):
         if self.world > 1:
@@ -780,7 +788,7 @@ def run_c3(args):
                 "resident_load_s": t_load, "shard_text_bytes_rank0": shard_bytes,
                 "l2": "inputs exceed L2: %.2f GB text per rank + %.2f GB table vs 126 MB" % (shard_bytes / 1e9, kset.table_bytes / 1e9),
                 "hit_rate": h, "second_sector_rate": p2, "table_probe_rate": tot_table / max(tot_kmers, 1),
-                "host_cores": os.cpu_count(),
+                "host_cores": os.cpu_count(), "cores_allowed_per_rank": cx.cpus_per_rank,
                 "step": "resident: K1 + K3 + K3b over this rank's shard + all-reduce; e2e: from the .fq.gz files"})
             line.update({"reads_per_s": n_reads / (ms_per_step * 1e-3), "wall_ms_per_step": wall_ms,
                          "kernel_ms": {"index": sum(s.ms_index for s in sts) / len(sts), "probe": probe_ms,

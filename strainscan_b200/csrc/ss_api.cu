@@ -5,6 +5,7 @@
 //   library/identify.py:73-103, library/identify_low_mem.py:67-90, library/identify_low_depth.py:46-74,
 //   library/Vote_Strain_L2_Lasso_new_sp.py:354-403.
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -773,7 +774,12 @@ static int ensure_source(ss_ctx *c) {
     if (c->src && c->src->ready()) return SS_OK;
     if (!c->src) c->src = new ss_text_source();
     unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-    int threads = (int)std::min(12u, std::max(2u, hw > 4 ? hw - 4 : 2u));   // measured: 8 -> 21-30, 12 -> 35 GB/s of plain text
+    {   // the cores this process may actually run on (a rank bound to its GPU's cores, a container quota)
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof set, &set) == 0) { int n = CPU_COUNT(&set); if (n >= 1) hw = std::max(2u, std::min(hw, (unsigned)n)); }
+    }
+    int threads = (int)(hw > 8 ? std::min(12u, hw - 4) : hw);   // measured: 8 -> 21-30, 12 -> 35 GB/s of plain text; few cores: all of them
     if (const char *e = getenv("SS_INGEST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) threads = v; }
     // one buffer per producer, the copies the consumer may have in flight (released as they complete), and slack
     int rc = c->src->init(c->chunk_bytes, threads + 3 + SS_NPEND, threads, true, c->device_bgzf, c->bgzf_out_cap);

@@ -35,7 +35,11 @@ def bind_to_gpu_cpus(device_index):
         cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu]
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
-        if not cpus:
+        # a rank's ingest runs a dozen producer threads (pread / inflate into pinned chunks): pinning it to a handful of
+        # cores costs more than remote memory does (seen on a 4-GPU lease: two ranks uploaded at a fifth of the others'
+        # rate), so the binding is only taken when it leaves the rank a fair share of the box
+        world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+        if len(cpus) < max(4, len(allowed) // (2 * world)):
             return None
         os.sched_setaffinity(0, cpus)
         return cpus
