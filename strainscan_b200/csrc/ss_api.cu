@@ -12,6 +12,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <chrono>
 #include <cstdio>
@@ -792,16 +795,17 @@ struct pending_ring {
     ss_ctx *c;
     ss_chunk *chunk[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
     int at = 0;
+    std::function<void(ss_chunk *)> on_done;          // called when a chunk's copy has completed, before it is handed back
     explicit pending_ring(ss_ctx *ctx) : c(ctx) {}
+    void give_back(int i) { if (on_done) on_done(chunk[i]); c->src->release(chunk[i]); chunk[i] = nullptr; }
     // call right after the copy of `ch` was issued on `st`
     cudaError_t push(ss_chunk *ch, cudaStream_t st) {
         for (int i = 0; i < SS_NPEND; i++)              // hand back every buffer whose copy has completed by now
-            if (chunk[i] && i != at && cudaEventQuery(c->ev_pend[i]) == cudaSuccess) { c->src->release(chunk[i]); chunk[i] = nullptr; }
+            if (chunk[i] && i != at && cudaEventQuery(c->ev_pend[i]) == cudaSuccess) give_back(i);
         if (chunk[at]) {
             cudaError_t e = cudaEventSynchronize(c->ev_pend[at]);
             if (e != cudaSuccess) return e;
-            c->src->release(chunk[at]);
-            chunk[at] = nullptr;
+            give_back(at);
         }
         cudaError_t e = cudaEventRecord(c->ev_pend[at], st);
         if (e != cudaSuccess) return e;
@@ -811,7 +815,7 @@ struct pending_ring {
     }
     void drain() {
         for (int i = 0; i < SS_NPEND; i++)
-            if (chunk[i]) { cudaEventSynchronize(c->ev_pend[i]); c->src->release(chunk[i]); chunk[i] = nullptr; }
+            if (chunk[i]) { cudaEventSynchronize(c->ev_pend[i]); give_back(i); }
     }
 };
 
@@ -945,34 +949,63 @@ static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, d
 
 // Inflate one file on the device and hand its text out in pieces of whole FASTQ records:
 // sink(const uint8_t *d_text, size_t n) -> SS_* code.  `d_text` stays valid until the sink returns.
-// the compressed bytes of one file (range) on the device
+// the compressed bytes of one file (range) on their way to the device
 struct dgz_upload {
-    uint8_t *d_alloc = nullptr;       // 64 bytes of zero padding, the bytes, 64 bytes of zero padding
+    uint8_t *d_alloc = nullptr;       // 64 bytes of zero padding, the bytes, 64 bytes of zero padding (allocated by the caller)
+    size_t n_up = 0;
     double ms = 0;
     int rc = SS_OK;
     std::string msg;
+    // bytes [0, watermark) of the range are on the device; `finished` once the upload ended (well or badly)
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t watermark = 0;
+    bool finished = false;
+    // block until bytes [0, need) are on the device (or the upload ended); returns false when the upload failed
+    bool wait(size_t need) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return finished || watermark >= std::min(need, n_up); });
+        return rc == SS_OK;
+    }
+    void finish(int code, const std::string &m) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (code && !rc) { rc = code; msg = m; }
+        if (!code) watermark = n_up;
+        finished = true;
+        cv.notify_all();
+    }
 };
 
-// Upload [first_member, up_hi) of the file: several readers, pinned chunks, any order, H2D on the copy stream.
-// Runs beside the inflate of the PREVIOUS file (its own thread): touches the text source and the copy stream only.
+// Upload [first_member, up_hi) of the file: several readers, pinned chunks, any order, H2D on the copy stream; the
+// watermark follows the completed copies, so the inflate of the SAME file starts on its first batches while the rest
+// is still on its way (and the upload of the next file runs beside the inflate of this one).  Own thread: touches the
+// text source and the copy stream only.
 static void dgz_upload_file(ss_ctx *c, const dgz_file &df, dgz_upload &up) {
-    up = dgz_upload();
-    if (df.first_member >= df.size) return;
+    if (df.first_member >= df.size || !up.d_alloc) { up.finish(SS_OK, ""); return; }
     cudaSetDevice(c->device);
     const double t0 = now_ms();
-    const size_t base_off = df.first_member, n_up = df.up_hi - base_off;
-    auto cuda_fail = [&](cudaError_t e, const char *what) {
-        up.rc = SS_ERR_CUDA; up.msg = std::string("CUDA error (") + cudaGetErrorString(e) + ") in the upload of " + df.path + ": " + what;
-        cudaFree(up.d_alloc); up.d_alloc = nullptr;
-    };
-    cudaError_t ce = cudaMalloc(&up.d_alloc, n_up + 128);
-    if (ce != cudaSuccess) { cuda_fail(ce, "cudaMalloc"); return; }
+    const size_t base_off = df.first_member, n_up = up.n_up;
     uint8_t *d_comp = up.d_alloc + 64;
     cudaMemsetAsync(up.d_alloc, 0, 64, c->copy_stream);
     cudaMemsetAsync(d_comp + n_up, 0, 64, c->copy_stream);
     int rc = c->src->start_raw(df.path.c_str(), base_off, df.up_hi);
-    if (rc) { up.rc = rc; up.msg = c->src->error(); cudaFree(up.d_alloc); up.d_alloc = nullptr; return; }
+    if (rc) { up.finish(rc, c->src->error()); return; }
+    const size_t chunk = c->src->chunk_bytes();
+    std::vector<uint8_t> done((n_up + chunk - 1) / chunk, 0);
+    size_t next_chunk = 0;
     pending_ring pend(c);
+    pend.on_done = [&](ss_chunk *ch) {
+        done[(size_t)(ch->file_off - base_off) / chunk] = 1;
+        size_t w = next_chunk;
+        while (w < done.size() && done[w]) w++;
+        if (w != next_chunk) {
+            next_chunk = w;
+            std::lock_guard<std::mutex> lk(up.mu);
+            up.watermark = std::min(n_up, w * chunk);
+            up.cv.notify_all();
+        }
+    };
+    cudaError_t ce = cudaSuccess;
     while (ss_chunk *ch = c->src->next()) {
         ce = cudaMemcpyAsync(d_comp + (ch->file_off - base_off), ch->text, ch->len, cudaMemcpyHostToDevice, c->copy_stream);
         if (ce != cudaSuccess) { c->src->release(ch); break; }
@@ -982,18 +1015,19 @@ static void dgz_upload_file(ss_ctx *c, const dgz_file &df, dgz_upload &up) {
     pend.drain();
     int src_rc = c->src->finish();
     cudaStreamSynchronize(c->copy_stream);
-    if (ce != cudaSuccess) { cuda_fail(ce, "H2D of compressed reads"); return; }
-    if (src_rc) { up.rc = src_rc; up.msg = c->src->error(); cudaFree(up.d_alloc); up.d_alloc = nullptr; return; }
     up.ms = now_ms() - t0;
+    if (ce != cudaSuccess) { up.finish(SS_ERR_CUDA, std::string("CUDA error (") + cudaGetErrorString(ce) + ") in the upload of " + df.path); return; }
+    if (src_rc) { up.finish(src_rc, c->src->error()); return; }
+    up.finish(SS_OK, "");
 }
 
 // Inflate one uploaded file on the device and hand its text out in pieces of whole FASTQ records:
 // sink(const uint8_t *d_text, size_t n) -> SS_* code.  `d_text` stays valid until the sink returns.
 template <typename Sink>
-static int dgz_inflate_file(ss_ctx *c, dgz_file &df, const dgz_upload &up, Sink &&sink) {
+static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink) {
     if (df.first_member >= df.size) return SS_OK;
     int rc = SS_OK;
-    const size_t base_off = df.first_member, n_up = df.up_hi - base_off;
+    const size_t base_off = df.first_member, n_up = up.n_up;
     uint8_t *d_scratch = nullptr, *d_carry = nullptr;
     size_t carry_cap = 0;
     size_t scratch_cap = 2048ull << 20;
@@ -1023,6 +1057,9 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, const dgz_upload &up, Sink 
     // ---- inflate, batch by batch
     if (!c->dgz) c->dgz = new ss_dgz();
     ss_dgz &dz = *c->dgz;
+    // a batch is decoded once its compressed bytes (and SS_DGZ_GATE_SLACK behind them) have arrived
+    dz.set_input_gate([&up, base_off](size_t need_byte) { return up.wait(need_byte > base_off ? need_byte - base_off : 0); },
+                      [&up]() { std::lock_guard<std::mutex> lk(up.mu); return up.finished; });
     rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, max_pieces, piece);
     if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
     std::vector<char> h_win(1u << 20);
@@ -1147,23 +1184,33 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, const dgz_upload &up, Sink 
     return SS_OK;
 }
 
-// All device-gzip files of a call: the upload of file i + 1 runs beside the inflate of file i.
+// All device-gzip files of a call: ONE uploader thread sends the files up one after the other while this thread
+// inflates them in the same order, each batch as soon as its bytes are there.
 template <typename Sink>
 static int dgz_run_files(ss_ctx *c, std::vector<dgz_file> &files, Sink &&sink) {
     if (files.empty()) return SS_OK;
     int rc = ensure_source(c);
-    if (rc) { for (auto &f : files) f.close_map(); return rc; }
-    dgz_upload cur, nxt;
-    dgz_upload_file(c, files[0], cur);
+    std::vector<std::unique_ptr<dgz_upload>> ups;
     for (size_t i = 0; i < files.size() && !rc; i++) {
-        std::thread th;
-        if (i + 1 < files.size()) th = std::thread([&, i]() { dgz_upload_file(c, files[i + 1], nxt); });
-        rc = cur.rc ? fail(cur.rc, cur.msg) : dgz_inflate_file(c, files[i], cur, sink);
-        if (th.joinable()) th.join();
-        cudaFree(cur.d_alloc);
-        cur = nxt; nxt = dgz_upload();
+        ups.emplace_back(new dgz_upload());
+        dgz_upload &u = *ups.back();
+        if (files[i].first_member >= files[i].size) continue;
+        u.n_up = files[i].up_hi - files[i].first_member;
+        cudaError_t e = cudaMalloc(&u.d_alloc, u.n_up + 128);
+        if (e != cudaSuccess) rc = ss_cuda_fail(e, "cudaMalloc(compressed reads)", __FILE__, __LINE__);
     }
-    cudaFree(cur.d_alloc);
+    if (!rc) {
+        std::thread uploader([&]() { for (size_t i = 0; i < files.size(); i++) dgz_upload_file(c, files[i], *ups[i]); });
+        for (size_t i = 0; i < files.size() && !rc; i++) {
+            dgz_upload &u = *ups[i];
+            rc = dgz_inflate_file(c, files[i], u, sink);
+            u.wait(u.n_up);                                          // (an inflate that failed early: let the upload run out)
+            if (!rc && u.rc) rc = fail(u.rc, u.msg);
+            cudaFree(u.d_alloc); u.d_alloc = nullptr;
+        }
+        uploader.join();
+    }
+    for (auto &u : ups) cudaFree(u->d_alloc);
     for (auto &f : files) f.close_map();
     return rc;
 }

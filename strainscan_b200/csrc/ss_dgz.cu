@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32) ss_dgz_find_kernel(const uint8_t *__restri
 // K8: marker-mode decode, one decoder (lane 0 of a one-warp CTA, tables in shared memory) per piece, pieces handed
 // out dynamically.  Huffman decoding is a serial bit chain: parallelism = pieces in flight.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kernel(const uint8_t *__restrict__ comp, size_t comp_size, dgz_piece *pieces,
+__global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kernel(const uint8_t *__restrict__ comp, size_t comp_size, size_t true_size, dgz_piece *pieces,
                                                                 uint32_t n_pieces, uint64_t limit_bit, uint64_t stop_byte,
                                                                 uint16_t *__restrict__ sym_pool, uint32_t cap,
                                                                 unsigned int *__restrict__ next) {
@@ -58,58 +58,85 @@ __global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kern
     while (true) {
         const uint32_t j = atomicAdd(next, 1u);
         if (j >= n_pieces) break;
-        dgz_decode_piece(comp, comp_size, pieces, n_pieces, j, limit_bit, stop_byte, sym_pool + (uint64_t)j * cap, cap, s_tab);
+        dgz_decode_piece(comp, comp_size, true_size, pieces, n_pieces, j, limit_bit, stop_byte, sym_pool + (uint64_t)j * cap, cap, s_tab);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9: the window in front of every accepted piece, in stream order (one CTA; every step is a 32 KiB gather).
-// windows[k] = the 32 KiB in front of accepted piece k (right-aligned; win_len bytes valid); windows[0] is given.
+// K9: the window in front of every accepted piece.  windows[k] = the 32 KiB in front of accepted piece k;
+// windows[0] is given.  The dependency runs through the whole stream (headers copy headers copy headers ...: the last
+// 32 KiB of a piece always hold markers), but it composes: the TAIL MAP of piece k sends every position of the window
+// behind it either to a literal or to a position of the window in front of it, and (B after A)[i] = B[i] is a literal
+// ? B[i] : A[B[i]].  So the chain is a scan over maps, done in three steps: (a) groups of SS_DGZ_GROUP consecutive
+// pieces, one CTA each, compose their maps in order (relative to the group's first window); (b) one CTA composes the
+// group totals in order; (c) every piece applies the prefix of the groups before it and looks the rest up in
+// windows[0].  Every sequential step is a 32 KiB gather through two dependent loads, written so that the 32 loads of
+// a kind a thread owns are in flight together (4.9 us per step; a first form that walked its positions one dependent
+// pair at a time took 24 us).  7104 pieces: 32 + 222 sequential steps instead of 7104.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) ss_dgz_window_kernel(const uint32_t *__restrict__ order, uint32_t n_acc,
-                                                              const dgz_piece *__restrict__ pieces,
-                                                              const uint16_t *__restrict__ sym_pool, uint32_t cap,
-                                                              uint8_t *__restrict__ windows, uint32_t win_len0,
-                                                              unsigned int *__restrict__ err) {
-    // Every step is latency, not bandwidth: 32 KiB gathered through two dependent loads.  So a thread first issues the
-    // loads of all its 32 symbols, then all its 32 window lookups, then stores 32 bytes -- the loads of one kind are in
-    // flight together (the first form walked its 32 positions one dependent pair at a time: 24 us per piece).
-    // Positions that still lie in the OLD window are written as markers pointing at themselves shifted, so both kinds
-    // take the same path.
-    constexpr uint32_t PER = SS_DGZ_WINDOW / 1024u;     // 32 positions per thread: tid, tid + 1024, ... (coalesced)
-    uint32_t win_len = win_len0;
-    for (uint32_t k = 0; k < n_acc; k++) {
+#define SS_DGZ_GROUP 32u
+
+// positions tid, tid + 1024, ... of the tail map of a piece
+__device__ __forceinline__ void dgz_tail_map(const uint16_t *__restrict__ ps, uint32_t n, uint16_t (&x)[32]) {
+    const int64_t e0 = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)threadIdx.x;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; j++) {
+        const int64_t e = e0 + (int64_t)(j * 1024u);
+        x[j] = e >= 0 ? ps[e] : (uint16_t)(256 + (int64_t)SS_DGZ_WINDOW + e);   // still in the old window: points at itself, shifted
+    }
+}
+
+__global__ void __launch_bounds__(1024) ss_dgz_win_local_kernel(const uint32_t *__restrict__ order, uint32_t n_acc,
+                                                                 const dgz_piece *__restrict__ pieces,
+                                                                 const uint16_t *__restrict__ sym_pool, uint32_t cap,
+                                                                 uint16_t *__restrict__ maps) {
+    const uint32_t k0 = blockIdx.x * SS_DGZ_GROUP, k1 = min(n_acc, k0 + SS_DGZ_GROUP);
+    for (uint32_t k = k0; k < k1; k++) {
         const uint32_t pi = order[k];
-        const uint32_t n = pieces[pi].n_sym;
-        const uint16_t *__restrict__ ps = sym_pool + (uint64_t)pi * cap;
-        const uint8_t *__restrict__ w = windows + (uint64_t)k * SS_DGZ_WINDOW;
-        uint8_t *__restrict__ wn = windows + (uint64_t)(k + 1) * SS_DGZ_WINDOW;
-        const int64_t e0 = (int64_t)n - (int64_t)SS_DGZ_WINDOW + (int64_t)threadIdx.x;
-        uint16_t x[PER];
+        uint16_t x[32];
+        dgz_tail_map(sym_pool + (uint64_t)pi * cap, pieces[pi].n_sym, x);
+        uint16_t *__restrict__ out = maps + (uint64_t)k * SS_DGZ_WINDOW;
+        if (k > k0) {
+            const uint16_t *__restrict__ prev = maps + (uint64_t)(k - 1) * SS_DGZ_WINDOW;
 #pragma unroll
-        for (uint32_t j = 0; j < PER; j++) {
-            const int64_t e = e0 + (int64_t)(j * 1024u);
-            x[j] = e >= 0 ? ps[e] : (uint16_t)(256 + (int64_t)SS_DGZ_WINDOW + e);
-        }
-        uint8_t v[PER];
-        bool ok = true;
-#pragma unroll
-        for (uint32_t j = 0; j < PER; j++) {
-            if (x[j] < 256) v[j] = (uint8_t)x[j];
-            else {
-                const uint32_t off = (uint32_t)x[j] - 256u;
-                // a marker into the part of the old window that lies in front of the stream start is an error -- unless
-                // the position itself is old-window filler (e < 0), which nothing can reference either
-                if (off + win_len < SS_DGZ_WINDOW) { v[j] = 0; if (e0 + (int64_t)(j * 1024u) >= 0) ok = false; }
-                else v[j] = w[off];
-            }
+            for (uint32_t j = 0; j < 32; j++) if (x[j] >= 256) x[j] = prev[x[j] - 256u];
         }
 #pragma unroll
-        for (uint32_t j = 0; j < PER; j++) wn[j * 1024u + threadIdx.x] = v[j];
-        if (!ok) atomicMin(err, k);
-        win_len = min(SS_DGZ_WINDOW, win_len + n);
+        for (uint32_t j = 0; j < 32; j++) out[j * 1024u + threadIdx.x] = x[j];
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024) ss_dgz_win_groups_kernel(const uint16_t *__restrict__ maps, uint32_t n_acc,
+                                                                  uint16_t *__restrict__ gpre) {
+    const uint32_t n_groups = (n_acc + SS_DGZ_GROUP - 1) / SS_DGZ_GROUP;
+    for (uint32_t g = 0; g < n_groups; g++) {
+        const uint32_t last = min(n_acc, (g + 1) * SS_DGZ_GROUP) - 1u;
+        const uint16_t *__restrict__ G = maps + (uint64_t)last * SS_DGZ_WINDOW;
+        uint16_t *__restrict__ out = gpre + (uint64_t)g * SS_DGZ_WINDOW;
+        uint16_t x[32];
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) x[j] = G[j * 1024u + threadIdx.x];
+        if (g > 0) {
+            const uint16_t *__restrict__ prev = gpre + (uint64_t)(g - 1) * SS_DGZ_WINDOW;
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) if (x[j] >= 256) x[j] = prev[x[j] - 256u];
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) out[j * 1024u + threadIdx.x] = x[j];
+        __syncthreads();
+    }
+}
+
+// grid.y = accepted piece k (writes windows[k + 1]), grid.x * 256 threads cover the 32768 positions
+__global__ void __launch_bounds__(256) ss_dgz_win_apply_kernel(const uint16_t *__restrict__ maps, const uint16_t *__restrict__ gpre,
+                                                                uint8_t *__restrict__ windows) {
+    const uint32_t k = blockIdx.y, g = k / SS_DGZ_GROUP;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = maps[(uint64_t)k * SS_DGZ_WINDOW + i];
+    if (v >= 256u && g > 0) v = gpre[(uint64_t)(g - 1) * SS_DGZ_WINDOW + (v - 256u)];
+    if (v >= 256u) v = windows[v - 256u];                     // windows[0]: the window in front of the batch
+    windows[(uint64_t)(k + 1) * SS_DGZ_WINDOW + i] = (uint8_t)v;
 }
 
 // K10: symbols -> bytes at their place in the text.  grid.y = accepted piece, grid.x strides over its symbols; a
@@ -117,20 +144,28 @@ __global__ void __launch_bounds__(1024) ss_dgz_window_kernel(const uint32_t *__r
 __global__ void __launch_bounds__(256) ss_dgz_resolve_kernel(const uint32_t *__restrict__ order, const uint64_t *__restrict__ text_off,
                                                               const dgz_piece *__restrict__ pieces,
                                                               const uint16_t *__restrict__ sym_pool, uint32_t cap,
-                                                              const uint8_t *__restrict__ windows, uint8_t *__restrict__ out) {
+                                                              const uint8_t *__restrict__ windows, const uint32_t *__restrict__ win_len,
+                                                              uint8_t *__restrict__ out, unsigned int *__restrict__ err) {
     const uint32_t k = blockIdx.y;
     const uint32_t n = pieces[order[k]].n_sym;
+    const uint32_t invalid_below = 256u + SS_DGZ_WINDOW - win_len[k];     // a marker below this reaches in front of the stream start
     const uint16_t *__restrict__ sym = sym_pool + (uint64_t)order[k] * cap;
     const uint8_t *__restrict__ w = windows + (uint64_t)k * SS_DGZ_WINDOW;
     uint8_t *o = out + text_off[k];
     const uint32_t head = min(n, (uint32_t)((8u - (uint32_t)((uintptr_t)o & 7u)) & 7u));      // bytes in front of the first aligned address
-    if (blockIdx.x == 0 && threadIdx.x < head) o[threadIdx.x] = dgz_resolve1(sym[threadIdx.x], w);
+    if (blockIdx.x == 0 && threadIdx.x < head) {
+        const uint16_t x = sym[threadIdx.x];
+        if (x >= 256 && x < invalid_below) atomicMin(err, k);
+        o[threadIdx.x] = dgz_resolve1(x, w);
+    }
     const uint32_t n8 = (n - head) >> 3;                                                      // whole aligned groups of 8
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += gridDim.x * blockDim.x) {
         const uint16_t *ps = sym + head + 8u * g;
         uint16_t x[8];
+        bool bad = false;
 #pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = ps[j];
+        for (int j = 0; j < 8; j++) { x[j] = ps[j]; bad |= x[j] >= 256 && x[j] < invalid_below; }
+        if (bad) atomicMin(err, k);
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) lo |= (uint32_t)dgz_resolve1(x[j], w) << (8 * j);
@@ -139,7 +174,11 @@ __global__ void __launch_bounds__(256) ss_dgz_resolve_kernel(const uint32_t *__r
         *reinterpret_cast<uint2 *>(o + head + 8u * g) = make_uint2(lo, hi);
     }
     const uint32_t tail0 = head + 8u * n8;
-    if (blockIdx.x == 0 && tail0 + threadIdx.x < n && threadIdx.x < 8) o[tail0 + threadIdx.x] = dgz_resolve1(sym[tail0 + threadIdx.x], w);
+    if (blockIdx.x == 0 && tail0 + threadIdx.x < n && threadIdx.x < 8) {
+        const uint16_t x = sym[tail0 + threadIdx.x];
+        if (x >= 256 && x < invalid_below) atomicMin(err, k);
+        o[tail0 + threadIdx.x] = dgz_resolve1(x, w);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -155,7 +194,9 @@ ss_dgz::~ss_dgz() { close(); }
 
 void ss_dgz::close() {
     cudaFree(d_pieces_); cudaFree(d_sym_); cudaFree(d_windows_); cudaFree(d_order_); cudaFree(d_off_); cudaFree(d_ctr_);
+    cudaFree(d_maps_); cudaFree(d_gpre_); cudaFree(d_wlen_);
     d_pieces_ = nullptr; d_sym_ = nullptr; d_windows_ = nullptr; d_order_ = nullptr; d_off_ = nullptr; d_ctr_ = nullptr;
+    d_maps_ = nullptr; d_gpre_ = nullptr; d_wlen_ = nullptr;
 }
 
 int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
@@ -168,6 +209,8 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
     if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) expand = (uint32_t)v; }
     cap_ = piece_ * expand;
     done_ = false; win_len_ = 0; members_ = 0; pieces_used_ = pieces_found_ = batches_ = 0;
+    gate_slack_ = SS_DGZ_GATE_SLACK;
+    if (const char *e = getenv("SS_DGZ_GATE_SLACK")) { long long v = atoll(e); if (v >= 0) gate_slack_ = (size_t)v; }   // tests: small slack = retries
     ssi_gz_header h;
     if (first_member >= comp_size || ssi_gz_parse_header(h_comp + first_member, h_comp + comp_size, &h) != SSI_OK) {
         err_ = "device gzip inflate: no gzip member at the start of the range";
@@ -187,6 +230,9 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
     DGZ_CUDA(cudaMalloc(&d_order_, (size_t)max_pieces_ * sizeof(uint32_t)));
     DGZ_CUDA(cudaMalloc(&d_off_, (size_t)max_pieces_ * sizeof(uint64_t)));
     DGZ_CUDA(cudaMalloc(&d_ctr_, 2 * sizeof(unsigned int)));
+    DGZ_CUDA(cudaMalloc(&d_maps_, (size_t)max_pieces_ * SS_DGZ_WINDOW * sizeof(uint16_t)));
+    DGZ_CUDA(cudaMalloc(&d_gpre_, ((size_t)max_pieces_ / SS_DGZ_GROUP + 1) * SS_DGZ_WINDOW * sizeof(uint16_t)));
+    DGZ_CUDA(cudaMalloc(&d_wlen_, (size_t)max_pieces_ * sizeof(uint32_t)));
     DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));
     h_pieces_.resize(max_pieces_);
     return SS_OK;
@@ -212,12 +258,20 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     }
     if (P == 0) P = 1;
     const uint64_t limit_bit = std::min<uint64_t>((uint64_t)size_ * 8u, (first_byte + (uint64_t)P * piece_) * 8u);
+    bool input_complete = true;
+    size_t avail = size_;                                            // the kernels of this batch see the input end here
+    if (gate_wait_) {
+        const size_t need = (size_t)(limit_bit >> 3) + 1 + gate_slack_;
+        if (!gate_wait_(need)) { err_ = "the upload of the compressed bytes failed"; return SS_ERR_IO; }
+        input_complete = !gate_complete_ || gate_complete_();
+        if (!input_complete) avail = std::min(size_, need);          // bytes behind it may not have arrived: a decoder that
+    }                                                                // wants them reports a truncated stream, never garbage
     for (uint32_t j = 0; j < P; j++) { h_pieces_[j] = dgz_piece(); h_pieces_[j].start_bit = j == 0 ? cur_bit_ : ~0ull; }
     DGZ_CUDA(cudaMemcpyAsync(d_pieces_, h_pieces_.data(), (size_t)P * sizeof(dgz_piece), cudaMemcpyHostToDevice, st_));
     DGZ_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(unsigned int), st_));
     DGZ_CUDA(cudaMemsetAsync(d_ctr_ + 1, 0xFF, sizeof(unsigned int), st_));
-    if (P > 1) ss_dgz_find_kernel<<<std::min<uint32_t>(P - 1, (uint32_t)n_sm_ * 32u), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, first_byte, limit_bit, piece_);
-    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
+    if (P > 1) ss_dgz_find_kernel<<<std::min<uint32_t>(P - 1, (uint32_t)n_sm_ * 32u), 32, 0, st_>>>(d_comp_, avail, d_pieces_, P, first_byte, limit_bit, piece_);
+    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, avail, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
                                                                                     d_sym_, cap_, d_ctr_);
     DGZ_CUDA(cudaGetLastError());
     DGZ_CUDA(cudaMemcpyAsync(h_pieces_.data(), d_pieces_, (size_t)P * sizeof(dgz_piece), cudaMemcpyDeviceToHost, st_));
@@ -225,7 +279,7 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     batches_++;
     ms_decode_ += dgz_now_ms() - t0; t0 = dgz_now_ms();
     // ---- the chain: a piece counts only if the accepted piece before it ended exactly on its start
-    std::vector<uint32_t> order;
+    std::vector<uint32_t> order, wlen;
     std::vector<uint64_t> off;
     uint64_t total = 0;
     uint32_t cur = 0;
@@ -234,6 +288,11 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     while (true) {
         const dgz_piece &pc = h_pieces_[cur];
         if (pc.status == SS_DGZ_ERROR || pc.status == SS_DGZ_NOSTART) {
+            if (!input_complete && order.empty()) {                  // bytes that had not arrived yet?  once more, with all of them
+                if (!gate_wait_(size_)) { err_ = "the upload of the compressed bytes failed"; return SS_ERR_IO; }
+                return next(d_out, out_cap, n_out, done);
+            }
+            if (!input_complete) break;                              // keep what stands; the rest is decoded again by the next batch
             err_ = "invalid compressed data";
             return SS_ERR_IO;
         }
@@ -246,6 +305,7 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
             break;
         }
         order.push_back(cur); off.push_back(total);
+        wlen.push_back((uint32_t)std::min<uint64_t>(SS_DGZ_WINDOW, (uint64_t)win_len_ + total));   // window bytes that exist in front of it
         total += pc.n_sym;
         members_ += pc.members;
         cur_bit_ = pc.end_bit;
@@ -257,9 +317,13 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     const uint32_t n_acc = (uint32_t)order.size();
     DGZ_CUDA(cudaMemcpyAsync(d_order_, order.data(), n_acc * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
     DGZ_CUDA(cudaMemcpyAsync(d_off_, off.data(), n_acc * sizeof(uint64_t), cudaMemcpyHostToDevice, st_));
-    ss_dgz_window_kernel<<<1, 1024, 0, st_>>>(d_order_, n_acc, d_pieces_, d_sym_, cap_, d_windows_, win_len_, d_ctr_ + 1);
+    DGZ_CUDA(cudaMemcpyAsync(d_wlen_, wlen.data(), n_acc * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
+    const uint32_t n_groups = (n_acc + SS_DGZ_GROUP - 1) / SS_DGZ_GROUP;
+    ss_dgz_win_local_kernel<<<n_groups, 1024, 0, st_>>>(d_order_, n_acc, d_pieces_, d_sym_, cap_, d_maps_);
+    ss_dgz_win_groups_kernel<<<1, 1024, 0, st_>>>(d_maps_, n_acc, d_gpre_);
+    ss_dgz_win_apply_kernel<<<dim3(SS_DGZ_WINDOW / 256u, n_acc), 256, 0, st_>>>(d_maps_, d_gpre_, d_windows_);
     if (getenv("SS_DEBUG_TIMING")) { cudaStreamSynchronize(st_); ms_windows_ += dgz_now_ms() - t0; }
-    ss_dgz_resolve_kernel<<<dim3(16, n_acc), 256, 0, st_>>>(d_order_, d_off_, d_pieces_, d_sym_, cap_, d_windows_, d_out);
+    ss_dgz_resolve_kernel<<<dim3(16, n_acc), 256, 0, st_>>>(d_order_, d_off_, d_pieces_, d_sym_, cap_, d_windows_, d_wlen_, d_out, d_ctr_ + 1);
     // the last window becomes the first one of the next batch
     DGZ_CUDA(cudaMemcpyAsync(d_windows_, d_windows_ + (size_t)n_acc * SS_DGZ_WINDOW, SS_DGZ_WINDOW, cudaMemcpyDeviceToDevice, st_));
     unsigned int bad = 0xFFFFFFFFu;
@@ -314,7 +378,7 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
             for (uint64_t p = from; p < to; p++)
                 if (dgz_quick_test(comp, comp_size, p) && dgz_full_test(comp, comp_size, p, *tab)) { pieces[j].start_bit = p; found++; break; }
         }
-        for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
+        for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
         batches++;
         uint32_t cur = 0;
         bool end = false;

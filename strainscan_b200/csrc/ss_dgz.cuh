@@ -268,7 +268,9 @@ SS_HD int dgz_block(ssi_stream &s, ssi_tables &t, uint16_t *sym, uint32_t &n_io,
 // starting at or behind byte `stop_byte` ends the stream for this decoder (member-split files: the next member
 // belongs to another rank).  The window in front of the piece is unknown to the decoder (markers); a batch that
 // opens a member has an EMPTY known window, against which K9 rejects any marker.
-SS_HD void dgz_decode_piece(const uint8_t *comp, size_t comp_size, dgz_piece *pieces, uint32_t n_pieces, uint32_t me,
+// `comp_size` bytes are readable now; the stream really ends at `true_size` (>= comp_size: the rest is still being
+// uploaded, and whatever would need it is reported as an error for the caller to retry, never guessed).
+SS_HD void dgz_decode_piece(const uint8_t *comp, size_t comp_size, size_t true_size, dgz_piece *pieces, uint32_t n_pieces, uint32_t me,
                             uint64_t limit_bit, uint64_t stop_byte, uint16_t *sym, uint32_t cap, ssi_tables &t) {
     dgz_piece &pc = pieces[me];
     pc.n_sym = 0; pc.next = n_pieces; pc.members = 0; pc.fresh_from = 0xFFFFFFFFu; pc.end_bit = pc.start_bit;
@@ -296,7 +298,10 @@ SS_HD void dgz_decode_piece(const uint8_t *comp, size_t comp_size, dgz_piece *pi
             if (comp + comp_size - q < 8) { pc.status = SS_DGZ_ERROR; return; }
             q += 8;
             ssi_gz_header h;
-            if (q >= comp + comp_size || (uint64_t)(q - comp) >= stop_byte || ssi_gz_parse_header(q, comp + comp_size, &h) != SSI_OK) {
+            const bool at_end = q >= comp + true_size || (uint64_t)(q - comp) >= stop_byte;
+            // (a header that is not all there yet is nobody's "trailing garbage")
+            if (!at_end && comp_size < true_size && (size_t)(comp + comp_size - q) < 4096) { pc.status = SS_DGZ_ERROR; return; }
+            if (at_end || ssi_gz_parse_header(q, comp + comp_size, &h) != SSI_OK) {
                 pc.end_bit = (uint64_t)(q - comp) * 8u;
                 pc.status = SS_DGZ_END;
                 return;

@@ -3,10 +3,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
 #include "ss_dgz.cuh"
+
+// bytes behind a batch's limit that must have arrived before the batch is decoded (a decoder runs on to the end of the
+// deflate block that straddles the limit); what lies further is out of bounds for that batch's kernels
+#define SS_DGZ_GATE_SLACK (8u << 20)
 
 // One gzip file (or the members of one file part) inflated batch by batch on the device.  The compressed bytes
 // [0, comp_size) sit in device memory (d_comp, padded by 16 readable bytes) and in host memory (h_comp: headers are
@@ -20,6 +25,10 @@ public:
     // first_member: byte offset of a member header; members that start at or behind stop_member_at are not decoded
     int open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
              size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes);
+    // While the compressed bytes are still being uploaded: wait(need) blocks until bytes [0, need) of the file are on the
+    // device (false: the upload failed); complete() tells whether everything has arrived.  A batch that fails while the
+    // upload was still running is decoded again once it is complete (a block longer than the slack the gate allows).
+    void set_input_gate(std::function<bool(size_t)> wait, std::function<bool()> complete) { gate_wait_ = wait; gate_complete_ = complete; }
     size_t batch_text_capacity() const;
     int next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done);
     void close();
@@ -41,6 +50,7 @@ private:
     uint32_t max_pieces_ = 0, cap_ = 0, piece_ = 0;
     uint64_t cur_bit_ = 0;
     uint32_t win_len_ = 0;
+    size_t gate_slack_ = SS_DGZ_GATE_SLACK;
     double ms_decode_ = 0, ms_resolve_ = 0, ms_windows_ = 0;
     double ratio_ = 4.0;              // text bytes per compressed byte seen so far
     bool done_ = false;
@@ -51,8 +61,12 @@ private:
     uint32_t *d_order_ = nullptr;
     uint64_t *d_off_ = nullptr;
     unsigned int *d_ctr_ = nullptr;
+    uint16_t *d_maps_ = nullptr, *d_gpre_ = nullptr;     // tail maps of the accepted pieces / composed group totals (K9)
+    uint32_t *d_wlen_ = nullptr;                          // window bytes that exist in front of every accepted piece
     std::vector<dgz_piece> h_pieces_;
     std::string err_;
+    std::function<bool(size_t)> gate_wait_;
+    std::function<bool()> gate_complete_;
 };
 
 // the same pipeline on host threads (tests: the algorithms against zlib without a GPU); out is resized to the text

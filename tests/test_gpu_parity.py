@@ -601,6 +601,23 @@ def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape):
     reads = eng.reads_from_files([p1, p2])
     got2, st2 = eng.count(ks, reads)
     assert np.array_equal(got2, got) and st2.n_reads == 38_000
+    # batches decoded while the rest of the file is still being uploaded (small chunks, one reader, hardly any slack
+    # behind a batch: decoders run into bytes that are not there yet, report it, and the batch is decoded again)
+    from strainscan_b200 import Engine
+    monkeypatch.setenv("SS_CHUNK_BYTES", str(256 << 10))
+    monkeypatch.setenv("SS_INGEST_THREADS", "1")
+    monkeypatch.setenv("SS_DGZ_GATE_SLACK", "4096")
+    monkeypatch.setenv("SS_DGZ_MAX_PIECES", "8")
+    eng2 = Engine(0)
+    ks2 = eng2.kmerset_from_text(fa, 31)
+    got_s, st_s = eng2.count_files(ks2, [p1, p2])
+    assert np.array_equal(got_s, got) and st_s.n_reads == 38_000
+    ks2.free()
+    eng2.close()
+    for name in ("SS_CHUNK_BYTES", "SS_INGEST_THREADS", "SS_DGZ_GATE_SLACK"):
+        monkeypatch.delenv(name)
+    if shape != "level9_small_batches":
+        monkeypatch.delenv("SS_DGZ_MAX_PIECES")
     # the host decoders give the same vector (SS_DGZ=0)
     monkeypatch.setenv("SS_DGZ", "0")
     got3, _ = eng.count_files(ks, [p1, p2])
