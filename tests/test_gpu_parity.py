@@ -24,12 +24,6 @@ def _gold_dense(case):
     return adapters.count_dense(case["fasta"].encode(), case["k"], [r.encode() for r in case["reads"]])
 
 
-def _supported(case):
-    """Every dialect the reference engine accepts is supported: FASTA and multi-line FASTQ reads are rewritten
-    as 4-line FASTQ on the host (csrc/ss_fastx.h) before the scan."""
-    return True
-
-
 def _check_against_dump(case, got, flags):
     """Direct check against the jellyfish dump, not via the oracle."""
     lines = case["fasta"].split("\n")
@@ -43,8 +37,6 @@ def _check_against_dump(case, got, flags):
 
 def test_golden_resident(eng, golden_cases):
     for case in golden_cases:
-        if not _supported(case):
-            continue
         ks = eng.kmerset_from_text(case["fasta"], case["k"])
         reads = eng.reads_from_host([r.encode() for r in case["reads"]])
         got, st = eng.count(ks, reads)
@@ -62,8 +54,6 @@ def test_golden_resident(eng, golden_cases):
 
 def test_golden_streaming_host(eng, golden_cases):
     for case in golden_cases:
-        if not _supported(case):
-            continue
         ks = eng.kmerset_from_text(case["fasta"], case["k"])
         got, st = eng.count_host(ks, [r.encode() for r in case["reads"]])
         _check_against_dump(case, got, ks.flags)
@@ -71,8 +61,6 @@ def test_golden_streaming_host(eng, golden_cases):
 
 def test_golden_files_plain_and_gz(eng, golden_cases, tmp_path):
     for case in golden_cases:
-        if not _supported(case):
-            continue
         fa = tmp_path / ("%s.fa" % case["name"])
         fa.write_bytes(case["fasta"].encode())
         plain, gz = [], []
@@ -147,8 +135,6 @@ def test_random_vs_oracle(eng, k, filt, monkeypatch):
 def test_golden_with_filter_forced(eng, golden_cases, monkeypatch):
     monkeypatch.setenv("SS_FILTER", "1")
     for case in golden_cases:
-        if not _supported(case):
-            continue
         ks = eng.kmerset_from_text(case["fasta"], case["k"])
         got, st = eng.count(ks, eng.reads_from_host([r.encode() for r in case["reads"]]))
         _check_against_dump(case, got, ks.flags)
