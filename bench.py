@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the N>1 full parity check on rank 0")
+    ap.add_argument("--e2e-variants", default="", help="c3: 'NAME=VAL[,NAME=VAL];...' -- the file pass timed again under "
+                                                       "each environment setting (same files; A/B of library knobs)")
     ap.add_argument("--tmp", default=None, help="scratch directory for generated files (default /dev/shm)")
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args()
@@ -766,6 +768,25 @@ def run_c3(args):
                "api": "ss_count_files(paths=[r1.fq.gz, r2.fq.gz], shard=rank, n_shards=world) (C ABI): host threads inflate "
                       "this rank's gzip members into pinned chunks, chunked H2D, K1+K3 per chunk, K3b, all-reduce, D2H; "
                       "h2d bytes are this rank's text"}
+
+        # ---- optional: the same file pass under other settings of the library's knobs ---------------
+        variants = []
+        for spec in [v for v in args.e2e_variants.split(";") if v]:
+            sets = dict(kv.split("=", 1) for kv in spec.split(","))
+            old_env = {k: os.environ.get(k) for k in sets}
+            os.environ.update(sets)
+            try:
+                v_ms, v_wall, _ = cx.timed(step_files, 1, args.steps)
+                assert torch.equal(counts, resident), "file pass under %s disagrees with the resident pass" % spec
+            finally:
+                for k, v in old_env.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            variants.append({"env": sets, "ms_per_step": v_ms, "wall_ms_per_step": v_wall, "value": tot_kmers / (v_ms * 1e-3)})
+        if variants:
+            e2e["variants"] = variants
 
         # ---- N > 1: rank 0 counts the whole sample alone and compares -----------------------------
         check = None

@@ -101,6 +101,12 @@ struct ss_ctx {
     ss_dgz *dgz = nullptr;
     uint8_t *d_dgz_scratch = nullptr;
     size_t dgz_scratch_cap = 0;
+    uint32_t *d_dgz_line = nullptr;          // line index of the batch being scanned where it was inflated (grows only)
+    size_t dgz_line_words = 0;
+    uint8_t *d_dgz_up[2] = {nullptr, nullptr};   // compressed bytes of the file being inflated / of the next one (grow only)
+    size_t dgz_up_cap[2] = {0, 0};
+    uint8_t *d_dgz_carry = nullptr;          // the partial record behind a batch's last whole one (grows only)
+    size_t dgz_carry_cap = 0;
     cudaEvent_t ev_pend[SS_NPEND] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -219,6 +225,8 @@ extern "C" int ss_shutdown(ss_ctx *c) {
     delete c->src;
     delete c->dgz;
     cudaFree(c->d_dgz_scratch);
+    cudaFree(c->d_dgz_line);
+    cudaFree(c->d_dgz_up[0]); cudaFree(c->d_dgz_up[1]); cudaFree(c->d_dgz_carry);
     for (int i = 0; i < SS_NGZ; i++) {
         cudaFree(c->d_comp[i]); cudaFree(c->d_members[i]);
         cudaEventDestroy(c->ev_gz_done[i]); cudaEventDestroy(c->ev_gz_copied[i]);
@@ -940,7 +948,7 @@ static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, d
     df.up_hi = df.hi >= df.size ? df.size : ss_gz_next_member_start(df.map, df.size, df.hi, df.size);
     if (df.up_hi < df.size) df.up_hi = std::min(df.size, df.up_hi + 64);
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < (df.up_hi - std::min(df.up_hi, df.first_member)) + (14ull << 30)) {
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < (df.up_hi - std::min(df.up_hi, df.first_member)) + ((ss_dgz::shape_from_env().lanes ? 24ull : 14ull) << 30)) {
         df.close_map();
         return false;                                                // not enough room beside the read cache: host threads
     }
@@ -1028,22 +1036,23 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
     if (df.first_member >= df.size) return SS_OK;
     int rc = SS_OK;
     const size_t base_off = df.first_member, n_up = up.n_up;
-    uint8_t *d_scratch = nullptr, *d_carry = nullptr;
-    size_t carry_cap = 0;
-    size_t scratch_cap = 2048ull << 20;
+    uint8_t *d_scratch = nullptr;
+    size_t scratch_cap = (ss_dgz::shape_from_env().lanes ? 4096ull : 2048ull) << 20;     // one wave of pieces inflates into it
     if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) scratch_cap = (size_t)v << 20; }
-    // Pieces of ~128 KiB, sized so that the file is a whole number of WAVES of decoders (148 SMs x 24): a last wave with
-    // a few pieces takes as long as a full one (an eighth of a config-3 file is 2.5 waves of 128 KiB pieces).
-    const uint32_t wave = (uint32_t)c->n_sm * 24u;
-    uint32_t piece = 128u << 10, max_pieces = 2 * wave;
+    // Pieces of at most 128 KiB, small enough for a whole WAVE of decoders (148 SMs x 24, or x 92 with several decoders
+    // per warp) to inflate into the scratch buffer, and sized so that the file is a whole number of waves: a last wave
+    // with a few pieces takes as long as a full one (an eighth of a config-3 file is 2.5 waves of 128 KiB pieces).
+    const uint32_t wave = (uint32_t)c->n_sm * ss_dgz::decoders_per_sm(ss_dgz::shape_from_env());
+    const double target = std::min<double>(128u << 10, std::floor((double)scratch_cap / ((double)wave * 4.6) / 4096.0) * 4096.0);
+    uint32_t piece = (uint32_t)std::max(16384.0, target), max_pieces = std::min<uint32_t>(2 * wave, SS_DGZ_MAX_PIECES);
     {
         const double waves = std::max(1.0, std::floor((double)n_up / ((double)wave * piece) + 0.5));
         const double fit = std::ceil((double)n_up / (waves * wave) / 4096.0) * 4096.0;
-        if (fit >= (64u << 10) && fit <= (256u << 10)) piece = (uint32_t)fit;
+        if (fit >= 0.5 * piece && fit <= 1.1 * piece) piece = (uint32_t)fit;
     }
     if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) piece = (uint32_t)v; }
-    if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= 8192) max_pieces = (uint32_t)v; }
-    auto cleanup = [&]() { cudaFree(d_carry); };
+    if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= (long long)SS_DGZ_MAX_PIECES) max_pieces = (uint32_t)v; }
+    auto cleanup = [&]() {};
 #define DGZ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
     if (c->dgz_scratch_cap != scratch_cap) {
         cudaFree(c->d_dgz_scratch); c->d_dgz_scratch = nullptr; c->dgz_scratch_cap = 0;
@@ -1148,12 +1157,13 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
         // the partial record behind the cut is set aside (the sink may pad behind its text), then moved to the front
         carry = len - cut;
         if (carry) {
-            if (carry > carry_cap) {
-                cudaFree(d_carry); d_carry = nullptr;
-                carry_cap = std::max<size_t>(carry, 1u << 20);
-                DGZ_TRY(cudaMalloc(&d_carry, carry_cap));
+            if (carry > c->dgz_carry_cap) {
+                cudaFree(c->d_dgz_carry); c->d_dgz_carry = nullptr; c->dgz_carry_cap = 0;
+                const size_t cap = std::max<size_t>(carry, 1u << 20);
+                DGZ_TRY(cudaMalloc(&c->d_dgz_carry, cap));
+                c->dgz_carry_cap = cap;
             }
-            DGZ_TRY(cudaMemcpyAsync(d_carry, d_scratch + cut, carry, cudaMemcpyDeviceToDevice, c->stream));
+            DGZ_TRY(cudaMemcpyAsync(c->d_dgz_carry, d_scratch + cut, carry, cudaMemcpyDeviceToDevice, c->stream));
         }
         if (cut > start) {
             const uint8_t *text = d_scratch + start;
@@ -1171,7 +1181,7 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
             if (rc) { cleanup(); return rc; }
             t_sink += now_ms() - t0;
         }
-        if (carry) DGZ_TRY(cudaMemcpyAsync(d_scratch, d_carry, carry, cudaMemcpyDeviceToDevice, c->stream));
+        if (carry) DGZ_TRY(cudaMemcpyAsync(d_scratch, c->d_dgz_carry, carry, cudaMemcpyDeviceToDevice, c->stream));
     }
     if (dbg)
         fprintf(stderr, "[ss dgz] %s: %llu batches, %llu/%llu pieces used, %llu members; upload %.1f ms (%.1f MB), inflate %.1f ms "
@@ -1185,33 +1195,63 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
 }
 
 // All device-gzip files of a call: ONE uploader thread sends the files up one after the other while this thread
-// inflates them in the same order, each batch as soon as its bytes are there.
+// inflates them in the same order, each batch as soon as its bytes are there.  Two upload buffers (kept by the context,
+// growing only: no allocation in a steady run): file i goes into buffer i % 2 once file i - 2 has been inflated.
 template <typename Sink>
 static int dgz_run_files(ss_ctx *c, std::vector<dgz_file> &files, Sink &&sink) {
     if (files.empty()) return SS_OK;
+    const bool dbg = getenv("SS_DEBUG_TIMING") != nullptr;
+    const double t_begin = now_ms();
     int rc = ensure_source(c);
     std::vector<std::unique_ptr<dgz_upload>> ups;
-    for (size_t i = 0; i < files.size() && !rc; i++) {
+    size_t need[2] = {0, 0};
+    for (size_t i = 0; i < files.size(); i++) {
         ups.emplace_back(new dgz_upload());
-        dgz_upload &u = *ups.back();
         if (files[i].first_member >= files[i].size) continue;
-        u.n_up = files[i].up_hi - files[i].first_member;
-        cudaError_t e = cudaMalloc(&u.d_alloc, u.n_up + 128);
-        if (e != cudaSuccess) rc = ss_cuda_fail(e, "cudaMalloc(compressed reads)", __FILE__, __LINE__);
+        ups.back()->n_up = files[i].up_hi - files[i].first_member;
+        need[i & 1] = std::max(need[i & 1], ups.back()->n_up + 128);
     }
+    for (int k = 0; k < 2 && !rc; k++)
+        if (need[k] > c->dgz_up_cap[k]) {
+            cudaFree(c->d_dgz_up[k]); c->d_dgz_up[k] = nullptr; c->dgz_up_cap[k] = 0;
+            cudaError_t e = cudaMalloc(&c->d_dgz_up[k], need[k]);
+            if (e != cudaSuccess) rc = ss_cuda_fail(e, "cudaMalloc(compressed reads)", __FILE__, __LINE__);
+            else c->dgz_up_cap[k] = need[k];
+        }
+    const double t_alloc = now_ms();
     if (!rc) {
-        std::thread uploader([&]() { for (size_t i = 0; i < files.size(); i++) dgz_upload_file(c, files[i], *ups[i]); });
-        for (size_t i = 0; i < files.size() && !rc; i++) {
+        for (size_t i = 0; i < files.size(); i++) if (ups[i]->n_up) ups[i]->d_alloc = c->d_dgz_up[i & 1];
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t inflated = 0;                                          // files [0, inflated) are done with their buffers
+        bool stop = false;
+        std::thread uploader([&]() {
+            for (size_t i = 0; i < files.size(); i++) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&]() { return stop || i < inflated + 2; });
+                    if (stop) { for (size_t j = i; j < files.size(); j++) ups[j]->finish(SS_ERR_IO, "cancelled"); return; }
+                }
+                dgz_upload_file(c, files[i], *ups[i]);
+            }
+        });
+        for (size_t i = 0; i < files.size(); i++) {
             dgz_upload &u = *ups[i];
-            rc = dgz_inflate_file(c, files[i], u, sink);
-            u.wait(u.n_up);                                          // (an inflate that failed early: let the upload run out)
-            if (!rc && u.rc) rc = fail(u.rc, u.msg);
-            cudaFree(u.d_alloc); u.d_alloc = nullptr;
+            if (!rc) {
+                rc = dgz_inflate_file(c, files[i], u, sink);
+                u.wait(u.n_up);                                      // (an inflate that failed early: let this upload run out)
+                if (!rc && u.rc) rc = fail(u.rc, u.msg);
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (rc) stop = true;                                     // no further uploads
+            inflated = i + 1;
+            cv.notify_all();
         }
         uploader.join();
+        cudaStreamSynchronize(c->copy_stream);
     }
-    for (auto &u : ups) cudaFree(u->d_alloc);
     for (auto &f : files) f.close_map();
+    if (dbg) fprintf(stderr, "[ss dgz] %zu files: %.1f ms in all (buffers %.1f ms)\n", files.size(), now_ms() - t_begin, t_alloc - t_begin);
     return rc;
 }
 
@@ -1815,8 +1855,6 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
     // where it was inflated (ss_dgz.cu)
     std::vector<const char *> rest;
     {
-        uint32_t *d_line = nullptr;
-        size_t line_words = 0;
         std::vector<dgz_file> dgz_files;
         for (int i = 0; i < n_paths; i++) {
             dgz_file df;
@@ -1825,19 +1863,19 @@ extern "C" int ss_count_files(ss_ctx *c, const ss_kmerset *s, const char *const 
         }
         rc = dgz_run_files(c, dgz_files, [&](const uint8_t *d_text, size_t n) {
             const uint32_t tiles = (uint32_t)((n + SS_TILE - 1) / SS_TILE);
-            if (ss_index_words(tiles) > line_words) {
-                cudaFree(d_line); d_line = nullptr;
-                line_words = ss_index_words(tiles) + (1u << 16);
-                SS_CUDA(cudaMalloc(&d_line, line_words * sizeof(uint32_t)));
+            if (ss_index_words(tiles) > c->dgz_line_words) {
+                cudaFree(c->d_dgz_line); c->d_dgz_line = nullptr; c->dgz_line_words = 0;
+                const size_t words = ss_index_words(tiles) + (1u << 16);
+                SS_CUDA(cudaMalloc(&c->d_dgz_line, words * sizeof(uint32_t)));
+                c->dgz_line_words = words;
             }
             SS_CUDA(cudaMemsetAsync((uint8_t *)d_text + n, '\n', ss_reads_device_capacity(n) - n, c->stream));
-            SS_CUDA(ss_launch_index(d_text, tiles, d_line, 0, c->n_sm, c->stream));
-            SS_CUDA(ss_launch_probe(d_text, n, tiles, d_line, s->view(), c->d_stats, c->d_stats + 4, c->n_sm, c->stream));
+            SS_CUDA(ss_launch_index(d_text, tiles, c->d_dgz_line, 0, c->n_sm, c->stream));
+            SS_CUDA(ss_launch_probe(d_text, n, tiles, c->d_dgz_line, s->view(), c->d_stats, c->d_stats + 4, c->n_sm, c->stream));
             SS_CUDA(cudaStreamSynchronize(c->stream));
             ss.probe_launches++; ss.total_launches += 2; ss.bytes += n;
             return (int)SS_OK;
         });
-        cudaFree(d_line);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
     }
     paths = rest.data(); n_paths = (int)rest.size();

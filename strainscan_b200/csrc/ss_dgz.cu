@@ -8,6 +8,7 @@
 
 #include "ss_common.cuh"
 #include "ss_dgz.cuh"
+#include "ss_dgz2.cuh"
 #include "ss_dgz_host.h"
 
 #ifndef SS_DGZ_DECODERS_PER_SM
@@ -60,6 +61,76 @@ __global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kern
         if (j >= n_pieces) break;
         dgz_decode_piece(comp, comp_size, true_size, pieces, n_pieces, j, limit_bit, stop_byte, sym_pool + (uint64_t)j * cap, cap, s_tab);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8, several decoders per warp (ss_dgz2.cuh): one CTA per SM, LANES decoders in each of its warps, every decoder's
+// 2.5 KB of tables in shared memory.  Between rounds a decoder does whatever its state asks for (fetch a piece, read a
+// block header, build tables, end a piece); rounds are entered by all decoders of a warp together.
+// ---------------------------------------------------------------------------------------------
+#define SS_DGZ2_ROUND 256u
+#define SS_DGZ2_SMEM_MAX 232448u
+constexpr uint32_t dgz2_smem(uint32_t lanes, uint32_t warps) { return 256u + warps * lanes * (uint32_t)sizeof(dgz_ctables); }
+
+template <int LANES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) ss_dgz_decode_lanes_kernel(dgz2_job J, unsigned int *__restrict__ next) {
+    extern __shared__ __align__(16) uint8_t dgz2_shared[];
+    uint32_t *base_tab = reinterpret_cast<uint32_t *>(dgz2_shared);
+    if (threadIdx.x < 64u) base_tab[threadIdx.x] = dgc_base_entry(threadIdx.x);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane >= (uint32_t)LANES) return;
+    dgz_ctables &t = *reinterpret_cast<dgz_ctables *>(dgz2_shared + 256u + (warp * LANES + lane) * sizeof(dgz_ctables));
+    const uint32_t mask = LANES >= 32 ? 0xFFFFFFFFu : (1u << LANES) - 1u;
+    dgz2_lane L;
+    L.mode = DGZ2_IDLE;
+    while (true) {
+        uint32_t budget;
+        while (true) {
+            budget = dgz2_advance(L, J, t);
+            if (L.mode != DGZ2_IDLE) break;
+            const uint32_t j = atomicAdd(next, 1u);
+            if (j >= J.n_pieces) { L.mode = DGZ2_DONE; break; }
+            dgz2_begin_piece(L, J, j);
+        }
+        if (__all_sync(mask, L.mode == DGZ2_DONE)) break;
+        const int rc = dgz2_round(L, t, base_tab, budget, SS_DGZ2_ROUND, J.prefetch, [mask](bool a) { return __any_sync(mask, a) != 0; });
+        dgz2_after_round(L, J, rc);
+    }
+}
+
+// the shapes K8 is built in: decoders per warp x warps per CTA (one CTA per SM); SS_DGZ_LANES / SS_DGZ_WARPS pick one
+struct dgz2_shape { int lanes, warps; };
+static const dgz2_shape dgz2_shapes[] = {{1, 24}, {1, 32}, {2, 24}, {2, 32}, {3, 24}, {4, 23}, {8, 11}};
+
+ss_dgz_shape ss_dgz::shape_from_env() {
+    int lanes = SS_DGZ_LANES_DEFAULT, warps = 0;
+    if (const char *e = getenv("SS_DGZ_LANES")) lanes = atoi(e);
+    if (const char *e = getenv("SS_DGZ_WARPS")) warps = atoi(e);
+    ss_dgz_shape r = {0, 0};
+    for (const dgz2_shape &sh : dgz2_shapes)
+        if (sh.lanes == lanes && (warps == 0 ? r.lanes == 0 : sh.warps == warps)) { r.lanes = sh.lanes; r.warps = sh.warps; }
+    return r;                                                        // {0, 0}: one decoder per one-warp CTA (ss_dgz.cuh)
+}
+
+uint32_t ss_dgz::decoders_per_sm(ss_dgz_shape sh) { return sh.lanes ? (uint32_t)(sh.lanes * sh.warps) : SS_DGZ_DECODERS_PER_SM; }
+
+template <int LANES, int WARPS>
+static cudaError_t dgz2_launch(const dgz2_job &J, unsigned int *next, int n_sm, cudaStream_t st) {
+    static_assert(dgz2_smem(LANES, WARPS) <= SS_DGZ2_SMEM_MAX, "the decode tables of a CTA must fit the shared memory of an SM");
+    cudaError_t e = cudaFuncSetAttribute(ss_dgz_decode_lanes_kernel<LANES, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgz2_smem(LANES, WARPS));
+    if (e != cudaSuccess) return e;
+    const uint32_t per_cta = WARPS * LANES;
+    const uint32_t grid = std::min<uint32_t>((J.n_pieces + per_cta - 1) / per_cta, (uint32_t)n_sm);
+    ss_dgz_decode_lanes_kernel<LANES, WARPS><<<grid, WARPS * 32, dgz2_smem(LANES, WARPS), st>>>(J, next);
+    return cudaGetLastError();
+}
+
+static cudaError_t dgz2_launch_shape(ss_dgz_shape sh, const dgz2_job &J, unsigned int *next, int n_sm, cudaStream_t st) {
+#define DGZ2_CASE(l, w) if (sh.lanes == l && sh.warps == w) return dgz2_launch<l, w>(J, next, n_sm, st)
+    DGZ2_CASE(1, 24); DGZ2_CASE(1, 32); DGZ2_CASE(2, 24); DGZ2_CASE(2, 32); DGZ2_CASE(3, 24); DGZ2_CASE(4, 23); DGZ2_CASE(8, 11);
+#undef DGZ2_CASE
+    return cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,13 +268,17 @@ void ss_dgz::close() {
     cudaFree(d_maps_); cudaFree(d_gpre_); cudaFree(d_wlen_);
     d_pieces_ = nullptr; d_sym_ = nullptr; d_windows_ = nullptr; d_order_ = nullptr; d_off_ = nullptr; d_ctr_ = nullptr;
     d_maps_ = nullptr; d_gpre_ = nullptr; d_wlen_ = nullptr;
+    alloc_pieces_ = 0; alloc_sym_ = 0;
 }
 
 int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
                  size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes) {
     const uint32_t old_pieces = max_pieces_, old_cap = cap_;
     n_sm_ = n_sm; st_ = st; d_comp_ = d_comp; h_comp_ = h_comp; size_ = comp_size; stop_at_ = std::min(stop_member_at, comp_size);
-    max_pieces_ = std::max(2u, std::min(max_pieces, 8192u));
+    max_pieces_ = std::max(2u, std::min(max_pieces, SS_DGZ_MAX_PIECES));
+    shape_ = shape_from_env();
+    prefetch_ = SS_DGZ_PREFETCH_DEFAULT;
+    if (const char *e = getenv("SS_DGZ_PREFETCH")) prefetch_ = (uint32_t)atoi(e);
     piece_ = std::max(4096u, piece_bytes);
     uint32_t expand = SS_DGZ_EXPAND_DEFAULT;
     if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) expand = (uint32_t)v; }
@@ -218,14 +293,16 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
     }
     cur_bit_ = (uint64_t)(first_member + h.header_len) * 8u;
     ratio_ = 4.0; ms_decode_ = ms_resolve_ = ms_windows_ = 0;
-    if (d_pieces_ && old_pieces == max_pieces_ && old_cap == cap_) {      // the buffers of an earlier stream fit: keep them
+    (void)old_pieces; (void)old_cap;
+    const size_t need_sym = (size_t)max_pieces_ * cap_;
+    if (d_pieces_ && alloc_pieces_ >= max_pieces_ && alloc_sym_ >= need_sym) {      // the buffers of an earlier stream do: keep them
         DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));
         h_pieces_.resize(max_pieces_);
         return SS_OK;
     }
     close();
     DGZ_CUDA(cudaMalloc(&d_pieces_, (size_t)max_pieces_ * sizeof(dgz_piece)));
-    DGZ_CUDA(cudaMalloc(&d_sym_, (size_t)max_pieces_ * cap_ * sizeof(uint16_t)));
+    DGZ_CUDA(cudaMalloc(&d_sym_, need_sym * sizeof(uint16_t)));
     DGZ_CUDA(cudaMalloc(&d_windows_, ((size_t)max_pieces_ + 1) * SS_DGZ_WINDOW));
     DGZ_CUDA(cudaMalloc(&d_order_, (size_t)max_pieces_ * sizeof(uint32_t)));
     DGZ_CUDA(cudaMalloc(&d_off_, (size_t)max_pieces_ * sizeof(uint64_t)));
@@ -234,6 +311,7 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
     DGZ_CUDA(cudaMalloc(&d_gpre_, ((size_t)max_pieces_ / SS_DGZ_GROUP + 1) * SS_DGZ_WINDOW * sizeof(uint16_t)));
     DGZ_CUDA(cudaMalloc(&d_wlen_, (size_t)max_pieces_ * sizeof(uint32_t)));
     DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));
+    alloc_pieces_ = max_pieces_; alloc_sym_ = need_sym;
     h_pieces_.resize(max_pieces_);
     return SS_OK;
 }
@@ -253,7 +331,7 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     uint32_t P = (uint32_t)std::min<uint64_t>(max_pieces_, (span + piece_ - 1) / piece_);
     P = (uint32_t)std::min<double>((double)P, (double)out_cap / ((double)piece_ * ratio_ * 1.15));
     {   // whole waves of decoders: a last wave with a few pieces costs as much as a full one
-        const uint32_t wave = (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM;
+        const uint32_t wave = (uint32_t)n_sm_ * decoders_per_sm(shape_);
         if (P > wave && P < (uint32_t)std::min<uint64_t>(max_pieces_, (span + piece_ - 1) / piece_)) P -= P % wave;
     }
     if (P == 0) P = 1;
@@ -271,9 +349,16 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     DGZ_CUDA(cudaMemsetAsync(d_ctr_, 0, sizeof(unsigned int), st_));
     DGZ_CUDA(cudaMemsetAsync(d_ctr_ + 1, 0xFF, sizeof(unsigned int), st_));
     if (P > 1) ss_dgz_find_kernel<<<std::min<uint32_t>(P - 1, (uint32_t)n_sm_ * 32u), 32, 0, st_>>>(d_comp_, avail, d_pieces_, P, first_byte, limit_bit, piece_);
-    ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, avail, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
-                                                                                    d_sym_, cap_, d_ctr_);
-    DGZ_CUDA(cudaGetLastError());
+    if (shape_.lanes) {
+        dgz2_job J;
+        J.comp = d_comp_; J.comp_size = avail; J.true_size = size_; J.pieces = d_pieces_; J.n_pieces = P;
+        J.limit_bit = limit_bit; J.stop_byte = (uint64_t)stop_at_; J.sym_pool = d_sym_; J.cap = cap_; J.prefetch = prefetch_;
+        DGZ_CUDA(dgz2_launch_shape(shape_, J, d_ctr_, n_sm_, st_));
+    } else {
+        ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, avail, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
+                                                                                        d_sym_, cap_, d_ctr_);
+        DGZ_CUDA(cudaGetLastError());
+    }
     DGZ_CUDA(cudaMemcpyAsync(h_pieces_.data(), d_pieces_, (size_t)P * sizeof(dgz_piece), cudaMemcpyDeviceToHost, st_));
     DGZ_CUDA(cudaStreamSynchronize(st_));
     batches_++;
@@ -364,6 +449,9 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
     std::vector<dgz_piece> pieces(max_pieces);
     std::vector<uint16_t> sym((size_t)max_pieces * cap);
     ssi_tables *tab = new ssi_tables;
+    const int lanes = ss_dgz::shape_from_env().lanes;
+    uint32_t rounds = SS_DGZ2_ROUND;
+    if (const char *e = getenv("SS_DGZ_ROUND")) { int v = atoi(e); if (v >= 1) rounds = (uint32_t)v; }    // tests: short rounds
     uint64_t found = 0, used = 0, batches = 0, members = 0;
     int rc = SS_OK;
     while (true) {
@@ -378,7 +466,13 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
             for (uint64_t p = from; p < to; p++)
                 if (dgz_quick_test(comp, comp_size, p) && dgz_full_test(comp, comp_size, p, *tab)) { pieces[j].start_bit = p; found++; break; }
         }
-        for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
+        if (lanes) {                                                  // the decoder of ss_dgz2.cuh (any lane count: the CPU runs one)
+            dgz2_job J;
+            J.comp = comp; J.comp_size = comp_size; J.true_size = comp_size; J.pieces = pieces.data(); J.n_pieces = P;
+            J.limit_bit = limit_bit; J.stop_byte = stop_byte; J.sym_pool = sym.data(); J.cap = cap; J.prefetch = 0;
+            dgz2_decode_pieces_host(J, rounds);
+        } else
+            for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
         batches++;
         uint32_t cur = 0;
         bool end = false;

@@ -12,6 +12,16 @@
 // bytes behind a batch's limit that must have arrived before the batch is decoded (a decoder runs on to the end of the
 // deflate block that straddles the limit); what lies further is out of bounds for that batch's kernels
 #define SS_DGZ_GATE_SLACK (8u << 20)
+#define SS_DGZ_MAX_PIECES 16384u          // pieces per batch at most
+// K8's shape: decoders per warp x warps per CTA of ss_dgz2.cuh (SS_DGZ_LANES, SS_DGZ_WARPS), or {0, 0}: one decoder
+// per one-warp CTA (ss_dgz.cuh)
+#ifndef SS_DGZ_LANES_DEFAULT
+#define SS_DGZ_LANES_DEFAULT 2
+#endif
+#ifndef SS_DGZ_PREFETCH_DEFAULT
+#define SS_DGZ_PREFETCH_DEFAULT 0
+#endif
+struct ss_dgz_shape { int lanes, warps; };
 
 // One gzip file (or the members of one file part) inflated batch by batch on the device.  The compressed bytes
 // [0, comp_size) sit in device memory (d_comp, padded by 16 readable bytes) and in host memory (h_comp: headers are
@@ -41,13 +51,18 @@ public:
     double ms_decode() const { return ms_decode_; }
     double ms_resolve() const { return ms_resolve_; }
     double ms_windows() const { return ms_windows_; }     // part of ms_resolve, SS_DEBUG_TIMING only
+    static ss_dgz_shape shape_from_env();
+    static uint32_t decoders_per_sm(ss_dgz_shape sh);      // K8 decoders resident per SM
 
 private:
     int n_sm_ = 0;
+    ss_dgz_shape shape_ = {0, 0};
+    uint32_t prefetch_ = 0;
     cudaStream_t st_ = nullptr;
     const uint8_t *d_comp_ = nullptr, *h_comp_ = nullptr;
     size_t size_ = 0, stop_at_ = 0;
     uint32_t max_pieces_ = 0, cap_ = 0, piece_ = 0;
+    size_t alloc_pieces_ = 0, alloc_sym_ = 0;     // what the device buffers were allocated for (they only grow)
     uint64_t cur_bit_ = 0;
     uint32_t win_len_ = 0;
     size_t gate_slack_ = SS_DGZ_GATE_SLACK;

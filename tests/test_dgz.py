@@ -27,6 +27,16 @@ def dgz(blob, first=0, stop=None, max_pieces=64, piece=8192, sym_per_byte=64, ca
     return out.raw[:n.value], stopped.value, list(stats)
 
 
+@pytest.fixture(autouse=True, params=["one_decoder_per_warp", "lanes", "lanes_short_rounds"])
+def decoder(request, monkeypatch):
+    """K8 exists twice: dgz_decode_piece (ss_dgz.cuh) and the decoder of ss_dgz2.cuh that several lanes of a warp run
+    (16-bit tables, rounds); every test runs on both, the second one also with rounds of 3 iterations."""
+    monkeypatch.setenv("SS_DGZ_LANES", "0" if request.param == "one_decoder_per_warp" else "4")
+    if request.param == "lanes_short_rounds":
+        monkeypatch.setenv("SS_DGZ_ROUND", "3")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def fastq():
     rng = np.random.default_rng(11)
@@ -123,3 +133,16 @@ def test_random_binary_streams_roundtrip():
         blob = gzip.compress(data, level)
         text, _, _ = dgz(blob, piece=int(rng.choice([4096, 8192, 32768])), max_pieces=int(rng.integers(2, 40)), sym_per_byte=64)
         assert text == data, (trial, level)
+
+
+def test_both_decoders_tell_the_same_story(fastq, monkeypatch):
+    """Pieces found / used, batches and members are properties of the stream and the piece size, not of the decoder."""
+    blobs = [gzip.compress(fastq, 1), gzip.compress(fastq, 9), b"".join(gzip.compress(fastq[i:i + 300_007], 4) for i in range(0, len(fastq), 300_007))]
+    for blob in blobs:
+        seen = []
+        for lanes in ("0", "4"):
+            monkeypatch.setenv("SS_DGZ_LANES", lanes)
+            text, stopped, st = dgz(blob, max_pieces=40, piece=8192, sym_per_byte=16)
+            assert text == fastq
+            seen.append((stopped, st))
+        assert seen[0] == seen[1]

@@ -553,8 +553,9 @@ def test_host_generator_equals_device_generator(eng):
     assert np.array_equal(buf.cpu().numpy(), synth_host.reads(p, n, first, threads=3))
 
 
+@pytest.mark.parametrize("lanes", ["0", "4", "8"])
 @pytest.mark.parametrize("shape", ["single", "members", "level9_small_batches"])
-def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape):
+def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape, lanes):
     """ss_dgz.cu: ordinary (non-blocked) gzip read files inflated on the device -- block starts found per piece, marker
     symbols, exact stitching, window chain -- through ss_count_files and ss_reads_from_files, against the oracle.  Small
     pieces / batches force many pieces, several batches and records carried from batch to batch; sharded runs split a
@@ -568,6 +569,7 @@ def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape):
     monkeypatch.setenv("SS_DGZ_PIECE_BYTES", "16384")
     monkeypatch.setenv("SS_DGZ_SYM_PER_BYTE", "32")
     monkeypatch.setenv("SS_DGZ_BATCH_MB", "8")
+    monkeypatch.setenv("SS_DGZ_LANES", lanes)            # K8: one decoder per warp (0) or 4 / 8 per warp (ss_dgz2.cuh)
     p1, p2 = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq.gz")
     if shape == "single":
         open(p1, "wb").write(gzip.compress(fq1, 6))
