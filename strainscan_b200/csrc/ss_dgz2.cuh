@@ -215,6 +215,7 @@ struct dgz2_job {            // what all decoders of a batch share
     uint16_t *sym_pool;
     uint32_t cap;
     uint32_t prefetch;       // device: 32-byte sectors the input is prefetched ahead of the bit reader (0 = not at all)
+    uint32_t rounds;         // iterations per round
 };
 
 #define DGZ2_ITER_SYMBOLS 259u           // an iteration writes at most a literal and a 258-symbol match
@@ -492,7 +493,7 @@ SS_HD void dgz2_after_round(dgz2_lane &L, const dgz2_job &J, int rc) {
 struct dgz2_vote_alone { SS_HD bool operator()(bool a) const { return a; } };     // a decoder that shares its warp with nobody
 
 // the CPU form of K8: one decoder takes the pieces one after the other
-inline void dgz2_decode_pieces_host(const dgz2_job &J, uint32_t rounds) {
+inline void dgz2_decode_pieces_host(const dgz2_job &J) {
     dgz_ctables *t = new dgz_ctables;
     uint32_t base_tab[64];
     for (uint32_t i = 0; i < 64; i++) base_tab[i] = dgc_base_entry(i);
@@ -506,7 +507,7 @@ inline void dgz2_decode_pieces_host(const dgz2_job &J, uint32_t rounds) {
             dgz2_begin_piece(L, J, next++);
             continue;
         }
-        const int rc = dgz2_round(L, *t, base_tab, budget, rounds, 0u, dgz2_vote_alone());
+        const int rc = dgz2_round(L, *t, base_tab, budget, J.rounds, 0u, dgz2_vote_alone());
         dgz2_after_round(L, J, rc);
     }
     delete t;
