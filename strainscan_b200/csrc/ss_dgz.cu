@@ -70,9 +70,11 @@ __global__ void __launch_bounds__(32, SS_DGZ_DECODERS_PER_SM) ss_dgz_decode_kern
 // ---------------------------------------------------------------------------------------------
 #define SS_DGZ2_ROUND 256u
 #define SS_DGZ2_SMEM_MAX 232448u
-constexpr uint32_t dgz2_smem(uint32_t lanes, uint32_t warps) { return 256u + warps * lanes * (uint32_t)sizeof(dgz_ctables); }
+constexpr uint32_t dgz2_smem(uint32_t lanes, uint32_t warps, bool ring) {
+    return 256u + warps * lanes * ((uint32_t)sizeof(dgz_ctables) + (ring ? DGZ2_RING * 2u : 0u));
+}
 
-template <int LANES, int WARPS, bool LOCKSTEP>
+template <int LANES, int WARPS, bool LOCKSTEP, bool RING>
 __global__ void __launch_bounds__(WARPS * 32, 1) ss_dgz_decode_lanes_kernel(dgz2_job J, unsigned int *__restrict__ next) {
     extern __shared__ __align__(16) uint8_t dgz2_shared[];
     uint32_t *base_tab = reinterpret_cast<uint32_t *>(dgz2_shared);
@@ -80,7 +82,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) ss_dgz_decode_lanes_kernel(dgz2
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (lane >= (uint32_t)LANES) return;
-    dgz_ctables &t = *reinterpret_cast<dgz_ctables *>(dgz2_shared + 256u + (warp * LANES + lane) * sizeof(dgz_ctables));
+    const uint32_t me = warp * LANES + lane;
+    dgz_ctables &t = *reinterpret_cast<dgz_ctables *>(dgz2_shared + 256u + me * sizeof(dgz_ctables));
+    uint16_t *ring = reinterpret_cast<uint16_t *>(dgz2_shared + 256u + WARPS * LANES * sizeof(dgz_ctables)) + (RING ? me * DGZ2_RING : 0u);
     const uint32_t mask = LANES >= 32 ? 0xFFFFFFFFu : (1u << LANES) - 1u;
     dgz2_lane L;
     L.mode = DGZ2_IDLE;
@@ -95,46 +99,51 @@ __global__ void __launch_bounds__(WARPS * 32, 1) ss_dgz_decode_lanes_kernel(dgz2
         }
         if (__all_sync(mask, L.mode == DGZ2_DONE)) break;
         int rc;
-        if constexpr (LOCKSTEP) rc = dgz2_round(L, t, base_tab, budget, J.rounds, J.prefetch, [mask](bool a) { return __any_sync(mask, a) != 0; });
-        else rc = dgz2_round(L, t, base_tab, budget, J.rounds, J.prefetch, dgz2_vote_alone());     // every lane at its own pace
+        if constexpr (LOCKSTEP) rc = dgz2_round<RING>(L, t, base_tab, ring, budget, J.rounds, [mask](bool a) { return __any_sync(mask, a) != 0; });
+        else rc = dgz2_round<RING>(L, t, base_tab, ring, budget, J.rounds, dgz2_vote_alone());        // every lane at its own pace
         dgz2_after_round(L, J, rc);
     }
 }
 
 // the shapes K8 is built in: decoders per warp x warps per CTA (one CTA per SM), the decoders of a warp in lockstep
-// (one vote per iteration) or each at its own pace inside a round; SS_DGZ_LANES / SS_DGZ_WARPS / SS_DGZ_LOCKSTEP pick one
-static const ss_dgz_shape dgz2_shapes[] = {{1, 24, 1}, {1, 32, 1}, {2, 24, 1}, {2, 32, 1}, {3, 24, 1}, {4, 23, 1}, {8, 11, 1},
-                                           {2, 24, 0}, {3, 24, 0}, {4, 23, 0}, {8, 11, 0}};
+// (one vote per iteration) or each at its own pace inside a round, with or without the ring of recent symbols in
+// shared memory; SS_DGZ_LANES / SS_DGZ_WARPS / SS_DGZ_LOCKSTEP / SS_DGZ_RING pick one
+static const ss_dgz_shape dgz2_shapes[] = {{2, 24, 1, 1}, {1, 24, 1, 1}, {1, 32, 1, 1}, {2, 24, 0, 1},
+                                           {1, 24, 1, 0}, {1, 32, 1, 0}, {2, 24, 1, 0}, {2, 32, 1, 0}, {3, 24, 1, 0}, {4, 23, 1, 0}, {8, 11, 1, 0},
+                                           {2, 24, 0, 0}, {3, 24, 0, 0}, {4, 23, 0, 0}};
 
 ss_dgz_shape ss_dgz::shape_from_env() {
-    int lanes = SS_DGZ_LANES_DEFAULT, warps = 0, lockstep = SS_DGZ_LOCKSTEP_DEFAULT;
+    int lanes = SS_DGZ_LANES_DEFAULT, warps = 0, lockstep = SS_DGZ_LOCKSTEP_DEFAULT, ring = SS_DGZ_RING_DEFAULT;
     if (const char *e = getenv("SS_DGZ_LANES")) lanes = atoi(e);
     if (const char *e = getenv("SS_DGZ_WARPS")) warps = atoi(e);
     if (const char *e = getenv("SS_DGZ_LOCKSTEP")) lockstep = atoi(e) != 0;
+    if (const char *e = getenv("SS_DGZ_RING")) ring = atoi(e) != 0;
     if (lanes == 1) lockstep = 1;
-    ss_dgz_shape r = {0, 0, 1};
+    if (lanes > 2) ring = 0;                                         // the rings of more than 50 decoders do not fit beside the tables
+    ss_dgz_shape r = {0, 0, 1, 0};
     for (const ss_dgz_shape &sh : dgz2_shapes)
-        if (r.lanes == 0 && sh.lanes == lanes && sh.lockstep == lockstep && (warps == 0 || sh.warps == warps)) r = sh;
+        if (r.lanes == 0 && sh.lanes == lanes && sh.lockstep == lockstep && sh.ring == ring && (warps == 0 || sh.warps == warps)) r = sh;
     return r;                                                        // {0, 0}: one decoder per one-warp CTA (ss_dgz.cuh)
 }
 
 uint32_t ss_dgz::decoders_per_sm(ss_dgz_shape sh) { return sh.lanes ? (uint32_t)(sh.lanes * sh.warps) : SS_DGZ_DECODERS_PER_SM; }
 
-template <int LANES, int WARPS, bool LOCKSTEP>
+template <int LANES, int WARPS, bool LOCKSTEP, bool RING>
 static cudaError_t dgz2_launch(const dgz2_job &J, unsigned int *next, int n_sm, cudaStream_t st) {
-    static_assert(dgz2_smem(LANES, WARPS) <= SS_DGZ2_SMEM_MAX, "the decode tables of a CTA must fit the shared memory of an SM");
-    cudaError_t e = cudaFuncSetAttribute(ss_dgz_decode_lanes_kernel<LANES, WARPS, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgz2_smem(LANES, WARPS));
+    static_assert(dgz2_smem(LANES, WARPS, RING) <= SS_DGZ2_SMEM_MAX, "the decode tables (and rings) of a CTA must fit the shared memory of an SM");
+    cudaError_t e = cudaFuncSetAttribute(ss_dgz_decode_lanes_kernel<LANES, WARPS, LOCKSTEP, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgz2_smem(LANES, WARPS, RING));
     if (e != cudaSuccess) return e;
     const uint32_t per_cta = WARPS * LANES;
     const uint32_t grid = std::min<uint32_t>((J.n_pieces + per_cta - 1) / per_cta, (uint32_t)n_sm);
-    ss_dgz_decode_lanes_kernel<LANES, WARPS, LOCKSTEP><<<grid, WARPS * 32, dgz2_smem(LANES, WARPS), st>>>(J, next);
+    ss_dgz_decode_lanes_kernel<LANES, WARPS, LOCKSTEP, RING><<<grid, WARPS * 32, dgz2_smem(LANES, WARPS, RING), st>>>(J, next);
     return cudaGetLastError();
 }
 
 static cudaError_t dgz2_launch_shape(ss_dgz_shape sh, const dgz2_job &J, unsigned int *next, int n_sm, cudaStream_t st) {
-#define DGZ2_CASE(l, w, k) if (sh.lanes == l && sh.warps == w && sh.lockstep == k) return dgz2_launch<l, w, k != 0>(J, next, n_sm, st)
-    DGZ2_CASE(1, 24, 1); DGZ2_CASE(1, 32, 1); DGZ2_CASE(2, 24, 1); DGZ2_CASE(2, 32, 1); DGZ2_CASE(3, 24, 1); DGZ2_CASE(4, 23, 1); DGZ2_CASE(8, 11, 1);
-    DGZ2_CASE(2, 24, 0); DGZ2_CASE(3, 24, 0); DGZ2_CASE(4, 23, 0); DGZ2_CASE(8, 11, 0);
+#define DGZ2_CASE(l, w, k, r) if (sh.lanes == l && sh.warps == w && sh.lockstep == k && sh.ring == r) return dgz2_launch<l, w, k != 0, r != 0>(J, next, n_sm, st)
+    DGZ2_CASE(2, 24, 1, 1); DGZ2_CASE(1, 24, 1, 1); DGZ2_CASE(1, 32, 1, 1); DGZ2_CASE(2, 24, 0, 1);
+    DGZ2_CASE(1, 24, 1, 0); DGZ2_CASE(1, 32, 1, 0); DGZ2_CASE(2, 24, 1, 0); DGZ2_CASE(2, 32, 1, 0); DGZ2_CASE(3, 24, 1, 0); DGZ2_CASE(4, 23, 1, 0); DGZ2_CASE(8, 11, 1, 0);
+    DGZ2_CASE(2, 24, 0, 0); DGZ2_CASE(3, 24, 0, 0); DGZ2_CASE(4, 23, 0, 0);
 #undef DGZ2_CASE
     return cudaErrorInvalidValue;
 }
@@ -283,8 +292,6 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
     n_sm_ = n_sm; st_ = st; d_comp_ = d_comp; h_comp_ = h_comp; size_ = comp_size; stop_at_ = std::min(stop_member_at, comp_size);
     max_pieces_ = std::max(2u, std::min(max_pieces, SS_DGZ_MAX_PIECES));
     shape_ = shape_from_env();
-    prefetch_ = SS_DGZ_PREFETCH_DEFAULT;
-    if (const char *e = getenv("SS_DGZ_PREFETCH")) prefetch_ = (uint32_t)atoi(e);
     rounds_ = SS_DGZ2_ROUND;
     if (const char *e = getenv("SS_DGZ_ROUND")) { int v = atoi(e); if (v >= 1) rounds_ = (uint32_t)v; }
     piece_ = std::max(4096u, piece_bytes);
@@ -360,7 +367,7 @@ int ss_dgz::next(uint8_t *d_out, size_t out_cap, size_t *n_out, bool *done) {
     if (shape_.lanes) {
         dgz2_job J;
         J.comp = d_comp_; J.comp_size = avail; J.true_size = size_; J.pieces = d_pieces_; J.n_pieces = P;
-        J.limit_bit = limit_bit; J.stop_byte = (uint64_t)stop_at_; J.sym_pool = d_sym_; J.cap = cap_; J.prefetch = prefetch_; J.rounds = rounds_;
+        J.limit_bit = limit_bit; J.stop_byte = (uint64_t)stop_at_; J.sym_pool = d_sym_; J.cap = cap_; J.rounds = rounds_;
         DGZ_CUDA(dgz2_launch_shape(shape_, J, d_ctr_, n_sm_, st_));
     } else {
         ss_dgz_decode_kernel<<<std::min<uint32_t>(P, (uint32_t)n_sm_ * SS_DGZ_DECODERS_PER_SM), 32, 0, st_>>>(d_comp_, avail, size_, d_pieces_, P, limit_bit, (uint64_t)stop_at_,
@@ -458,6 +465,8 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
     std::vector<uint16_t> sym((size_t)max_pieces * cap);
     ssi_tables *tab = new ssi_tables;
     const int lanes = ss_dgz::shape_from_env().lanes;
+    bool with_ring = SS_DGZ_RING_DEFAULT != 0;                        // (the CPU form has room for a ring whatever the lane count)
+    if (const char *e = getenv("SS_DGZ_RING")) with_ring = atoi(e) != 0;
     uint32_t rounds = SS_DGZ2_ROUND;
     if (const char *e = getenv("SS_DGZ_ROUND")) { int v = atoi(e); if (v >= 1) rounds = (uint32_t)v; }    // tests: short rounds
     uint64_t found = 0, used = 0, batches = 0, members = 0;
@@ -477,8 +486,8 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
         if (lanes) {                                                  // the decoder of ss_dgz2.cuh (any lane count: the CPU runs one)
             dgz2_job J;
             J.comp = comp; J.comp_size = comp_size; J.true_size = comp_size; J.pieces = pieces.data(); J.n_pieces = P;
-            J.limit_bit = limit_bit; J.stop_byte = stop_byte; J.sym_pool = sym.data(); J.cap = cap; J.prefetch = 0; J.rounds = rounds;
-            dgz2_decode_pieces_host(J);
+            J.limit_bit = limit_bit; J.stop_byte = stop_byte; J.sym_pool = sym.data(); J.cap = cap; J.rounds = rounds;
+            dgz2_decode_pieces_host(J, with_ring);
         } else
             for (uint32_t j = 0; j < P; j++) dgz_decode_piece(comp, comp_size, comp_size, pieces.data(), P, j, limit_bit, stop_byte, sym.data() + (size_t)j * cap, cap, *tab);
         batches++;

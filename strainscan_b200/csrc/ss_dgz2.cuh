@@ -202,6 +202,7 @@ struct dgz2_lane {
     ssi_stream s;
     uint16_t *sym;
     uint32_t me, n, nx, fresh;
+    uint32_t ring_from;      // symbols [ring_from, n) are in the decoder's ring (dgz2_round)
     int mode;
     bool unknown;
 };
@@ -214,7 +215,6 @@ struct dgz2_job {            // what all decoders of a batch share
     uint64_t limit_bit, stop_byte;
     uint16_t *sym_pool;
     uint32_t cap;
-    uint32_t prefetch;       // device: 32-byte sectors the input is prefetched ahead of the bit reader (0 = not at all)
     uint32_t rounds;         // iterations per round
 };
 
@@ -228,7 +228,7 @@ SS_HD void dgz2_begin_piece(dgz2_lane &L, const dgz2_job &J, uint32_t me) {
     if (pc.start_bit == ~0ull) { pc.status = SS_DGZ_NOSTART; L.mode = DGZ2_IDLE; return; }
     dgz_seek(L.s, J.comp, J.comp_size, pc.start_bit);
     L.sym = J.sym_pool + (uint64_t)me * J.cap;
-    L.n = 0; L.nx = me + 1; L.fresh = 0; L.unknown = true;
+    L.n = 0; L.nx = me + 1; L.fresh = 0; L.unknown = true; L.ring_from = 0;
     L.mode = DGZ2_BOUNDARY;
 }
 
@@ -357,11 +357,17 @@ SS_HD void dgz2_careful(dgz2_lane &L, const dgz2_job &J, const dgz_ctables &t) {
 // mode == DGZ2_IDLE (the caller hands it a piece: dgz2_begin_piece) or DGZ2_DONE.
 SS_HD uint32_t dgz2_advance(dgz2_lane &L, const dgz2_job &J, dgz_ctables &t) {
     while (true) {
-        if (L.mode == DGZ2_BOUNDARY) { dgz2_boundary(L, J, t); continue; }
+        if (L.mode == DGZ2_BOUNDARY) {
+            const uint32_t n0 = L.n;
+            dgz2_boundary(L, J, t);
+            if (L.n != n0) L.ring_from = L.n;                          // a stored block: its symbols are not in the ring
+            continue;
+        }
         if (L.mode == DGZ2_HUFF) {
             const uint32_t budget = dgz2_budget(L, J.cap);
             if (budget) return budget;
             dgz2_careful(L, J, t);
+            L.ring_from = L.n;
             continue;
         }
         return 0;
@@ -382,8 +388,15 @@ SS_HD uint32_t dgz2_advance(dgz2_lane &L, const dgz2_job &J, dgz_ctables &t) {
 // One round: up to `rounds` iterations of a decoder with `budget` (0: it sits the round out).  All decoders of a warp
 // enter together and run the same loop; `any_active(bool)` tells whether any of them still works (a warp vote on the
 // device).  Returns 0 (inside the block), 1 (the end-of-block code was consumed) or SSI_ERR_DATA.
-template <typename Vote>
-SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_tab, uint32_t budget, uint32_t rounds, uint32_t prefetch, Vote any_active) {
+//
+// RING: the decoder also keeps its last DGZ2_RING symbols in `ring` (shared memory on the device), and a match whose
+// source lies in there is copied out of it.  The symbol buffer of a piece lives in HBM / L2 (the windows of all
+// decoders in flight are several times the L2), so a copy out of it waits hundreds of cycles for its source -- the
+// largest single stall of the kernel -- while deflate's matches mostly reach back a few hundred bytes.  Positions
+// [L.ring_from, n) of the ring are valid (symbols produced outside a round do not go through it).
+#define DGZ2_RING 1024u
+template <bool RING, typename Vote>
+SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_tab, uint16_t *ring, uint32_t budget, uint32_t rounds, Vote any_active) {
     ssi_bits &b = L.s.bits;
     uint32_t cnt = 0, wi = 0, nextw = 0, n = L.n;
     uint64_t buf = 0;
@@ -401,15 +414,12 @@ SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_ta
     DGZ2_TABLE(base, base_tab);
     uint16_t *const sym = L.sym;
     const uint32_t fresh = L.fresh;
-    const uint32_t LM = (1u << DGC_LIT_BITS) - 1u, DM = (1u << DGC_DIST_BITS) - 1u;
+    const uint32_t ring_lo = RING ? (fresh > L.ring_from ? fresh : L.ring_from) : 0u;    // the ring serves sources at or behind it
+    const uint32_t LM = (1u << DGC_LIT_BITS) - 1u, DM = (1u << DGC_DIST_BITS) - 1u, RM = DGZ2_RING - 1u;
     uint32_t left = budget < rounds ? budget : rounds;
     int ret = 0;
-#ifdef __CUDA_ARCH__
-#define DGZ2_PREFETCH() do { if (prefetch && (wi & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(words + wi + 8u * prefetch)); } while (0)
-#else
-#define DGZ2_PREFETCH() do { (void)prefetch; } while (0)
-#endif
-#define DGZ2_REFILL() do { if (cnt < 32u) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; DGZ2_PREFETCH(); } } while (0)
+#define DGZ2_REFILL() do { if (cnt < 32u) { buf |= (uint64_t)nextw << cnt; cnt += 32u; nextw = words[++wi]; } } while (0)
+#define DGZ2_EMIT(pos, v) do { sym[pos] = (uint16_t)(v); if (RING) ring[(pos) & RM] = (uint16_t)(v); } while (0)
     while (any_active(left != 0)) {
         if (left == 0) continue;
         left--;
@@ -418,11 +428,11 @@ SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_ta
         DGZ2_LD16(e, lit, (uint32_t)buf & LM);
         if (DGC_KIND(e) == DGC_LIT) {                                  // first token a literal: a second one may follow
             buf >>= DGC_LEN(e); cnt -= DGC_LEN(e);
-            sym[n++] = (uint16_t)DGC_VAL(e);
+            DGZ2_EMIT(n, DGC_VAL(e)); n++;
             DGZ2_LD16(e, lit, (uint32_t)buf & LM);
             if (DGC_KIND(e) == DGC_LIT) {
                 buf >>= DGC_LEN(e); cnt -= DGC_LEN(e);
-                sym[n++] = (uint16_t)DGC_VAL(e);
+                DGZ2_EMIT(n, DGC_VAL(e)); n++;
                 continue;
             }
             DGZ2_REFILL();
@@ -432,7 +442,7 @@ SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_ta
             DGZ2_LD16(e, lit, DGC_VAL(e) + ((uint32_t)buf & ((1u << DGC_LEN(e)) - 1u)));
         }
         buf >>= DGC_LEN(e); cnt -= DGC_LEN(e);
-        if (DGC_KIND(e) == DGC_LIT) { sym[n++] = (uint16_t)DGC_VAL(e); continue; }
+        if (DGC_KIND(e) == DGC_LIT) { DGZ2_EMIT(n, DGC_VAL(e)); n++; continue; }
         if (DGC_KIND(e) != DGC_SYM) { ret = DGC_TAG(e) == DGC_TAG_EOB ? 1 : SSI_ERR_DATA; left = 0; continue; }
         uint32_t info;
         DGZ2_LD32(info, base, DGC_VAL(e));
@@ -450,8 +460,31 @@ SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_ta
         DGZ2_LD32(info, base, 32u + DGC_VAL(d));
         const uint32_t dist = (info & 0xFFFFu) + ((uint32_t)buf & ((1u << (info >> 16)) - 1u));
         buf >>= (info >> 16); cnt -= (info >> 16);
-        uint16_t *dst = sym + n;
-        if (dist <= n - fresh) {
+        if (RING && dist <= DGZ2_RING && dist <= n - ring_lo) {
+            // out of the ring.  Four symbols per step while neither the source nor the destination run wraps and the
+            // step's loads do not need its own stores; one at a time otherwise.
+            uint32_t i = 0;
+            if (dist >= 4u) {
+                for (; i < len; i += 4) {
+                    const uint32_t s0 = (n + i - dist) & RM, d0 = (n + i) & RM;
+                    if (s0 > RM - 3u || d0 > RM - 3u) break;
+                    const uint32_t rest = len - i;
+                    const uint16_t a0 = ring[s0];
+                    const uint16_t a1 = rest > 1 ? ring[s0 + 1] : (uint16_t)0;
+                    const uint16_t a2 = rest > 2 ? ring[s0 + 2] : (uint16_t)0;
+                    const uint16_t a3 = rest > 3 ? ring[s0 + 3] : (uint16_t)0;
+                    sym[n + i] = a0; ring[d0] = a0;
+                    if (rest > 1) { sym[n + i + 1] = a1; ring[d0 + 1] = a1; }
+                    if (rest > 2) { sym[n + i + 2] = a2; ring[d0 + 2] = a2; }
+                    if (rest > 3) { sym[n + i + 3] = a3; ring[d0 + 3] = a3; }
+                }
+            }
+            for (; i < len; i++) {
+                const uint16_t a = ring[(n + i - dist) & RM];
+                sym[n + i] = a; ring[(n + i) & RM] = a;
+            }
+        } else if (dist <= n - fresh) {
+            uint16_t *dst = sym + n;
             const uint16_t *src = dst - dist;
             if (dist >= 4u) {
                 // four symbols per step, the last step predicated (a step's loads never need its own stores)
@@ -465,18 +498,28 @@ SS_HD int dgz2_round(dgz2_lane &L, const dgz_ctables &t, const uint32_t *base_ta
                     if (rest > 1) dst[i + 1] = a1;
                     if (rest > 2) dst[i + 2] = a2;
                     if (rest > 3) dst[i + 3] = a3;
+                    if (RING) {
+                        ring[(n + i) & RM] = a0;
+                        if (rest > 1) ring[(n + i + 1) & RM] = a1;
+                        if (rest > 2) ring[(n + i + 2) & RM] = a2;
+                        if (rest > 3) ring[(n + i + 3) & RM] = a3;
+                    }
                 }
             } else {
-                for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+                for (uint32_t i = 0; i < len; i++) { const uint16_t a = src[i]; DGZ2_EMIT(n + i, a); }
             }
         } else {
             if (fresh != 0 || !L.unknown) { ret = SSI_ERR_DATA; left = 0; continue; }
-            dgz2_copy_marked(sym, n, dist, len);
+            for (uint32_t i = 0; i < len; i++) {                       // (partly) in the unknown window in front of the piece: markers
+                const int32_t idx = (int32_t)(n + i) - (int32_t)dist;
+                const uint16_t a = idx >= 0 ? sym[idx] : (uint16_t)(256 + (int32_t)SS_DGZ_WINDOW + idx);
+                DGZ2_EMIT(n + i, a);
+            }
         }
         n += len;
     }
 #undef DGZ2_REFILL
-#undef DGZ2_PREFETCH
+#undef DGZ2_EMIT
     if (budget) {
         b.in = reinterpret_cast<const uint8_t *>(words + wi); b.buf = buf; b.cnt = cnt;
         L.n = n;
@@ -493,10 +536,11 @@ SS_HD void dgz2_after_round(dgz2_lane &L, const dgz2_job &J, int rc) {
 struct dgz2_vote_alone { SS_HD bool operator()(bool a) const { return a; } };     // a decoder that shares its warp with nobody
 
 // the CPU form of K8: one decoder takes the pieces one after the other
-inline void dgz2_decode_pieces_host(const dgz2_job &J) {
+inline void dgz2_decode_pieces_host(const dgz2_job &J, bool with_ring) {
     dgz_ctables *t = new dgz_ctables;
     uint32_t base_tab[64];
     for (uint32_t i = 0; i < 64; i++) base_tab[i] = dgc_base_entry(i);
+    uint16_t *ring = new uint16_t[DGZ2_RING];
     dgz2_lane L;
     L.mode = DGZ2_IDLE;
     uint32_t next = 0;
@@ -507,8 +551,10 @@ inline void dgz2_decode_pieces_host(const dgz2_job &J) {
             dgz2_begin_piece(L, J, next++);
             continue;
         }
-        const int rc = dgz2_round(L, *t, base_tab, budget, J.rounds, 0u, dgz2_vote_alone());
+        const int rc = with_ring ? dgz2_round<true>(L, *t, base_tab, ring, budget, J.rounds, dgz2_vote_alone())
+                                 : dgz2_round<false>(L, *t, base_tab, ring, budget, J.rounds, dgz2_vote_alone());
         dgz2_after_round(L, J, rc);
     }
+    delete[] ring;
     delete t;
 }

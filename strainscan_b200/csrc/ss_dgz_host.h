@@ -18,13 +18,13 @@
 #ifndef SS_DGZ_LANES_DEFAULT
 #define SS_DGZ_LANES_DEFAULT 2
 #endif
-#ifndef SS_DGZ_PREFETCH_DEFAULT
-#define SS_DGZ_PREFETCH_DEFAULT 0
+#ifndef SS_DGZ_RING_DEFAULT
+#define SS_DGZ_RING_DEFAULT 1
 #endif
 #ifndef SS_DGZ_LOCKSTEP_DEFAULT
 #define SS_DGZ_LOCKSTEP_DEFAULT 1
 #endif
-struct ss_dgz_shape { int lanes, warps, lockstep; };
+struct ss_dgz_shape { int lanes, warps, lockstep, ring; };
 
 // One gzip file (or the members of one file part) inflated batch by batch on the device.  The compressed bytes
 // [0, comp_size) sit in device memory (d_comp, padded by 16 readable bytes) and in host memory (h_comp: headers are
@@ -59,8 +59,8 @@ public:
 
 private:
     int n_sm_ = 0;
-    ss_dgz_shape shape_ = {0, 0, 1};
-    uint32_t prefetch_ = 0, rounds_ = 256;
+    ss_dgz_shape shape_ = {0, 0, 1, 0};
+    uint32_t rounds_ = 256;
     cudaStream_t st_ = nullptr;
     const uint8_t *d_comp_ = nullptr, *h_comp_ = nullptr;
     size_t size_ = 0, stop_at_ = 0;

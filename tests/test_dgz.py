@@ -27,13 +27,16 @@ def dgz(blob, first=0, stop=None, max_pieces=64, piece=8192, sym_per_byte=64, ca
     return out.raw[:n.value], stopped.value, list(stats)
 
 
-@pytest.fixture(autouse=True, params=["one_decoder_per_warp", "lanes", "lanes_short_rounds"])
+@pytest.fixture(autouse=True, params=["one_decoder_per_warp", "lanes", "lanes_ring_short_rounds"])
 def decoder(request, monkeypatch):
     """K8 exists twice: dgz_decode_piece (ss_dgz.cuh) and the decoder of ss_dgz2.cuh that several lanes of a warp run
-    (16-bit tables, rounds); every test runs on both, the second one also with rounds of 3 iterations."""
+    (16-bit tables, rounds, a ring of recent symbols); every test runs on both, the second one also with the ring and
+    rounds of 3 iterations."""
     monkeypatch.setenv("SS_DGZ_LANES", "0" if request.param == "one_decoder_per_warp" else "4")
-    if request.param == "lanes_short_rounds":
+    monkeypatch.setenv("SS_DGZ_RING", "0")
+    if request.param == "lanes_ring_short_rounds":       # + the ring of recent symbols the match copies read from
         monkeypatch.setenv("SS_DGZ_ROUND", "3")
+        monkeypatch.setenv("SS_DGZ_RING", "1")
     return request.param
 
 
@@ -146,3 +149,21 @@ def test_both_decoders_tell_the_same_story(fastq, monkeypatch):
             assert text == fastq
             seen.append((stopped, st))
         assert seen[0] == seen[1]
+
+
+def test_match_distances_around_the_ring():
+    """Matches whose source lies exactly at, just inside and just outside the 1024-symbol ring of the lane decoder,
+    run-length matches (distance 1-3, overlapping copies) and copies that wrap around the ring's end."""
+    rng = np.random.default_rng(5)
+    parts = []
+    for period in (1, 2, 3, 4, 5, 1020, 1021, 1022, 1023, 1024, 1025, 1026, 1027, 2048, 5000, 31000):
+        block = bytes(rng.integers(33, 127, period, dtype=np.uint8))
+        reps = max(3, 2600 // period)
+        parts.append(block * reps)                                   # every repetition is a match at distance `period`
+        parts.append(bytes(rng.integers(33, 127, int(rng.integers(1, 40)), dtype=np.uint8)))     # shifts the ring phase
+    data = b"".join(parts) * 3
+    for level in (1, 6, 9):
+        blob = gzip.compress(data, level)
+        for piece, spb, max_pieces in ((4096, 256, 16), (65536, 64, 8)):
+            text, _, _ = dgz(blob, piece=piece, max_pieces=max_pieces, sym_per_byte=spb)
+            assert text == data, (level, piece)

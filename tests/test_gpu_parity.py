@@ -553,7 +553,7 @@ def test_host_generator_equals_device_generator(eng):
     assert np.array_equal(buf.cpu().numpy(), synth_host.reads(p, n, first, threads=3))
 
 
-@pytest.mark.parametrize("lanes", ["0", "2", "4", "3free"])
+@pytest.mark.parametrize("lanes", ["0", "2ring", "2", "4", "3free"])
 @pytest.mark.parametrize("shape", ["single", "members", "level9_small_batches"])
 def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape, lanes):
     """ss_dgz.cu: ordinary (non-blocked) gzip read files inflated on the device -- block starts found per piece, marker
@@ -569,11 +569,13 @@ def test_device_inflate_of_ordinary_gzip(eng, tmp_path, monkeypatch, shape, lane
     monkeypatch.setenv("SS_DGZ_PIECE_BYTES", "16384")
     monkeypatch.setenv("SS_DGZ_SYM_PER_BYTE", "32")
     monkeypatch.setenv("SS_DGZ_BATCH_MB", "8")
-    # K8: one decoder per one-warp CTA (0), or 2 / 4 per warp in lockstep, or 3 per warp each at its own pace (ss_dgz2.cuh)
-    monkeypatch.setenv("SS_DGZ_LANES", lanes.replace("free", ""))
+    # K8: one decoder per one-warp CTA (0); 2 per warp in lockstep with the shared-memory ring of recent symbols (what
+    # ships) or without it; 4 per warp with short rounds; 3 per warp, each at its own pace (ss_dgz2.cuh)
+    monkeypatch.setenv("SS_DGZ_LANES", lanes.rstrip("freing"))
     monkeypatch.setenv("SS_DGZ_LOCKSTEP", "0" if lanes.endswith("free") else "1")
+    monkeypatch.setenv("SS_DGZ_RING", "1" if lanes.endswith("ring") else "0")
     if lanes == "4":
-        monkeypatch.setenv("SS_DGZ_ROUND", "5")          # short rounds: many trips through the state machine
+        monkeypatch.setenv("SS_DGZ_ROUND", "5")          # many trips through the state machine
     p1, p2 = str(tmp_path / "a.fq.gz"), str(tmp_path / "b.fq.gz")
     if shape == "single":
         open(p1, "wb").write(gzip.compress(fq1, 6))
