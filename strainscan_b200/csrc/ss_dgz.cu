@@ -108,9 +108,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) ss_dgz_decode_lanes_kernel(dgz2
 // the shapes K8 is built in: decoders per warp x warps per CTA (one CTA per SM), the decoders of a warp in lockstep
 // (one vote per iteration) or each at its own pace inside a round, with or without the ring of recent symbols in
 // shared memory; SS_DGZ_LANES / SS_DGZ_WARPS / SS_DGZ_LOCKSTEP / SS_DGZ_RING pick one
-static const ss_dgz_shape dgz2_shapes[] = {{2, 24, 1, 1}, {1, 24, 1, 1}, {1, 32, 1, 1}, {2, 24, 0, 1},
-                                           {1, 24, 1, 0}, {1, 32, 1, 0}, {2, 24, 1, 0}, {2, 32, 1, 0}, {3, 24, 1, 0}, {4, 23, 1, 0}, {8, 11, 1, 0},
-                                           {2, 24, 0, 0}, {3, 24, 0, 0}, {4, 23, 0, 0}};
+static const ss_dgz_shape dgz2_shapes[] = {{2, 24, 1, 0}, {2, 24, 1, 1}, {1, 24, 1, 0}, {3, 24, 1, 0}, {4, 23, 1, 0}, {2, 24, 0, 0}, {3, 24, 0, 0}};
 
 ss_dgz_shape ss_dgz::shape_from_env() {
     int lanes = SS_DGZ_LANES_DEFAULT, warps = 0, lockstep = SS_DGZ_LOCKSTEP_DEFAULT, ring = SS_DGZ_RING_DEFAULT;
@@ -119,7 +117,7 @@ ss_dgz_shape ss_dgz::shape_from_env() {
     if (const char *e = getenv("SS_DGZ_LOCKSTEP")) lockstep = atoi(e) != 0;
     if (const char *e = getenv("SS_DGZ_RING")) ring = atoi(e) != 0;
     if (lanes == 1) lockstep = 1;
-    if (lanes > 2) ring = 0;                                         // the rings of more than 50 decoders do not fit beside the tables
+    if (lanes != 2 || !lockstep) ring = 0;                           // (the rings of more than 50 decoders do not fit beside the tables)
     ss_dgz_shape r = {0, 0, 1, 0};
     for (const ss_dgz_shape &sh : dgz2_shapes)
         if (r.lanes == 0 && sh.lanes == lanes && sh.lockstep == lockstep && sh.ring == ring && (warps == 0 || sh.warps == warps)) r = sh;
@@ -141,9 +139,8 @@ static cudaError_t dgz2_launch(const dgz2_job &J, unsigned int *next, int n_sm, 
 
 static cudaError_t dgz2_launch_shape(ss_dgz_shape sh, const dgz2_job &J, unsigned int *next, int n_sm, cudaStream_t st) {
 #define DGZ2_CASE(l, w, k, r) if (sh.lanes == l && sh.warps == w && sh.lockstep == k && sh.ring == r) return dgz2_launch<l, w, k != 0, r != 0>(J, next, n_sm, st)
-    DGZ2_CASE(2, 24, 1, 1); DGZ2_CASE(1, 24, 1, 1); DGZ2_CASE(1, 32, 1, 1); DGZ2_CASE(2, 24, 0, 1);
-    DGZ2_CASE(1, 24, 1, 0); DGZ2_CASE(1, 32, 1, 0); DGZ2_CASE(2, 24, 1, 0); DGZ2_CASE(2, 32, 1, 0); DGZ2_CASE(3, 24, 1, 0); DGZ2_CASE(4, 23, 1, 0); DGZ2_CASE(8, 11, 1, 0);
-    DGZ2_CASE(2, 24, 0, 0); DGZ2_CASE(3, 24, 0, 0); DGZ2_CASE(4, 23, 0, 0);
+    DGZ2_CASE(2, 24, 1, 0); DGZ2_CASE(2, 24, 1, 1); DGZ2_CASE(1, 24, 1, 0); DGZ2_CASE(3, 24, 1, 0); DGZ2_CASE(4, 23, 1, 0);
+    DGZ2_CASE(2, 24, 0, 0); DGZ2_CASE(3, 24, 0, 0);
 #undef DGZ2_CASE
     return cudaErrorInvalidValue;
 }

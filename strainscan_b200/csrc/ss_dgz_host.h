@@ -19,7 +19,7 @@
 #define SS_DGZ_LANES_DEFAULT 2
 #endif
 #ifndef SS_DGZ_RING_DEFAULT
-#define SS_DGZ_RING_DEFAULT 1
+#define SS_DGZ_RING_DEFAULT 0
 #endif
 #ifndef SS_DGZ_LOCKSTEP_DEFAULT
 #define SS_DGZ_LOCKSTEP_DEFAULT 1
