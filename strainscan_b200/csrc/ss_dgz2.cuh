@@ -1,16 +1,20 @@
-// ss_dgz2.cuh -- K8 of the device gzip inflate (ss_dgz.cuh) for SEVERAL decoders per warp.
+// ss_dgz2.cuh -- K8 of the device gzip inflate (ss_dgz.cuh) for SEVERAL decoders per warp; the form that ships.
+// Replaces the `zcat` of library/identify.py:82 / Vote_Strain_L2_Lasso_new_sp.py:359,367 together with K7, K9, K10.
 //
 // A Huffman decoder is one serial bit chain, so K8's throughput is decoders in flight x the rate of one.  With one
 // decoder per warp (ss_dgz.cuh: dgz_decode_piece) the register file allows 24 per SM and every instruction issued
-// works for one lane.  Here DGZ2_LANES lanes of a warp decode one piece each:
-//   - 16-bit decode-table entries and a 9-bit literal index (2.5 KB per decoder instead of 6.9 KB: 88 decoders per SM
-//     fit the shared memory);
-//   - the decoder is a state machine (want a piece / on a block boundary / inside a Huffman block), and the part that
+// works for one lane.  Here a few lanes of a warp decode one piece each (measured best: 2 lanes x 24 warps per SM,
+// DESIGN.md section 3b has the table):
+//   - 16-bit decode-table entries and a 9-bit literal index: 2.5 KB per decoder instead of 6.9 KB (up to 92 decoders
+//     per SM fit the shared memory);
+//   - the decoder is a state machine (wants a piece / on a block boundary / inside a Huffman block), and the part that
 //     is the work -- the symbols of a Huffman block -- runs in ROUNDS of a fixed number of iterations that the lanes
 //     of a warp enter together: inside a round the lanes follow the same instruction stream (an instruction issued
 //     serves all of them), everything rare (block headers, table building, stored blocks, the last bytes of the
 //     input, piece ends) happens between rounds, lane by lane;
-//   - an iteration takes up to two tokens: a literal, then a literal or a match.
+//   - an iteration takes up to two tokens: a literal, then a literal or a match;
+//   - optionally (measured slower, off by default) a ring of the decoder's last 1024 symbols in shared memory that
+//     match copies read instead of the symbol buffer in HBM / L2.
 // Same contract as dgz_decode_piece: the pieces' status / end_bit / n_sym / next / members / fresh_from come out
 // identical (tests/test_dgz.py runs both on the CPU against zlib).  SS_HD like the rest: the CPU runs the lanes one
 // after the other.
@@ -25,7 +29,7 @@
 
 // entry = val << 6 | kind << 4 | len
 //   LIT      val = the byte (code-length code: the symbol), len = code bits this step consumes
-//   SYM      val = length code - 257 / distance code; base and extra bits come from dgc_base_table
+//   SYM      val = length code - 257 / distance code; base and extra bits come from dgc_base_entry's table
 //   SUB      val = offset of the sub-table, len = its index bits (the step itself consumes the main index bits)
 //   SPECIAL  val 0 = invalid code, 1 = end of block (len = code bits), 2 = (while building) longest code under a prefix
 enum { DGC_LIT = 0, DGC_SYM = 1, DGC_SUB = 2, DGC_SPECIAL = 3 };
