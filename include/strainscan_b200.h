@@ -143,6 +143,12 @@ int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n
 int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
                         uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, char *out, size_t out_cap,
                         size_t *out_len, size_t *stopped_at, uint64_t *stats4);
+/* Host-only helper (no GPU needed): how the device inflate would cut up a gzip file (range) of `compressed_bytes` on a
+ * GPU of `n_sm` SMs whose head inflates to `head_ratio` text bytes per compressed byte.  out6 = piece bytes, pieces per
+ * batch at most, symbols of room per compressed byte of a piece, text bytes per batch, device bytes the plan takes,
+ * decoders in flight (one wave).  The kernel shape and the SS_DGZ_* overrides are read from the environment as in a
+ * real call (strainscan_b200/csrc/ss_dgz_host.h: ss_dgz_make_plan). */
+int ss_dgz_plan_host(size_t compressed_bytes, int n_sm, double head_ratio, uint64_t *out6);
 /* Same from in-memory FASTQ text (each buffer = one file's uncompressed contents). */
 int ss_reads_from_host(ss_ctx *ctx, const char *const *bufs, const size_t *lens, int n_bufs,
                        ss_reads **reads);

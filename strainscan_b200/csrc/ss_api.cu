@@ -892,6 +892,7 @@ struct dgz_file {
     size_t lo = 0, hi = 0;            // members that START in [lo, hi) are mine
     size_t first_member = 0;          // the first of them (== size: none)
     size_t up_hi = 0;                 // compressed bytes [first_member, up_hi) are uploaded
+    double ratio = 4.0;               // text bytes per compressed byte at the head of the file (sizes the decoder's buffers)
     void close_map() {
         if (map) munmap((void *)map, size);
         if (fd >= 0) close(fd);
@@ -930,9 +931,11 @@ static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, d
         ssi_gz_init(*g, df.map, df.size);
         uint8_t *pos = head.data() + SS_INGEST_HIST;
         int rc = ssi_gz_read(*g, &pos, head.data() + head.size());
-        delete g;
         const size_t hn = (size_t)(pos - (head.data() + SS_INGEST_HIST));
+        const size_t used = g->in_member ? (size_t)(ssi_in_pos(g->s.bits) - df.map) : (size_t)(g->p - df.map);
+        delete g;
         if (rc < 0 || hn == 0 || ss_fastx_kind((const char *)head.data() + SS_INGEST_HIST, hn, rc == SSI_OK) != 0) { df.close_map(); return false; }
+        if (used > h.header_len + 64) df.ratio = (double)hn / (double)(used - h.header_len);
     }
     df.lo = 0; df.hi = df.size;
     if (n_shards > 1) {
@@ -947,8 +950,15 @@ static bool dgz_eligible(ss_ctx *c, const char *path, int shard, int n_shards, d
     // everything up to the end of the member that straddles `hi`
     df.up_hi = df.hi >= df.size ? df.size : ss_gz_next_member_start(df.map, df.size, df.hi, df.size);
     if (df.up_hi < df.size) df.up_hi = std::min(df.size, df.up_hi + 64);
+    // room for what the device path still has to allocate: the decoder's buffers for this file's plan, the batch buffer,
+    // an upload buffer (what the context already holds from earlier files counts as there)
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < (df.up_hi - std::min(df.up_hi, df.first_member)) + ((ss_dgz::shape_from_env().lanes ? 24ull : 14ull) << 30)) {
+    const size_t n_up = df.up_hi - std::min(df.up_hi, df.first_member);
+    const ss_dgz_plan plan = ss_dgz_make_plan(n_up, c->n_sm, ss_dgz::shape_from_env(), df.ratio);
+    const size_t held = (c->dgz ? c->dgz->held_bytes() : 0) + c->dgz_scratch_cap;
+    size_t need = (plan.device_bytes > held ? plan.device_bytes - held : 0) + (1ull << 30);
+    if (n_up + 128 > std::min(c->dgz_up_cap[0], c->dgz_up_cap[1])) need += n_up + 128;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need) {
         df.close_map();
         return false;                                                // not enough room beside the read cache: host threads
     }
@@ -1037,21 +1047,8 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
     int rc = SS_OK;
     const size_t base_off = df.first_member, n_up = up.n_up;
     uint8_t *d_scratch = nullptr;
-    size_t scratch_cap = (ss_dgz::shape_from_env().lanes ? 4096ull : 2048ull) << 20;     // one wave of pieces inflates into it
-    if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) scratch_cap = (size_t)v << 20; }
-    // Pieces of at most 128 KiB, small enough for a whole WAVE of decoders (148 SMs x 24, or x 92 with several decoders
-    // per warp) to inflate into the scratch buffer, and sized so that the file is a whole number of waves: a last wave
-    // with a few pieces takes as long as a full one (an eighth of a config-3 file is 2.5 waves of 128 KiB pieces).
-    const uint32_t wave = (uint32_t)c->n_sm * ss_dgz::decoders_per_sm(ss_dgz::shape_from_env());
-    const double target = std::min<double>(128u << 10, std::floor((double)scratch_cap / ((double)wave * 4.6) / 4096.0) * 4096.0);
-    uint32_t piece = (uint32_t)std::max(16384.0, target), max_pieces = std::min<uint32_t>(2 * wave, SS_DGZ_MAX_PIECES);
-    {
-        const double waves = std::max(1.0, std::floor((double)n_up / ((double)wave * piece) + 0.5));
-        const double fit = std::ceil((double)n_up / (waves * wave) / 4096.0) * 4096.0;
-        if (fit >= 0.5 * piece && fit <= 1.1 * piece) piece = (uint32_t)fit;
-    }
-    if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) piece = (uint32_t)v; }
-    if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= (long long)SS_DGZ_MAX_PIECES) max_pieces = (uint32_t)v; }
+    const ss_dgz_plan plan = ss_dgz_make_plan(n_up, c->n_sm, ss_dgz::shape_from_env(), df.ratio);
+    const size_t scratch_cap = plan.scratch;
     auto cleanup = [&]() {};
 #define DGZ_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return ss_cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
     if (c->dgz_scratch_cap != scratch_cap) {
@@ -1069,7 +1066,7 @@ static int dgz_inflate_file(ss_ctx *c, dgz_file &df, dgz_upload &up, Sink &&sink
     // a batch is decoded once its compressed bytes (and SS_DGZ_GATE_SLACK behind them) have arrived
     dz.set_input_gate([&up, base_off](size_t need_byte) { return up.wait(need_byte > base_off ? need_byte - base_off : 0); },
                       [&up]() { std::lock_guard<std::mutex> lk(up.mu); return up.finished; });
-    rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, max_pieces, piece);
+    rc = dz.open(c->n_sm, c->stream, d_comp - base_off, df.map, df.up_hi, df.first_member, df.hi, plan);
     if (rc) { cleanup(); return fail(rc, "inflate failed on " + df.path + ": " + dz.error()); }
     std::vector<char> h_win(1u << 20);
     size_t carry = 0;
@@ -1424,6 +1421,16 @@ extern "C" int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t fi
         if (text.size() > out_cap) return fail(SS_ERR_ARG, "ss_dgz_inflate_host: output buffer too small");
         if (!text.empty()) memcpy(out, text.data(), text.size());
     }
+    return SS_OK;
+}
+
+// host-only: how a gzip file (range) of `compressed_bytes` would be cut up for the device inflate
+extern "C" int ss_dgz_plan_host(size_t compressed_bytes, int n_sm, double head_ratio, uint64_t *out6) {
+    if (!out6 || n_sm < 1) return fail(SS_ERR_ARG, "ss_dgz_plan_host: bad argument");
+    const ss_dgz_shape sh = ss_dgz::shape_from_env();
+    const ss_dgz_plan pl = ss_dgz_make_plan(compressed_bytes, n_sm, sh, head_ratio);
+    out6[0] = pl.piece; out6[1] = pl.max_pieces; out6[2] = pl.expand; out6[3] = pl.scratch; out6[4] = pl.device_bytes;
+    out6[5] = (uint64_t)n_sm * ss_dgz::decoders_per_sm(sh);
     return SS_OK;
 }
 

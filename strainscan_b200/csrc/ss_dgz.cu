@@ -283,18 +283,46 @@ void ss_dgz::close() {
     alloc_pieces_ = 0; alloc_sym_ = 0;
 }
 
+ss_dgz_plan ss_dgz_make_plan(size_t n_up, int n_sm, ss_dgz_shape shape, double ratio) {
+    ss_dgz_plan pl;
+    pl.ratio = std::min(64.0, std::max(1.0, ratio));
+    const uint32_t wave = (uint32_t)std::max(1, n_sm) * ss_dgz::decoders_per_sm(shape);
+    pl.scratch = (shape.lanes ? 4096ull : 2048ull) << 20;
+    if (const char *e = getenv("SS_DGZ_BATCH_MB")) { long long v = atoll(e); if (v >= 8 && v <= 16384) pl.scratch = (size_t)v << 20; }
+    // symbol room: 2.5 x the head's ratio (a piece runs on to the next FOUND start, which may lie well behind the next
+    // nominal one, and the head under-estimates), never under the 5 of the first version
+    pl.expand = (uint32_t)std::min(48.0, std::max((double)SS_DGZ_EXPAND_DEFAULT, std::ceil(2.5 * pl.ratio)));
+    if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) pl.expand = (uint32_t)v; }
+    // piece size: a wave's text (1.3 x the head's ratio per compressed byte, at least what 3.5 would give) fits the batch buffer
+    const double per_byte = 1.3 * std::max(3.5, pl.ratio);
+    const double p_max = std::max(16384.0, std::min<double>(128u << 10, std::floor((double)pl.scratch / ((double)wave * per_byte) / 4096.0) * 4096.0));
+    const double waves = std::max(1.0, std::ceil((double)n_up / ((double)wave * p_max)));
+    double fit = std::ceil((double)n_up / (waves * wave) / 256.0) * 256.0;
+    if (fit > p_max) fit = p_max;
+    if (fit < std::min(p_max, 32768.0)) fit = std::min(p_max, 32768.0);       // small inputs: fewer pieces than decoders
+    pl.piece = (uint32_t)fit;
+    if (const char *e = getenv("SS_DGZ_PIECE_BYTES")) { long long v = atoll(e); if (v >= 4096 && v <= (16 << 20)) pl.piece = (uint32_t)v; }
+    pl.max_pieces = std::min<uint32_t>(wave + wave / 8u, SS_DGZ_MAX_PIECES);   // (two waves would need a ratio under 2 to fit the batch buffer)
+    if (const char *e = getenv("SS_DGZ_MAX_PIECES")) { long long v = atoll(e); if (v >= 2 && v <= (long long)SS_DGZ_MAX_PIECES) pl.max_pieces = (uint32_t)v; }
+    pl.max_pieces = std::max(2u, pl.max_pieces);
+    pl.piece = std::max(4096u, pl.piece);
+    pl.device_bytes = pl.scratch + (size_t)pl.max_pieces * ((size_t)pl.piece * pl.expand * sizeof(uint16_t) + SS_DGZ_WINDOW * 3u + 64u) + (64u << 20);
+    return pl;
+}
+
+size_t ss_dgz::held_bytes() const {
+    return d_pieces_ ? alloc_sym_ * sizeof(uint16_t) + alloc_pieces_ * ((size_t)SS_DGZ_WINDOW * 3u + 64u) : 0;
+}
+
 int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
-                 size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes) {
-    const uint32_t old_pieces = max_pieces_, old_cap = cap_;
+                 size_t stop_member_at, const ss_dgz_plan &plan) {
     n_sm_ = n_sm; st_ = st; d_comp_ = d_comp; h_comp_ = h_comp; size_ = comp_size; stop_at_ = std::min(stop_member_at, comp_size);
-    max_pieces_ = std::max(2u, std::min(max_pieces, SS_DGZ_MAX_PIECES));
+    max_pieces_ = std::max(2u, std::min(plan.max_pieces, SS_DGZ_MAX_PIECES));
     shape_ = shape_from_env();
     rounds_ = SS_DGZ2_ROUND;
     if (const char *e = getenv("SS_DGZ_ROUND")) { int v = atoi(e); if (v >= 1) rounds_ = (uint32_t)v; }
-    piece_ = std::max(4096u, piece_bytes);
-    uint32_t expand = SS_DGZ_EXPAND_DEFAULT;
-    if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) expand = (uint32_t)v; }
-    cap_ = piece_ * expand;
+    piece_ = std::max(4096u, plan.piece);
+    cap_ = piece_ * std::max(1u, plan.expand);
     done_ = false; win_len_ = 0; members_ = 0; pieces_used_ = pieces_found_ = batches_ = 0;
     gate_slack_ = SS_DGZ_GATE_SLACK;
     if (const char *e = getenv("SS_DGZ_GATE_SLACK")) { long long v = atoll(e); if (v >= 0) gate_slack_ = (size_t)v; }   // tests: small slack = retries
@@ -304,8 +332,7 @@ int ss_dgz::open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t
         return SS_ERR_IO;
     }
     cur_bit_ = (uint64_t)(first_member + h.header_len) * 8u;
-    ratio_ = 4.0; ms_decode_ = ms_resolve_ = ms_windows_ = 0;
-    (void)old_pieces; (void)old_cap;
+    ratio_ = std::max(2.0, 1.3 * plan.ratio); ms_decode_ = ms_resolve_ = ms_windows_ = 0;     // sizes the first batch; the stream corrects it
     const size_t need_sym = (size_t)max_pieces_ * cap_;
     if (d_pieces_ && alloc_pieces_ >= max_pieces_ && alloc_sym_ >= need_sym) {      // the buffers of an earlier stream do: keep them
         DGZ_CUDA(cudaMemsetAsync(d_windows_, 0, SS_DGZ_WINDOW, st_));

@@ -26,6 +26,26 @@
 #endif
 struct ss_dgz_shape { int lanes, warps, lockstep, ring; };
 
+// How one file is cut up for the device: piece size, pieces per batch, symbol room per piece, text room per batch.
+//   - a WAVE is one piece per resident decoder (n_sm x decoders_per_sm); a wave's text must fit the batch buffer, so the
+//     piece size is bounded by scratch / (wave x expected text per compressed byte), and by 128 KiB;
+//   - the file should be a whole number of waves (a last wave with a few pieces takes as long as a full one): the
+//     smallest number of waves whose pieces respect the bound, pieces sized to fill them exactly;
+//   - `ratio` = text bytes per compressed byte the stream's head inflated to (dgz_eligible measures it on the first
+//     64 KiB of text; the empty window at the start makes it an under-estimate, hence the margins): it sizes the symbol
+//     room of a piece -- a piece that runs out of it ends the batch early (status FULL), so a fixed room would turn
+//     well-compressed inputs into one piece per batch.
+// Environment overrides (tests, experiments): SS_DGZ_BATCH_MB, SS_DGZ_PIECE_BYTES, SS_DGZ_MAX_PIECES, SS_DGZ_SYM_PER_BYTE.
+struct ss_dgz_plan {
+    uint32_t piece;          // compressed bytes per piece
+    uint32_t max_pieces;     // pieces per batch at most
+    uint32_t expand;         // symbols a piece may produce per compressed byte of its nominal size
+    size_t scratch;          // text bytes per batch
+    size_t device_bytes;     // what the decoder's device buffers and the batch buffer take with this plan
+    double ratio;            // the estimate the plan was made with
+};
+ss_dgz_plan ss_dgz_make_plan(size_t n_up, int n_sm, ss_dgz_shape shape, double ratio);
+
 // One gzip file (or the members of one file part) inflated batch by batch on the device.  The compressed bytes
 // [0, comp_size) sit in device memory (d_comp, padded by 16 readable bytes) and in host memory (h_comp: headers are
 // parsed there).  Text comes out in stream order, cut anywhere (the caller carries partial records over).
@@ -37,7 +57,8 @@ public:
     ss_dgz &operator=(const ss_dgz &) = delete;
     // first_member: byte offset of a member header; members that start at or behind stop_member_at are not decoded
     int open(int n_sm, cudaStream_t st, const uint8_t *d_comp, const uint8_t *h_comp, size_t comp_size, size_t first_member,
-             size_t stop_member_at, uint32_t max_pieces, uint32_t piece_bytes);
+             size_t stop_member_at, const ss_dgz_plan &plan);
+    size_t held_bytes() const;                             // device memory the buffers take now
     // While the compressed bytes are still being uploaded: wait(need) blocks until bytes [0, need) of the file are on the
     // device (false: the upload failed); complete() tells whether everything has arrived.  A batch that fails while the
     // upload was still running is decoded again once it is complete (a block longer than the slack the gate allows).

@@ -50,7 +50,7 @@ def fastq():
 def test_single_stream_levels_and_piece_sizes(fastq):
     for level in (1, 6, 9):
         blob = gzip.compress(fastq, level)
-        for piece, max_pieces in ((4096, 1000), (16384, 7), (65536, 3), (1 << 20, 2)):
+        for piece, max_pieces in ((4096, 1000), (12544, 37), (16384, 7), (65536, 3), (1 << 20, 2)):      # (any multiple of 256 may be planned)
             text, stopped, st = dgz(blob, max_pieces=max_pieces, piece=piece)
             assert text == fastq, (level, piece)
             assert stopped == len(blob) and st[3] == 1
@@ -167,3 +167,41 @@ def test_match_distances_around_the_ring():
         for piece, spb, max_pieces in ((4096, 256, 16), (65536, 64, 8)):
             text, _, _ = dgz(blob, piece=piece, max_pieces=max_pieces, sym_per_byte=spb)
             assert text == data, (level, piece)
+
+
+def test_plan_of_pieces_and_buffers(monkeypatch):
+    """ss_dgz_make_plan: whole waves of decoders, a wave's text inside the batch buffer, symbol room that follows the
+    input's compression ratio (a piece out of room ends its batch), environment overrides."""
+    lib = _lib.load()
+    for name in ("SS_DGZ_LANES", "SS_DGZ_WARPS", "SS_DGZ_BATCH_MB", "SS_DGZ_PIECE_BYTES", "SS_DGZ_MAX_PIECES", "SS_DGZ_SYM_PER_BYTE", "SS_DGZ_RING"):
+        monkeypatch.delenv(name, raising=False)
+
+    def plan(n, ratio, n_sm=148):
+        out = (C.c_uint64 * 6)()
+        assert lib.ss_dgz_plan_host(n, n_sm, ratio, out) == 0
+        return dict(zip(("piece", "max_pieces", "expand", "scratch", "device_bytes", "wave"), [int(x) for x in out]))
+
+    for lanes in ("0", "2", "4"):
+        monkeypatch.setenv("SS_DGZ_LANES", lanes)
+        for n, ratio in ((9_300_000_000, 1.7), (1_160_000_000, 1.7), (3_700_000_000, 4.5), (40_000_000, 3.0), (2_000_000_000, 9.0)):
+            p = plan(n, ratio)
+            assert p["wave"] == 148 * {"0": 24, "2": 48, "4": 92}[lanes]
+            assert 16384 <= p["piece"] <= 128 << 10 and p["piece"] % 256 == 0
+            assert p["max_pieces"] >= p["wave"]                                    # a whole wave per batch ...
+            assert p["wave"] * p["piece"] * 1.3 * max(3.5, ratio) <= p["scratch"] * 1.001 or p["piece"] == 16384   # ... whose text fits
+            assert p["expand"] >= max(5, int(2.5 * ratio))                         # room for well-compressed inputs
+            n_pieces = -(-n // p["piece"])
+            waves = -(-n_pieces // p["wave"])
+            if n_pieces > p["wave"]:                                               # the last wave is (nearly) full
+                assert n_pieces > (waves - 1) * p["wave"] + 0.9 * p["wave"], (lanes, n, ratio, p)
+            assert p["device_bytes"] < 60 << 30
+    monkeypatch.setenv("SS_DGZ_LANES", "2")
+    # an eighth of a config-3 file: two full waves of ~80 KiB pieces, not one full and a quarter
+    p = plan(1_160_000_000, 1.7)
+    assert 2 * p["wave"] * p["piece"] >= 1_160_000_000 > 2 * p["wave"] * (p["piece"] - 256)
+    monkeypatch.setenv("SS_DGZ_PIECE_BYTES", "20480")
+    monkeypatch.setenv("SS_DGZ_MAX_PIECES", "17")
+    monkeypatch.setenv("SS_DGZ_SYM_PER_BYTE", "33")
+    monkeypatch.setenv("SS_DGZ_BATCH_MB", "64")
+    p = plan(10 ** 9, 2.0)
+    assert (p["piece"], p["max_pieces"], p["expand"], p["scratch"]) == (20480, 17, 33, 64 << 20)
