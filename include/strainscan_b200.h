@@ -143,6 +143,11 @@ int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n
 int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
                         uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, char *out, size_t out_cap,
                         size_t *out_len, size_t *stopped_at, uint64_t *stats4);
+/* Host-only self-test (no GPU needed): the 16-bit Huffman decode tables of the device gzip decoder (ss_dgz2.cuh) against
+ * the 32-bit tables of the host decoder (ss_inflate.cuh) on `trials` random prefix codes -- literal/length codes of
+ * 257..286 symbols and distance codes of 1..30 symbols with lengths up to 15, the single-code and the empty distance
+ * code, over-subscribed and incomplete codes; every 15-bit pattern must decode alike.  *n_checked = patterns compared. */
+int ss_dgz_tables_selftest_host(uint64_t seed, uint32_t trials, uint64_t *n_checked);
 /* Host-only helper (no GPU needed): how the device inflate would cut up a gzip file (range) of `compressed_bytes` on a
  * GPU of `n_sm` SMs whose head inflates to `head_ratio` text bytes per compressed byte.  out6 = piece bytes, pieces per
  * batch at most, symbols of room per compressed byte of a piece, text bytes per batch, device bytes the plan takes,

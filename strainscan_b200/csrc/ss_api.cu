@@ -1424,6 +1424,13 @@ extern "C" int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t fi
     return SS_OK;
 }
 
+// host-only: the two decode-table forms against each other on random prefix codes
+extern "C" int ss_dgz_tables_selftest_host(uint64_t seed, uint32_t trials, uint64_t *n_checked) {
+    std::string err;
+    if (ss_dgz_tables_selftest(seed, trials, n_checked, err)) return fail(SS_ERR_FORMAT, "decode-table self-test: " + err);
+    return SS_OK;
+}
+
 // host-only: how a gzip file (range) of `compressed_bytes` would be cut up for the device inflate
 extern "C" int ss_dgz_plan_host(size_t compressed_bytes, int n_sm, double head_ratio, uint64_t *out6) {
     if (!out6 || n_sm < 1) return fail(SS_ERR_ARG, "ss_dgz_plan_host: bad argument");

@@ -541,3 +541,111 @@ int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_memb
     if (stats4) { stats4[0] = found; stats4[1] = used; stats4[2] = batches; stats4[3] = members; }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// host-only self-test: the 16-bit decode tables of ss_dgz2.cuh against the 32-bit ones of ss_inflate.cuh on RANDOM
+// prefix codes (zlib's own streams only show the code shapes zlib's heuristics produce; other compressors make others)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct dgz_rng {
+    uint64_t s;
+    uint32_t next() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 16); }
+    uint32_t below(uint32_t n) { return next() % n; }
+};
+
+// code lengths of a complete prefix code with `used` of `n` symbols (used >= 2): leaves split at random, deep ones preferred
+void dgz_random_code(dgz_rng &r, uint8_t *lens, int n, int used, int max_len) {
+    std::vector<int> depth(1, 0);
+    while ((int)depth.size() < used) {
+        size_t pick = r.below((uint32_t)depth.size());
+        for (int tries = 0; tries < 3; tries++) {                  // prefer a deeper leaf: long codes, sub-tables
+            const size_t other = r.below((uint32_t)depth.size());
+            if (depth[other] > depth[pick] && depth[other] < max_len) pick = other;
+        }
+        if (depth[pick] >= max_len) {
+            bool any = false;
+            for (size_t i = 0; i < depth.size(); i++) if (depth[i] < max_len) { pick = i; any = true; break; }
+            if (!any) break;
+        }
+        depth[pick]++;
+        depth.push_back(depth[pick]);
+    }
+    for (int i = 0; i < n; i++) lens[i] = 0;
+    std::vector<int> sym(n);
+    for (int i = 0; i < n; i++) sym[i] = i;
+    for (int i = n - 1; i > 0; i--) std::swap(sym[i], sym[r.below((uint32_t)i + 1)]);
+    for (size_t i = 0; i < depth.size(); i++) lens[sym[i]] = (uint8_t)depth[i];
+}
+
+// what the next symbol of bit pattern v is, by either table: kind (0 literal, 1 base + extra, 2 end of block, 3 invalid),
+// value, extra bits, code bits consumed
+struct dgz_sym { uint32_t kind, val, extra, bits; };
+dgz_sym dgz_lookup32(const uint32_t *t, uint32_t v, uint32_t tb) {
+    uint32_t e = t[v & ((1u << tb) - 1u)], bits = 0;
+    if (SSI_KIND(e) == SSI_SUB) { bits = tb; e = t[SSI_VAL(e) + ((v >> tb) & ((1u << SSI_EXTRA(e)) - 1u))]; }
+    bits += SSI_LEN(e);
+    switch (SSI_KIND(e)) {
+    case SSI_LIT: return {0, SSI_VAL(e), 0, bits};
+    case SSI_BASE: return {1, SSI_VAL(e), SSI_EXTRA(e), bits};
+    case SSI_EOB: return {2, 0, 0, bits};
+    default: return {3, 0, 0, 0};
+    }
+}
+dgz_sym dgz_lookup16(const uint16_t *t, uint32_t v, uint32_t tb, uint32_t base_off) {
+    uint32_t e = t[v & ((1u << tb) - 1u)], bits = 0;
+    if (DGC_KIND(e) == DGC_SUB) { bits = tb; e = t[DGC_VAL(e) + ((v >> tb) & ((1u << DGC_LEN(e)) - 1u))]; }
+    bits += DGC_LEN(e);
+    if (DGC_KIND(e) == DGC_LIT) return {0, DGC_VAL(e), 0, bits};
+    if (DGC_KIND(e) == DGC_SYM) { const uint32_t info = dgc_base_entry(base_off + DGC_VAL(e)); return {1, info & 0xFFFFu, info >> 16, bits}; }
+    if (DGC_TAG(e) == DGC_TAG_EOB) return {2, 0, 0, bits};
+    return {3, 0, 0, 0};
+}
+}   // namespace
+
+int ss_dgz_tables_selftest(uint64_t seed, uint32_t trials, uint64_t *n_checked, std::string &err) {
+    dgz_rng r{seed * 0x9E3779B97F4A7C15ull + 1u};
+    ssi_tables *a = new ssi_tables;
+    dgz_ctables *b = new dgz_ctables;
+    uint64_t checked = 0;
+    int rc = 0;
+    for (uint32_t trial = 0; trial < trials && !rc; trial++) {
+        uint8_t lens[288];
+        // literal / length code: 257..286 symbols, 2..all of them used, lengths up to 15
+        const int hlit = 257 + (int)r.below(30), used = 2 + (int)r.below((uint32_t)hlit - 1);
+        dgz_random_code(r, lens, hlit, used, 15);
+        const int ra = ssi_build_table(a->lit, SSI_LIT_CAP, lens, hlit, SSI_LIT_BITS, SSI_CODE_LIT);
+        const int rb = dgc_build_table(b->lit, DGC_LIT_CAP, lens, hlit, DGC_LIT_BITS, SSI_CODE_LIT);
+        if (ra != rb) { err = "the two builders disagree on whether a literal code is valid"; rc = 1; break; }
+        if (!ra)
+            for (uint32_t v = 0; v < 32768u; v++) {
+                const dgz_sym x = dgz_lookup32(a->lit, v, SSI_LIT_BITS), y = dgz_lookup16(b->lit, v, DGC_LIT_BITS, 0);
+                if (x.kind != y.kind || x.val != y.val || x.extra != y.extra || x.bits != y.bits) { err = "literal / length tables decode a bit pattern differently"; rc = 1; break; }
+                checked++;
+            }
+        // distance code: 1..30 symbols; also the single code of length 1 and the empty code
+        const int hdist = 1 + (int)r.below(30);
+        const uint32_t shape = r.below(8);
+        if (shape == 0) { for (int i = 0; i < hdist; i++) lens[i] = 0; }
+        else if (shape == 1 || hdist < 2) { for (int i = 0; i < hdist; i++) lens[i] = 0; lens[r.below((uint32_t)hdist)] = 1; }
+        else dgz_random_code(r, lens, hdist, 2 + (int)r.below((uint32_t)hdist - 1), 15);
+        const int da = ssi_build_table(a->dist, SSI_DIST_CAP, lens, hdist, SSI_DIST_BITS, SSI_CODE_DIST);
+        const int db = dgc_build_table(b->dist, DGC_DIST_CAP, lens, hdist, DGC_DIST_BITS, SSI_CODE_DIST);
+        if (da != db) { err = "the two builders disagree on whether a distance code is valid"; rc = 1; break; }
+        if (!da && !rc)
+            for (uint32_t v = 0; v < 32768u; v++) {
+                const dgz_sym x = dgz_lookup32(a->dist, v, SSI_DIST_BITS), y = dgz_lookup16(b->dist, v, DGC_DIST_BITS, 32);
+                if (x.kind != y.kind || x.val != y.val || x.extra != y.extra || x.bits != y.bits) { err = "distance tables decode a bit pattern differently"; rc = 1; break; }
+                checked++;
+            }
+        // an over-subscribed and an incomplete code must be refused by both
+        if (hlit > 10) {
+            for (int i = 0; i < hlit; i++) lens[i] = (uint8_t)(i < 5 ? 2 : 0);
+            if (!ssi_build_table(a->lit, SSI_LIT_CAP, lens, hlit, SSI_LIT_BITS, SSI_CODE_LIT) || !dgc_build_table(b->lit, DGC_LIT_CAP, lens, hlit, DGC_LIT_BITS, SSI_CODE_LIT)) { err = "an over-subscribed code was accepted"; rc = 1; }
+            for (int i = 0; i < hlit; i++) lens[i] = (uint8_t)(i < 3 ? 2 : 0);
+            if (!ssi_build_table(a->lit, SSI_LIT_CAP, lens, hlit, SSI_LIT_BITS, SSI_CODE_LIT) || !dgc_build_table(b->lit, DGC_LIT_CAP, lens, hlit, DGC_LIT_BITS, SSI_CODE_LIT)) { err = "an incomplete code was accepted"; rc = 1; }
+        }
+    }
+    delete a; delete b;
+    if (n_checked) *n_checked = checked;
+    return rc;
+}

@@ -112,3 +112,7 @@ private:
 int ss_dgz_host_inflate(const uint8_t *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
                         uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, std::vector<uint8_t> &out,
                         size_t *stopped_at, uint64_t *stats4, std::string &err);
+
+// host-only self-test of the 16-bit decode tables (ss_dgz2.cuh) against the 32-bit ones (ss_inflate.cuh) on random
+// prefix codes: every 15-bit pattern must decode to the same symbol, value, extra bits and length.  0 = agree.
+int ss_dgz_tables_selftest(uint64_t seed, uint32_t trials, uint64_t *n_checked, std::string &err);

@@ -205,3 +205,14 @@ def test_plan_of_pieces_and_buffers(monkeypatch):
     monkeypatch.setenv("SS_DGZ_BATCH_MB", "64")
     p = plan(10 ** 9, 2.0)
     assert (p["piece"], p["max_pieces"], p["expand"], p["scratch"]) == (20480, 17, 33, 64 << 20)
+
+
+def test_decode_tables_agree_on_random_codes():
+    """The 16-bit decode tables of the lane decoder against the 32-bit tables of the host decoder on random prefix codes
+    (shapes zlib never writes: 15-bit codes under many prefixes, two-symbol codes, single-code and empty distance codes)."""
+    lib = _lib.load()
+    n = C.c_uint64()
+    for seed in (1, 2, 3):
+        rc = lib.ss_dgz_tables_selftest_host(seed, 150, C.byref(n))
+        assert rc == 0, lib.ss_last_error().decode()
+        assert n.value > 150 * 32768                                  # most codes are valid and were compared in full
