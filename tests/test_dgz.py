@@ -71,6 +71,9 @@ def test_stream_shapes(fastq):
     for i in range(0, len(fastq), 9973):
         parts += [co.compress(fastq[i:i + 9973]), co.flush(zlib.Z_SYNC_FLUSH)]
     shapes["sync_flush"] = b"".join(parts) + co.flush()
+    for name, strategy in (("huffman_only", zlib.Z_HUFFMAN_ONLY), ("rle", zlib.Z_RLE), ("filtered", zlib.Z_FILTERED)):
+        co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, strategy)            # no distance code at all / a single distance code
+        shapes[name] = co.compress(fastq) + co.flush()
     b = io.BytesIO()
     with gzip.GzipFile(filename="reads_R1.fastq", mode="wb", fileobj=b, mtime=1) as gz:
         gz.write(fastq)
