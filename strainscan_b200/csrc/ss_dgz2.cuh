@@ -378,7 +378,10 @@ SS_HD uint32_t dgz2_advance(dgz2_lane &L, const dgz2_job &J, dgz_ctables &t) {
     }
 }
 
-// table reads: 32-bit shared-memory addresses on the device (the generic form costs an address conversion per load)
+// table reads: 32-bit shared-memory addresses on the device (the generic form costs an address conversion per load).
+// The asm statements carry no memory clobber on purpose (a clobber would pin the symbol stores around them): every
+// address is computed from the bit buffer, which has moved on since the tables were last written, so no two
+// executions that straddle a table build share their operands, and nothing in the round loop writes the tables.
 #ifdef __CUDA_ARCH__
 #define DGZ2_TABLE(name, ptr) const uint32_t name = (uint32_t)__cvta_generic_to_shared(ptr)
 #define DGZ2_LD16(v, tab, idx) asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((tab) + ((idx) << 1)))
