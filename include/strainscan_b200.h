@@ -143,6 +143,15 @@ int ss_ingest_files_host(const char *const *paths, int n_paths, int shard, int n
 int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member, size_t stop_member_at,
                         uint32_t max_pieces, uint32_t piece_bytes, uint32_t sym_per_byte, char *out, size_t out_cap,
                         size_t *out_len, size_t *stopped_at, uint64_t *stats4);
+/* Host-only helper (no GPU needed): index lists of the non-zeros of a dense C-contiguous n0 x n1 array, on n_threads host
+ * threads (< 1: all the process may use).  The mirrors of the per-strain reducers (l2_shim: cal_cov_all, get_candidate_arr,
+ * get_remainc -- identify_strains_L2_Enet_Pscan_new_sp.py:44-49, 94-134) take the dense 0/1 matrices the reference builds
+ * (pX = X.A, :200-201) and need them as column lists for ss_strain_matrix_create.  elem_bytes-byte integers / bool
+ * (is_float = 0) or IEEE floats (is_float = 1, elem_bytes 4 or 8).  axis 0: n0 lists of axis-1 indices; axis 1: n1 lists
+ * of axis-0 indices, ascending.  Two calls: with idx == NULL, ptr[k + 1] receives the length of list k; the caller turns
+ * ptr into offsets (ptr[0] = 0, running sum) and calls again with idx of ptr[last] entries. */
+int ss_dense_nonzero_lists(const void *X, uint64_t n0, uint64_t n1, int elem_bytes, int is_float, int axis,
+                           int n_threads, uint64_t *ptr, uint32_t *idx);
 /* Host-only self-test (no GPU needed): the 16-bit Huffman decode tables of the device gzip decoder (ss_dgz2.cuh) against
  * the 32-bit tables of the host decoder (ss_inflate.cuh) on `trials` random prefix codes -- literal/length codes of
  * 257..286 symbols and distance codes of 1..30 symbols with lengths up to 15, the single-code and the empty distance

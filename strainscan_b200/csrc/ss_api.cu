@@ -1424,6 +1424,105 @@ extern "C" int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t fi
     return SS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host-only: index lists of the non-zeros of a dense 2-D array (the mirrors of the per-strain reducers take the dense
+// 0/1 strain matrices the reference builds -- pX = X.A, identify_strains_L2_Enet_Pscan_new_sp.py:200-201 -- and need
+// them as CSC; NumPy's flatnonzero, strain by strain, is one thread and was most of the mirrors' time)
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename T> inline bool dn_nonzero(const T *p, uint64_t i) { return p[i] != (T)0; }
+
+// lists along axis 0: list j = the axis-1 indices i with X[j][i] != 0
+template <typename T>
+void dn_axis0(const T *X, uint64_t n0, uint64_t n1, int n_threads, uint64_t *ptr, uint32_t *idx) {
+    std::vector<std::thread> th;
+    std::atomic<uint64_t> next{0};
+    auto work = [&]() {
+        for (uint64_t j; (j = next.fetch_add(1)) < n0;) {
+            const T *row = X + j * n1;
+            if (!idx) {
+                uint64_t c = 0;
+                for (uint64_t i = 0; i < n1; i++) c += dn_nonzero(row, i) ? 1u : 0u;
+                ptr[j + 1] = c;
+            } else {
+                uint32_t *out = idx + ptr[j];
+                for (uint64_t i = 0; i < n1; i++) if (dn_nonzero(row, i)) *out++ = (uint32_t)i;
+            }
+        }
+    };
+    for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+// lists along axis 1: list s = the axis-0 indices r with X[r][s] != 0, ascending (blocks of rows per thread, in order)
+template <typename T>
+void dn_axis1(const T *X, uint64_t n0, uint64_t n1, int n_threads, uint64_t *ptr, uint32_t *idx) {
+    const uint64_t T_ = (uint64_t)std::max(1, n_threads);
+    std::vector<std::vector<uint64_t>> cnt(T_, std::vector<uint64_t>(n1, 0));
+    auto block = [&](uint64_t t, uint64_t &lo, uint64_t &hi) { lo = n0 * t / T_; hi = n0 * (t + 1) / T_; };
+    {
+        std::vector<std::thread> th;
+        auto work = [&](uint64_t t) {
+            uint64_t lo, hi; block(t, lo, hi);
+            uint64_t *c = cnt[t].data();
+            for (uint64_t r = lo; r < hi; r++) { const T *row = X + r * n1; for (uint64_t s2 = 0; s2 < n1; s2++) c[s2] += dn_nonzero(row, s2) ? 1u : 0u; }
+        };
+        for (uint64_t t = 1; t < T_; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    if (!idx) {
+        for (uint64_t s2 = 0; s2 < n1; s2++) { uint64_t c = 0; for (uint64_t t = 0; t < T_; t++) c += cnt[t][s2]; ptr[s2 + 1] = c; }
+        return;
+    }
+    // where each thread's block starts inside every list
+    for (uint64_t s2 = 0; s2 < n1; s2++) { uint64_t at = ptr[s2]; for (uint64_t t = 0; t < T_; t++) { const uint64_t c = cnt[t][s2]; cnt[t][s2] = at; at += c; } }
+    std::vector<std::thread> th;
+    auto work = [&](uint64_t t) {
+        uint64_t lo, hi; block(t, lo, hi);
+        uint64_t *at = cnt[t].data();
+        for (uint64_t r = lo; r < hi; r++) { const T *row = X + r * n1; for (uint64_t s2 = 0; s2 < n1; s2++) if (dn_nonzero(row, s2)) idx[at[s2]++] = (uint32_t)r; }
+    };
+    for (uint64_t t = 1; t < T_; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+}
+
+template <typename T>
+void dn_run(const void *X, uint64_t n0, uint64_t n1, int axis, int n_threads, uint64_t *ptr, uint32_t *idx) {
+    if (axis == 0) dn_axis0((const T *)X, n0, n1, n_threads, ptr, idx);
+    else dn_axis1((const T *)X, n0, n1, n_threads, ptr, idx);
+}
+}   // namespace
+
+// X: C-contiguous n0 x n1 array of `elem_bytes`-byte integers (is_float = 0; bool counts) or IEEE floats (is_float = 1).
+// axis 0: n0 lists of axis-1 indices; axis 1: n1 lists of axis-0 indices (ascending).  Call with idx == NULL first: ptr[k + 1]
+// receives the length of list k (ptr[0] untouched); turn ptr into offsets and call again with idx of ptr[last] entries.
+extern "C" int ss_dense_nonzero_lists(const void *X, uint64_t n0, uint64_t n1, int elem_bytes, int is_float, int axis,
+                                      int n_threads, uint64_t *ptr, uint32_t *idx) {
+    if ((!X && n0 && n1) || !ptr || (axis != 0 && axis != 1)) return fail(SS_ERR_ARG, "ss_dense_nonzero_lists: bad argument");
+    if ((axis == 0 ? n1 : n0) > 0xFFFFFFFFull) return fail(SS_ERR_ARG, "ss_dense_nonzero_lists: more than 2^32 entries along the indexed axis");
+    if (n_threads < 1) {
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        n_threads = std::max(1, std::min(n_threads, 32));
+    }
+    if (n0 == 0 || n1 == 0) { if (!idx) for (uint64_t k = 0; k < (axis == 0 ? n0 : n1); k++) ptr[k + 1] = 0; return SS_OK; }
+    if (is_float) {
+        if (elem_bytes == 4) dn_run<float>(X, n0, n1, axis, n_threads, ptr, idx);
+        else if (elem_bytes == 8) dn_run<double>(X, n0, n1, axis, n_threads, ptr, idx);
+        else return fail(SS_ERR_ARG, "ss_dense_nonzero_lists: float element size must be 4 or 8");
+    } else {
+        if (elem_bytes == 1) dn_run<uint8_t>(X, n0, n1, axis, n_threads, ptr, idx);
+        else if (elem_bytes == 2) dn_run<uint16_t>(X, n0, n1, axis, n_threads, ptr, idx);
+        else if (elem_bytes == 4) dn_run<uint32_t>(X, n0, n1, axis, n_threads, ptr, idx);
+        else if (elem_bytes == 8) dn_run<uint64_t>(X, n0, n1, axis, n_threads, ptr, idx);
+        else return fail(SS_ERR_ARG, "ss_dense_nonzero_lists: integer element size must be 1, 2, 4 or 8");
+    }
+    return SS_OK;
+}
+
 // host-only: the two decode-table forms against each other on random prefix codes
 extern "C" int ss_dgz_tables_selftest_host(uint64_t seed, uint32_t trials, uint64_t *n_checked) {
     std::string err;

@@ -75,11 +75,11 @@ class StrainMatrix:
         if _csc is not None:
             self.n_rows, self.n_strains, self.col_ptr, self.rows = _csc
         elif isinstance(X, np.ndarray):
-            # the dense rows x strains array detect_strains builds (pX = X.A): one pass to a strains x rows bool array,
-            # then the row indices strain by strain (scipy's dense -> CSC conversion is several times slower)
+            # the dense rows x strains array detect_strains builds (pX = X.A): the rows of every strain, read in place
+            # (scipy's dense -> CSC conversion is several times slower)
             if X.ndim != 2:
                 raise ValueError("StrainMatrix: a 2-D matrix is expected, got shape %r" % (X.shape,))
-            self.n_rows, self.n_strains, self.col_ptr, self.rows = _csc_of_strains_by_rows(np.ascontiguousarray(X.T != 0))
+            self.n_rows, self.n_strains, self.col_ptr, self.rows = _csc_of_rows_by_strains(X)
         else:
             import scipy.sparse as sp
             X = sp.csc_matrix(X)
@@ -121,14 +121,47 @@ class StrainMatrix:
             pass
 
 
+def _nonzero_lists(X, axis):
+    """(ptr, idx): the index lists of the non-zeros of a dense 2-D array -- axis 0: one list per X[j] holding the
+    positions i with X[j, i] != 0; axis 1: one list per column holding the rows, ascending.  C- and F-contiguous arrays
+    of bool / integer / float32 / float64 go through the threaded host helper ss_dense_nonzero_lists (NumPy's
+    flatnonzero, list by list on one thread, was most of the dense mirrors' time); anything else through NumPy."""
+    n_lists = X.shape[axis]
+    if X.dtype.kind in "biuf" and X.dtype.itemsize in (1, 2, 4, 8) and not (X.dtype.kind == "f" and X.dtype.itemsize < 4) \
+            and X.dtype.isnative and (X.flags.c_contiguous or X.flags.f_contiguous) and X.size:
+        from . import _lib
+        lib = _lib.load()
+        if X.flags.c_contiguous:
+            A, ax = X, axis
+        else:                                  # the same memory read as the C-contiguous transpose
+            A, ax = X.T, 1 - axis
+        if A.shape[1 - ax] < 2 ** 32:
+            ptr = np.zeros(n_lists + 1, dtype=np.uint64)
+            args = (A.ctypes.data, A.shape[0], A.shape[1], A.dtype.itemsize, int(A.dtype.kind == "f"), ax, 0)
+            _lib.check(lib.ss_dense_nonzero_lists(*args, ptr.ctypes.data, None))
+            np.cumsum(ptr, out=ptr)
+            idx = np.empty(int(ptr[-1]), dtype=np.uint32)
+            _lib.check(lib.ss_dense_nonzero_lists(*args, ptr.ctypes.data, idx.ctypes.data if idx.size else None))
+            return ptr, idx
+    lists = [np.flatnonzero(X[j] if axis == 0 else X[:, j]).astype(np.uint32) for j in range(n_lists)]
+    ptr = np.zeros(n_lists + 1, dtype=np.uint64)
+    if n_lists:
+        ptr[1:] = np.cumsum([p.size for p in lists])
+    idx = np.concatenate(lists) if lists else np.zeros(0, dtype=np.uint32)
+    return ptr, idx
+
+
 def _csc_of_strains_by_rows(Xt):
-    """(n_rows, n_strains, col_ptr, rows) of a dense STRAINS x ROWS array (any dtype): np.flatnonzero row by row."""
+    """(n_rows, n_strains, col_ptr, rows) of a dense STRAINS x ROWS array: the rows of every strain."""
     S, R = Xt.shape
-    parts = [np.flatnonzero(Xt[j]).astype(np.uint32) for j in range(S)]
-    col_ptr = np.zeros(S + 1, dtype=np.uint64)
-    if S:
-        col_ptr[1:] = np.cumsum([p.size for p in parts])
-    rows = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
+    col_ptr, rows = _nonzero_lists(Xt, 0)
+    return R, S, col_ptr, rows
+
+
+def _csc_of_rows_by_strains(X):
+    """(n_rows, n_strains, col_ptr, rows) of a dense ROWS x STRAINS array (no transposed copy is made)."""
+    R, S = X.shape
+    col_ptr, rows = _nonzero_lists(X, 1)
     return R, S, col_ptr, rows
 
 

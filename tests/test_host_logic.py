@@ -238,3 +238,40 @@ def test_kid_row_order_is_one_rule():
     assert f(np.array([2, 3, 4, 5], dtype=np.uint64)) is None                # not 1..n
     assert f(np.array([0, 1, 2, 3], dtype=np.uint64)) is None
     assert f(np.array([3, 1, 4, 2], dtype=np.uint64)).tolist() == [1, 3, 0, 2]
+
+
+def test_dense_matrices_become_column_lists_like_numpy_says():
+    """l2_shim._nonzero_lists (threaded host helper ss_dense_nonzero_lists behind the dense forms of cal_cov_all /
+    get_candidate_arr / get_remainc) against np.flatnonzero: every dtype the reference's matrices come in, C / F /
+    strided layouts, both orientations, empty shapes, -0.0 and NaN."""
+    from strainscan_b200 import l2_shim
+    rng = np.random.default_rng(0)
+
+    def by_numpy(X, axis):
+        n = X.shape[axis]
+        lists = [np.flatnonzero(X[j] if axis == 0 else X[:, j]).astype(np.uint32) for j in range(n)]
+        ptr = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            ptr[1:] = np.cumsum([x.size for x in lists])
+        return ptr, (np.concatenate(lists) if lists else np.zeros(0, np.uint32))
+
+    for dt in (np.bool_, np.int8, np.uint8, np.int16, np.int32, np.int64, np.uint64, np.float32, np.float64, np.float16):
+        for shape in ((1, 1), (3, 1000), (1000, 3), (64, 5000), (257, 33), (0, 5), (5, 0)):
+            X = (rng.random(shape) < 0.1).astype(dt)
+            if np.dtype(dt).kind == "f" and X.size:
+                X.flat[0] = -0.0
+                X.flat[-1] = np.nan
+            if np.dtype(dt).kind == "i" and X.size:
+                X[X != 0] = -1
+            for arr in (X, np.asfortranarray(X), X[:, ::2] if shape[1] > 1 else X, X.T):
+                for axis in (0, 1):
+                    ptr, idx = l2_shim._nonzero_lists(arr, axis)
+                    rp, ri = by_numpy(arr, axis)
+                    assert np.array_equal(ptr, rp) and np.array_equal(idx, ri), (dt, shape, axis)
+    # the two orientations of one matrix give the same CSC
+    Xt = (rng.random((9, 20_000)) < 0.3).astype(np.int64)
+    a = l2_shim._csc_of_strains_by_rows(Xt)
+    b = l2_shim._csc_of_rows_by_strains(np.ascontiguousarray(Xt.T))
+    c = l2_shim._csc_of_rows_by_strains(Xt.T)
+    assert a[:2] == b[:2] == c[:2] == (20_000, 9)
+    assert all(np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]) for k in (2, 3))
