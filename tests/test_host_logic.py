@@ -275,3 +275,53 @@ def test_dense_matrices_become_column_lists_like_numpy_says():
     c = l2_shim._csc_of_rows_by_strains(Xt.T)
     assert a[:2] == b[:2] == c[:2] == (20_000, 9)
     assert all(np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]) for k in (2, 3))
+
+
+class _NumpyStrainEngine:
+    """Stand-in for Engine's strain-matrix handle (K5 on the GPU): the same three sums in NumPy, so that the host side
+    of the dense mirrors -- orientation checks, dense -> column lists, masks, ratios -- runs without a GPU."""
+
+    def strain_matrix_create(self, col_ptr, rows, n_rows):
+        return (np.asarray(col_ptr).copy(), np.asarray(rows).copy(), int(n_rows))
+
+    def strain_matrix_free(self, handle):
+        pass
+
+    def strain_matrix_reduce(self, handle, y, row_mask=None):
+        col_ptr, rows, n_rows = handle
+        y = np.asarray(y, dtype=np.int64)
+        assert y.size == n_rows
+        S = col_ptr.size - 1
+        total, covered, ssum = (np.zeros(S, dtype=np.uint64) for _ in range(3))
+        for j in range(S):
+            r = rows[int(col_ptr[j]):int(col_ptr[j + 1])].astype(np.int64)
+            if row_mask is not None:
+                r = r[np.asarray(row_mask)[r] != 0]
+            total[j] = r.size
+            hit = y[r] > 1
+            covered[j] = int(hit.sum())
+            ssum[j] = int(y[r][hit].sum())
+        return total, covered, ssum
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.int8, np.float64, np.bool_])
+def test_dense_mirrors_equal_the_reference_restatements_without_a_gpu(dtype):
+    """cal_cov_all / get_candidate_arr / get_remainc of l2_shim on the dense matrices the reference hands them
+    (identify_strains_L2_Enet_Pscan_new_sp.py:241-334), every layout, against oracle/adapters.py's restatements."""
+    from strainscan_b200 import l2_shim
+    rng = np.random.default_rng(3)
+    eng = _NumpyStrainEngine()
+    n, S = 3000, 11
+    pX = (rng.random((n, S)) < 0.2).astype(dtype)                       # rows x strains, as pX = X.A
+    y = (rng.poisson(3, n) * (rng.random(n) < 0.7)).astype(np.int64)
+    used = (rng.random(n) < 0.3).astype(np.int64)
+    want_cov = [0 if t == 0 else c / t for c, t in adapters.stat_cov_all(pX, y)]
+    for ix in (pX, np.asfortranarray(pX), pX.T.copy().T):
+        assert l2_shim.cal_cov_all(ix, y, engine=eng) == want_cov
+    cand = adapters.candidate_counts(pX, y)
+    best = int(np.argmax(cand))
+    for ixt in (pX.T, np.ascontiguousarray(pX.T)):
+        assert l2_shim.get_candidate_arr(ixt, y, engine=eng) == (best, cand[best])
+    want = {i: (0 if a == 0 else c / a) for i, (c, a) in enumerate(adapters.remain_cov(used, pX, y)) if i != 2}
+    for ixt in (pX.T, np.ascontiguousarray(pX.T)):
+        assert l2_shim.get_remainc(2, used, ixt, y, {}, engine=eng) == want
