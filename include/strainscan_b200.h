@@ -152,6 +152,14 @@ int ss_dgz_inflate_host(const char *comp, size_t comp_size, size_t first_member,
  * ptr into offsets (ptr[0] = 0, running sum) and calls again with idx of ptr[last] entries. */
 int ss_dense_nonzero_lists(const void *X, uint64_t n0, uint64_t n1, int elem_bytes, int is_float, int axis,
                            int n_threads, uint64_t *ptr, uint32_t *idx);
+/* Host-only helper (no GPU needed): the k-mer lists of n tree nodes (Tree_database/kmers/<node>, one line of record
+ * ordinals separated by single spaces; identify.py:115-119 reads it with list(map(int, line.rstrip().split(" "))) and
+ * makes a set of it) parsed and de-duplicated on n_threads host threads (< 1: all the process may use).  ptr[n + 1] =
+ * offsets into out, every list ascending; status[i]: 0 parsed, 1 empty file (the reference's "lines == []" case),
+ * 2 not of that exact shape (signs, other separators, values over 2^32 - 1: left to the caller's slow parser, which has
+ * the reference's semantics), 3 unreadable.  out_cap: half the total size of the files is always enough. */
+int ss_node_lists_parse(const char *const *paths, uint32_t n, int n_threads, uint64_t *ptr, uint32_t *out,
+                        uint64_t out_cap, uint8_t *status);
 /* Host-only self-test (no GPU needed): the 16-bit Huffman decode tables of the device gzip decoder (ss_dgz2.cuh) against
  * the 32-bit tables of the host decoder (ss_inflate.cuh) on `trials` random prefix codes -- literal/length codes of
  * 257..286 symbols and distance codes of 1..30 symbols with lengths up to 15, the single-code and the empty distance

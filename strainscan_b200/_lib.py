@@ -75,6 +75,7 @@ SIGNATURES = {
     "ss_dgz_inflate_host": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, _P,
                                       C.c_size_t, _SIZES, _SIZES, C.POINTER(C.c_uint64)]),
     "ss_dense_nonzero_lists": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "ss_node_lists_parse": (C.c_int, [_CSTRS, C.c_uint32, C.c_int, _P, _P, C.c_uint64, _P]),
     "ss_dgz_plan_host": (C.c_int, [C.c_size_t, C.c_int, C.c_double, C.POINTER(C.c_uint64)]),
     "ss_dgz_tables_selftest_host": (C.c_int, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "ss_reads_from_host": (C.c_int, [_P, _CSTRS, _SIZES, C.c_int, _PP]),

@@ -1523,6 +1523,81 @@ extern "C" int ss_dense_nonzero_lists(const void *X, uint64_t n0, uint64_t n1, i
     return SS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host-only: the k-mer lists of many tree nodes (Tree_database/kmers/<node>: one line of record ordinals separated by
+// single spaces, read by identify.py:118 as list(map(int, line.rstrip().split(" "))) and turned into a set) parsed and
+// de-duplicated on all host threads.  A file that is not exactly that shape is reported, not guessed at: the caller
+// parses it the slow way with the reference's own semantics.
+// ---------------------------------------------------------------------------------------------
+enum { SS_NODE_LIST_OK = 0, SS_NODE_LIST_EMPTY = 1, SS_NODE_LIST_UNUSUAL = 2, SS_NODE_LIST_UNREADABLE = 3 };
+
+static int parse_node_list(const char *path, std::vector<uint32_t> &out) {
+    out.clear();
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return SS_NODE_LIST_UNREADABLE;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return SS_NODE_LIST_UNREADABLE; }
+    const size_t size = (size_t)st.st_size;
+    if (size == 0) { close(fd); return SS_NODE_LIST_EMPTY; }
+    std::vector<char> buf(size);
+    for (size_t have = 0; have < size;) {
+        ssize_t got = pread(fd, buf.data() + have, size - have, (off_t)have);
+        if (got <= 0) { close(fd); return SS_NODE_LIST_UNREADABLE; }
+        have += (size_t)got;
+    }
+    close(fd);
+    size_t end = 0;
+    while (end < size && buf[end] != '\n') end++;                    // lines[0]
+    while (end > 0 && (buf[end - 1] == ' ' || buf[end - 1] == '\r' || buf[end - 1] == '\t' || buf[end - 1] == '\f' || buf[end - 1] == '\v')) end--;   // rstrip()
+    if (end == 0) return SS_NODE_LIST_UNUSUAL;                        // int('') raises in the reference
+    out.reserve(end / 6 + 1);
+    size_t i = 0;
+    while (i < end) {
+        uint64_t v = 0;
+        size_t digits = 0;
+        while (i < end && buf[i] >= '0' && buf[i] <= '9') { v = v * 10u + (uint64_t)(buf[i] - '0'); i++; digits++; if (digits > 10) return SS_NODE_LIST_UNUSUAL; }
+        if (digits == 0 || v > 0xFFFFFFFFull) return SS_NODE_LIST_UNUSUAL;      // sign, other characters, two spaces, too large
+        out.push_back((uint32_t)v);
+        if (i < end) { if (buf[i] != ' ') return SS_NODE_LIST_UNUSUAL; i++; if (i == end) return SS_NODE_LIST_UNUSUAL; }
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return SS_NODE_LIST_OK;
+}
+
+// paths[n] -> ptr[n + 1] (offsets into out), out[<= out_cap] (every list ascending, duplicates removed), status[n]
+// (SS_NODE_LIST_*; lists with a status other than OK are empty).  out_cap: half the files' total size is always enough.
+extern "C" int ss_node_lists_parse(const char *const *paths, uint32_t n, int n_threads, uint64_t *ptr, uint32_t *out,
+                                   uint64_t out_cap, uint8_t *status) {
+    if ((n && (!paths || !status)) || !ptr || (!out && out_cap)) return fail(SS_ERR_ARG, "ss_node_lists_parse: NULL argument");
+    if (n_threads < 1) {
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+        n_threads = std::max(1, std::min(n_threads, 32));
+    }
+    std::vector<std::vector<uint32_t>> lists(n);
+    {
+        std::atomic<uint32_t> next{0};
+        auto work = [&]() { for (uint32_t i; (i = next.fetch_add(1)) < n;) status[i] = (uint8_t)parse_node_list(paths[i], lists[i]); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+    }
+    ptr[0] = 0;
+    for (uint32_t i = 0; i < n; i++) ptr[i + 1] = ptr[i] + lists[i].size();
+    if (ptr[n] > out_cap) return fail(SS_ERR_ARG, "ss_node_lists_parse: output buffer too small");
+    {
+        std::atomic<uint32_t> next{0};
+        auto work = [&]() { for (uint32_t i; (i = next.fetch_add(1)) < n;) if (!lists[i].empty()) memcpy(out + ptr[i], lists[i].data(), lists[i].size() * sizeof(uint32_t)); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+    }
+    return SS_OK;
+}
+
 // host-only: the two decode-table forms against each other on random prefix codes
 extern "C" int ss_dgz_tables_selftest_host(uint64_t seed, uint32_t trials, uint64_t *n_checked) {
     std::string err;

@@ -230,6 +230,36 @@ def _node_ordinals(db_dir, node_id):
     return cache[nid]
 
 
+def _prefetch_node_lists(db_dir, node_ids):
+    """Fill the node cache for many nodes at once: the list files parsed and de-duplicated on all host threads
+    (ss_node_lists_parse).  Files that are not plain single-space separated ordinals, and unreadable ones, are left to
+    _node_ordinals, which has the reference's semantics (and its errors)."""
+    _, cache = _node_cache(db_dir)
+    todo = [str(n) for n in node_ids if str(n) not in cache]
+    if len(todo) < 4:
+        return
+    from . import _lib
+    import ctypes as C
+    paths = [os.path.join(db_dir, "kmers", n) for n in todo]
+    total = 0
+    for p in paths:
+        try:
+            total += os.path.getsize(p)
+        except OSError:
+            pass
+    lib = _lib.load()
+    ptr = np.zeros(len(todo) + 1, dtype=np.uint64)
+    out = np.empty(total // 2 + 1, dtype=np.uint32)
+    status = np.zeros(len(todo), dtype=np.uint8)
+    arr = (C.c_char_p * len(todo))(*[p.encode() for p in paths])
+    _lib.check(lib.ss_node_lists_parse(arr, len(todo), 0, ptr.ctypes.data, out.ctypes.data, out.size, status.ctypes.data))
+    for i, nid in enumerate(todo):
+        if status[i] == 0:
+            cache[nid] = out[int(ptr[i]):int(ptr[i + 1])].astype(np.int64)
+        elif status[i] == 1:
+            cache[nid] = None
+
+
 def _profile(match_results, d):
     d = d[(d >= 0) & (d < match_results.counts.size)]
     valid = d[match_results.valid_mask[d]]
@@ -302,6 +332,7 @@ def node_coverage_all(match_results, db_dir, node_ids, min_valid=1000):
                 ln, prof = match_node_low_depth(match_results, db_dir, nid)
                 out[nid] = -1 if ln == 0 else len(prof) / ln
         return out
+    _prefetch_node_lists(db_dir, node_ids)
     for nid in node_ids:
         length, prof = match_node_low_depth(match_results, db_dir, nid) if min_valid else match_node(match_results, db_dir, nid)
         out[nid] = -1 if length == 0 else len(prof) / length
@@ -312,6 +343,7 @@ def load_node_csr(db_dir, node_ids):
     """kmers/<node> files -> CSR (ptr uint64[n+1], ordinals uint32[nnz]), lists de-duplicated."""
     ptr = np.zeros(len(node_ids) + 1, dtype=np.uint64)
     parts = []
+    _prefetch_node_lists(db_dir, node_ids)
     for i, nid in enumerate(node_ids):
         d = _node_ordinals(db_dir, nid)
         if d is None:

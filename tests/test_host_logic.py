@@ -325,3 +325,41 @@ def test_dense_mirrors_equal_the_reference_restatements_without_a_gpu(dtype):
     want = {i: (0 if a == 0 else c / a) for i, (c, a) in enumerate(adapters.remain_cov(used, pX, y)) if i != 2}
     for ixt in (pX.T, np.ascontiguousarray(pX.T)):
         assert l2_shim.get_remainc(2, used, ixt, y, {}, engine=eng) == want
+
+
+def test_node_lists_parsed_in_bulk_equal_the_one_by_one_parser(tmp_path, monkeypatch):
+    """identify_shim.load_node_csr: the kmers/<node> files through the threaded host parser (ss_node_lists_parse) and
+    through the one-file-at-a-time NumPy parser give the same cache and the same CSR -- plain lists with and without the
+    trailing blank, duplicates, an empty file, and the shapes the fast parser must leave alone (a sign, two blanks, a
+    value over 2^32, a second line)."""
+    rng = np.random.default_rng(4)
+    db = tmp_path / "Tree_database"
+    (db / "kmers").mkdir(parents=True)
+    lists = {}
+    for v in range(40):
+        a = rng.integers(0, 5_000_000, int(rng.integers(1, 3000)))
+        if v % 5 == 0:
+            a = np.concatenate([a, a[:20]])
+        lists[str(v)] = a
+        (db / "kmers" / str(v)).write_text(" ".join(map(str, a.tolist())) + (" \n" if v % 2 else "\n"))
+    (db / "kmers" / "empty").write_text("")
+    odd = {"sign": "5 -3 7\n", "blanks": "5  7\n", "big": "5 99999999999 7\n", "lines": "9 8 7\n1 2 3\n", "cr": "4 2 4\r\n"}
+    for name, text in odd.items():
+        (db / "kmers" / name).write_text(text)
+    ids = list(lists) + ["empty", "sign", "big", "lines", "cr"]
+    identify_shim._NODES.clear()
+    ptr, ords = identify_shim.load_node_csr(str(db), ids)
+    _, cache = identify_shim._node_cache(str(db))
+    fast = {k: (None if v is None else v.copy()) for k, v in cache.items()}
+    identify_shim._NODES.clear()
+    monkeypatch.setattr(identify_shim, "_prefetch_node_lists", lambda *a: None)
+    ptr2, ords2 = identify_shim.load_node_csr(str(db), ids)
+    _, slow = identify_shim._node_cache(str(db))
+    assert np.array_equal(ptr, ptr2) and np.array_equal(ords, ords2)
+    assert set(fast) == set(slow)
+    for k in slow:
+        assert (fast[k] is None and slow[k] is None) or (fast[k].dtype == slow[k].dtype and np.array_equal(fast[k], slow[k])), k
+    for k, a in lists.items():
+        assert np.array_equal(slow[k], np.unique(a))
+    assert slow["empty"] is None and slow["lines"].tolist() == [7, 8, 9] and slow["cr"].tolist() == [2, 4]
+    identify_shim._NODES.clear()
