@@ -295,7 +295,7 @@ ss_dgz_plan ss_dgz_make_plan(size_t n_up, int n_sm, ss_dgz_shape shape, double r
     if (const char *e = getenv("SS_DGZ_SYM_PER_BYTE")) { int v = atoi(e); if (v >= 1 && v <= 64) pl.expand = (uint32_t)v; }
     // piece size: a wave's text (1.3 x the head's ratio per compressed byte, at least what 3.5 would give) fits the batch buffer
     const double per_byte = 1.3 * std::max(3.5, pl.ratio);
-    const double p_max = std::max(16384.0, std::min<double>(128u << 10, std::floor((double)pl.scratch / ((double)wave * per_byte) / 4096.0) * 4096.0));
+    const double p_max = std::max(16384.0, std::min<double>(SS_DGZ_PIECE_DEFAULT, std::floor((double)pl.scratch / ((double)wave * per_byte) / 4096.0) * 4096.0));
     const double waves = std::max(1.0, std::ceil((double)n_up / ((double)wave * p_max)));
     double fit = std::ceil((double)n_up / (waves * wave) / 256.0) * 256.0;
     if (fit > p_max) fit = p_max;

@@ -20,8 +20,8 @@
 #include "ss_inflate.cuh"
 
 #define SS_DGZ_WINDOW 32768u
-#define SS_DGZ_PIECE_DEFAULT (256u << 10)  // compressed bytes per piece (SS_DGZ_PIECE_BYTES)
-#define SS_DGZ_EXPAND_DEFAULT 5u          // symbols a piece may produce per compressed byte of its nominal size
+#define SS_DGZ_PIECE_DEFAULT (128u << 10)  // compressed bytes per piece at most (ss_dgz_make_plan; SS_DGZ_PIECE_BYTES)
+#define SS_DGZ_EXPAND_DEFAULT 5u          // symbols a piece may produce per compressed byte of its nominal size, at least (ss_dgz_make_plan)
 
 enum {
     SS_DGZ_LINKED = 0,      // stopped exactly on a later piece's start (dgz_piece::next) or on the batch limit
